@@ -1,0 +1,872 @@
+// gpb_core.cu -- host side of libgprmax_b200.so: the C ABI declared in include/gprmax_b200.h.
+//
+// Replaces the reference's solve_gpu driver (gprMax/model_build_run.py:477-716) and the PyCUDA
+// helpers it calls (grid.py:247-272, pml.py:298-364, receivers.py:45-88, sources.py:235-283,
+// snapshots.py:170-228, utilities.py:341-413).  No CPU fallback: every entry point that computes
+// needs a CUDA device and reports an error otherwise.
+#include "../../include/gprmax_b200.h"
+#include "gpb_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace gpb;
+
+static thread_local std::string g_err;
+
+static int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------------
+struct SolverBase {
+    virtual ~SolverBase() {}
+    virtual int run(int n) = 0;
+    virtual int half_step(int phase) = 0;
+    virtual int reset() = 0;
+    virtual int get_receivers(void *out, size_t bytes) = 0;
+    virtual int get_snapshot(int idx, void *out6[6], size_t bytes_each) = 0;
+    virtual int get_tline(int idx, void *v, void *i, size_t bytes_each) = 0;
+    virtual int get_field(int comp, void *out, size_t bytes) = 0;
+    virtual int set_field(int comp, const void *in, size_t bytes) = 0;
+    virtual int halo(int which, void **a, void **b, size_t *bytes) = 0;
+    virtual int profile(int n, double *ms4) = 0;
+    int device = 0;
+    int iteration = 0;
+    double elapsed = 0;
+    uint64_t mem = 0;
+    uint64_t launches = 0;
+    cudaStream_t stream = nullptr;
+};
+
+struct gpb_solver {
+    SolverBase *impl;
+};
+
+template <typename R>
+struct Solver : SolverBase {
+    // model
+    int nx, ny, nz, x_start, nplanes, pitch, iterations, nmat, maxpoles, form, order;
+    long long plane, narr;  // elements per plane / per padded array (nplanes+2 planes)
+    int idbytes;
+    bool tabsmem;
+    size_t smem_bytes;
+    // device memory
+    std::vector<void *> allocs;
+    R *F[6] = {0, 0, 0, 0, 0, 0};
+    void *ID[6] = {0, 0, 0, 0, 0, 0};
+    Coef4<R> *coefE = 0, *coefH = 0;
+    R *srcE = 0, *srcH = 0;
+    Cplx<R> *T[3] = {0, 0, 0};
+    Cplx<R> *dcoef = 0;
+    int *d_iter = 0;  // [0] current, [1] next
+    // receivers / sources / snapshots
+    int nrx = 0;
+    int *d_rxc = 0;
+    R *d_rxs = 0;
+    int nsrc = 0, ntl = 0;
+    SrcDev<R> *d_srcs = 0;
+    TLDev<R> *d_tls = 0;
+    std::vector<TLDev<R>> h_tls;
+    std::vector<std::vector<R>> tl_v0, tl_c0;
+    std::vector<R> tl_abc0;
+    bool has_hsrc = false, has_esrc = false;
+    std::vector<gpb_snapshot_t> snaps;
+    std::vector<SnapDev<R>> snapdev;
+    // phases
+    PhaseParams<R> ph_h, ph_e;
+    PointParams<R> pp;
+    std::vector<std::pair<R *, size_t>> phis;
+    // graph
+    cudaGraphExec_t graph = nullptr;
+    bool use_graph = true;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    ~Solver()
+    {
+        cudaSetDevice(device);
+        if (graph) cudaGraphExecDestroy(graph);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (void *p : allocs) cudaFree(p);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    template <typename T_>
+    int dalloc(T_ **p, size_t n, bool zero = true)
+    {
+        void *q = nullptr;
+        size_t bytes = std::max<size_t>(n, 1) * sizeof(T_);
+        CK(cudaMalloc(&q, bytes));
+        allocs.push_back(q);
+        mem += bytes;
+        if (zero) CK(cudaMemsetAsync(q, 0, bytes, stream));
+        *p = (T_ *)q;
+        return 0;
+    }
+    template <typename T_>
+    int upload(T_ **p, const T_ *h, size_t n)
+    {
+        if (dalloc(p, n, false)) return 1;
+        if (n) CK(cudaMemcpyAsync(*p, h, n * sizeof(T_), cudaMemcpyHostToDevice, stream));
+        return 0;
+    }
+
+    int upload_ids(const gpb_model_t &m);
+    int build(const gpb_model_t &m);
+    int setup_pml(const gpb_model_t &m);
+    int setup_points(const gpb_model_t &m);
+    void set_boxes();
+
+    template <typename IDT>
+    int launch_h(int p0, int p1);
+    template <typename IDT>
+    int launch_e(int p0, int p1);
+    int launch_phase(int phase, int p0, int p1);
+    int launch_sources(int phase);
+    int launch_begin();
+    int launch_snapshots();
+    int enqueue_step(bool with_snap);
+    bool snapshot_due(int it) const
+    {
+        for (auto &s : snaps)
+            if (s.time == it + 1) return true;
+        return false;
+    }
+
+    int run(int n) override;
+    int half_step(int phase) override;
+    int reset() override;
+    int get_receivers(void *out, size_t bytes) override;
+    int get_snapshot(int idx, void *out6[6], size_t bytes_each) override;
+    int get_tline(int idx, void *v, void *i, size_t bytes_each) override;
+    int get_field(int comp, void *out, size_t bytes) override;
+    int set_field(int comp, const void *in, size_t bytes) override;
+    int halo(int which, void **a, void **b, size_t *bytes) override;
+    int profile(int n, double *ms4) override;
+};
+
+static int choose_pitch(int nzp1)
+{
+    // rows start on a 128-byte line when the row is long enough to make that worthwhile
+    if (nzp1 >= 48) return (nzp1 + 31) / 32 * 32;
+    return (nzp1 + 7) / 8 * 8;
+}
+
+template <typename R>
+int Solver<R>::upload_ids(const gpb_model_t &m)
+{
+    // stage uint32 planes through a bounded device buffer and narrow on the device
+    const long long rows_per_plane = ny + 1;
+    const long long plane_src = rows_per_plane * (nz + 1);
+    const int chunk_planes = (int)std::max<long long>(1, std::min<long long>(nplanes, (256ll << 20) / (plane_src * 4)));
+    uint32_t *stage = nullptr;
+    unsigned *d_max = nullptr;
+    CK(cudaMalloc(&stage, (size_t)chunk_planes * plane_src * 4));
+    CK(cudaMalloc(&d_max, sizeof(unsigned)));
+    CK(cudaMemsetAsync(d_max, 0, sizeof(unsigned), stream));
+    for (int c = 0; c < 6; ++c) {
+        void *dst = nullptr;
+        size_t bytes = (size_t)narr * idbytes;
+        CK(cudaMalloc(&dst, bytes));
+        allocs.push_back(dst);
+        mem += bytes;
+        CK(cudaMemsetAsync(dst, 0, bytes, stream));
+        ID[c] = dst;
+        for (int p0 = 0; p0 < nplanes; p0 += chunk_planes) {
+            const int np = std::min(chunk_planes, nplanes - p0);
+            const uint32_t *src = m.ID + ((size_t)c * nplanes + p0) * plane_src;
+            CK(cudaMemcpyAsync(stage, src, (size_t)np * plane_src * 4, cudaMemcpyHostToDevice, stream));
+            const long long rows = (long long)np * rows_per_plane;
+            const long long n = rows * (nz + 1);
+            const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+            char *d = (char *)dst + (size_t)(p0 + 1) * plane * idbytes;
+            if (idbytes == 1) k_narrow_ids<uint8_t><<<blocks, 256, 0, stream>>>(stage, (uint8_t *)d, rows, nz + 1, pitch, d_max);
+            else if (idbytes == 2) k_narrow_ids<uint16_t><<<blocks, 256, 0, stream>>>(stage, (uint16_t *)d, rows, nz + 1, pitch, d_max);
+            else k_narrow_ids<uint32_t><<<blocks, 256, 0, stream>>>(stage, (uint32_t *)d, rows, nz + 1, pitch, d_max);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(stream));  // stage buffer is reused
+        }
+    }
+    unsigned mx = 0;
+    CK(cudaMemcpy(&mx, d_max, sizeof mx, cudaMemcpyDeviceToHost));
+    cudaFree(stage);
+    cudaFree(d_max);
+    if ((int)mx >= nmat) return fail("ID array references material %u but only %d materials were given", mx, nmat);
+    return 0;
+}
+
+template <typename R>
+void Solver<R>::set_boxes()
+{
+    // Index ranges of the CPU solver (fields_updates_ext.pyx), see SURVEY.md section 8(a).
+    auto setbox = [](Box &b, int i0, int i1, int j0, int j1, int k0, int k1) {
+        b.lo[0] = i0; b.hi[0] = i1; b.lo[1] = j0; b.hi[1] = j1; b.lo[2] = k0; b.hi[2] = k1;
+    };
+    Box none;
+    setbox(none, 0, 0, 0, 0, 0, 0);
+    // electric, :55-107 / :146-179 -- the same three boxes cover 3-D and every 2-D mode
+    setbox(ph_e.box[0], 0, nx, 1, ny, 1, nz);
+    setbox(ph_e.box[1], 1, nx, 0, ny, 1, nz);
+    setbox(ph_e.box[2], 1, nx, 1, ny, 0, nz);
+    // magnetic
+    if (nx == 1 || ny == 1 || nz == 1) {  // :376-399
+        ph_h.box[0] = ph_h.box[1] = ph_h.box[2] = none;
+        if (ny == 1 || nz == 1) setbox(ph_h.box[0], 1, nx, 0, ny, 0, nz);
+        if (nx == 1 || nz == 1) setbox(ph_h.box[1], 0, nx, 1, ny, 0, nz);
+        if (nx == 1 || ny == 1) setbox(ph_h.box[2], 0, nx, 0, ny, 1, nz);
+    } else {  // :401-412  Hx[i+1,j,k], Hy[i,j+1,k], Hz[i,j,k+1] for i<nx, j<ny, k<nz
+        setbox(ph_h.box[0], 1, nx + 1, 0, ny, 0, nz);
+        setbox(ph_h.box[1], 0, nx, 1, ny + 1, 0, nz);
+        setbox(ph_h.box[2], 0, nx, 0, ny, 1, nz + 1);
+    }
+}
+
+template <typename R>
+int Solver<R>::setup_pml(const gpb_model_t &m)
+{
+    ph_e.nslabs = ph_h.nslabs = 0;
+    if (m.npml > kMaxSlabs) return fail("at most %d PML slabs are supported, got %d", kMaxSlabs, m.npml);
+    for (int n = 0; n < m.npml; ++n) {
+        const gpb_pml_t &s = m.pmls[n];
+        if (s.direction < 0 || s.direction > 5) return fail("PML slab %d: bad direction %d", n, s.direction);
+        const int axis = s.direction % 3, minus = s.direction < 3;
+        const int t = s.thickness;
+        const int ext[3] = {s.xf - s.xs, s.yf - s.ys, s.zf - s.zs};
+        if (t <= 0 || ext[axis] != t) return fail("PML slab %d: thickness %d does not match its extent %d", n, t, ext[axis]);
+        const int lo0[3] = {s.xs, s.ys, s.zs}, hi0[3] = {s.xf, s.yf, s.zf};
+        const R *tabs[8];
+        const void *src[8] = {s.ERA, s.ERB, s.ERE, s.ERF, s.HRA, s.HRB, s.HRE, s.HRF};
+        for (int q = 0; q < 8; ++q) {
+            R *d = nullptr;
+            if (upload(&d, (const R *)src[q], (size_t)order * t)) return 1;
+            tabs[q] = d;
+        }
+        for (int phase = 0; phase < 2; ++phase) {  // 0 electric, 1 magnetic
+            SlabDev<R> sd;
+            memset(&sd, 0, sizeof sd);
+            for (int a = 0; a < 3; ++a) { sd.lo[a] = lo0[a]; sd.hi[a] = hi0[a]; }
+            // field index along the slab axis: electric minus  af - a  -> [as+1, af+1) ; magnetic minus af-(a+1) -> [as, af)
+            // (pml_updates_electric_HORIPML_ext.pyx:73 / pml_updates_magnetic_HORIPML_ext.pyx:69); plus: a + as
+            if (minus) {
+                if (phase == 0) { sd.lo[axis] = lo0[axis] + 1; sd.hi[axis] = hi0[axis] + 1; sd.dref = hi0[axis]; }
+                else { sd.dref = hi0[axis] - 1; }
+            } else {
+                sd.dref = lo0[axis];
+            }
+            sd.axis = axis;
+            sd.minus = minus;
+            sd.t = t;
+            // restrict to the planes this handle owns
+            const int glo = sd.lo[0], ghi = sd.hi[0];
+            sd.lo[0] = std::max(glo, x_start);
+            sd.hi[0] = std::min(ghi, x_start + nplanes);
+            if (sd.hi[0] <= sd.lo[0]) continue;
+            const long long n0 = sd.hi[0] - sd.lo[0];
+            sd.n1 = sd.hi[1] - sd.lo[1];
+            sd.n2 = sd.hi[2] - sd.lo[2];
+            sd.ostride = n0 * sd.n1 * sd.n2;
+            R *phi = nullptr;
+            const size_t nphi = (size_t)sd.ostride * 2 * order;
+            if (dalloc(&phi, nphi)) return 1;
+            phis.push_back({phi, nphi});
+            sd.phi = phi;
+            const int o = phase == 0 ? 0 : 4;
+            sd.RA = tabs[o]; sd.RB = tabs[o + 1]; sd.RE = tabs[o + 2]; sd.RF = tabs[o + 3];
+            sd.d = (R)(float)s.d;  // the reference kernels take `float d` (e.g. pml_updates_electric_HORIPML_ext.pyx:48)
+            PhaseParams<R> &ph = phase == 0 ? ph_e : ph_h;
+            ph.slab[ph.nslabs++] = sd;
+        }
+    }
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::setup_points(const gpb_model_t &m)
+{
+    nrx = m.nrx;
+    if (nrx) {
+        if (upload(&d_rxc, m.rxcoords, (size_t)nrx * 3)) return 1;
+        for (int r = 0; r < nrx; ++r) {
+            const int *c = m.rxcoords + 3 * r;
+            if (c[0] < 0 || c[0] > nx || c[1] < 0 || c[1] > ny || c[2] < 0 || c[2] > nz) return fail("receiver %d outside the grid", r);
+        }
+    }
+    if (dalloc(&d_rxs, (size_t)GPB_NRXOUT * iterations * std::max(nrx, 1))) return 1;
+    nsrc = m.nsources;
+    std::vector<SrcDev<R>> hs(nsrc);
+    const double dd[3] = {m.dx, m.dy, m.dz};
+    for (int s = 0; s < nsrc; ++s) {
+        const gpb_source_t &g = m.sources[s];
+        SrcDev<R> &d = hs[s];
+        if (g.kind < 0 || g.kind > 2 || g.polarisation < 0 || g.polarisation > 2) return fail("source %d: bad kind/polarisation", s);
+        if (g.i < 0 || g.i > nx || g.j < 0 || g.j > ny || g.k < 0 || g.k > nz) return fail("source %d outside the grid", s);
+        d.kind = g.kind; d.i = g.i; d.j = g.j; d.k = g.k; d.pol = g.polarisation;
+        d.it_first = g.it_first; d.it_last = g.it_last; d.hard = 0; d.f1 = 0; d.f2 = 0;
+        R *w = nullptr;
+        if (upload(&w, (const R *)g.waveform, (size_t)iterations)) return 1;
+        d.wave = w;
+        if (g.kind == GPB_SRC_HERTZIAN) {  // sources.py:181-193
+            d.f1 = (R)g.param;
+            d.f2 = (R)(1 / (m.dx * m.dy * m.dz));
+            has_esrc = true;
+        } else if (g.kind == GPB_SRC_MAGNETIC) {  // sources.py:220-232
+            d.f2 = (R)(1 / (m.dx * m.dy * m.dz));
+            has_hsrc = true;
+        } else {  // sources.py:97-117
+            if (g.param != 0) {
+                const int p = g.polarisation;
+                const double d1 = p == 0 ? m.dy : m.dx, d2 = p == 2 ? m.dy : m.dz;
+                d.f2 = (R)(1 / (g.param * d1 * d2));
+            } else {
+                d.hard = 1;
+                d.f2 = (R)dd[g.polarisation];
+            }
+            has_esrc = true;
+        }
+    }
+    if (nsrc && upload(&d_srcs, hs.data(), (size_t)nsrc)) return 1;
+    ntl = m.ntlines;
+    h_tls.resize(ntl);
+    tl_v0.resize(ntl);
+    tl_c0.resize(ntl);
+    tl_abc0.resize(2 * (size_t)ntl);
+    const double c0 = 299792458.0;
+    for (int t = 0; t < ntl; ++t) {
+        const gpb_tline_t &g = m.tlines[t];
+        TLDev<R> &d = h_tls[t];
+        if (g.nl < 2 || g.antpos >= g.nl || g.srcpos < 1 || g.srcpos >= g.nl) return fail("transmission line %d: bad line geometry", t);
+        d.i = g.i; d.j = g.j; d.k = g.k; d.pol = g.polarisation;
+        d.it_first = g.it_first; d.it_last = g.it_last;
+        d.nl = g.nl; d.srcpos = g.srcpos; d.antpos = g.antpos;
+        d.cdtdl = c0 * m.dt / g.dl;                           // sources.py:368-373
+        d.coefV = g.resistance * d.cdtdl;
+        d.coefI = (1 / g.resistance) * d.cdtdl;
+        d.h = (c0 * m.dt - g.dl) / (c0 * m.dt + g.dl);        // :355
+        const int p = g.polarisation;
+        d.dpol = (R)dd[p];
+        tl_v0[t].assign((const R *)g.voltage0, (const R *)g.voltage0 + g.nl);
+        tl_c0[t].assign((const R *)g.current0, (const R *)g.current0 + g.nl);
+        tl_abc0[2 * t] = (R)g.abcv0;
+        tl_abc0[2 * t + 1] = (R)g.abcv1;
+        R *v, *c, *abc, *ww, *wh, *vt, *itot;
+        if (upload(&v, tl_v0[t].data(), (size_t)g.nl) || upload(&c, tl_c0[t].data(), (size_t)g.nl) ||
+            upload(&abc, &tl_abc0[2 * t], 2) || upload(&ww, (const R *)g.wave_whole, (size_t)iterations) ||
+            upload(&wh, (const R *)g.wave_half, (size_t)iterations) || dalloc(&vt, (size_t)iterations) || dalloc(&itot, (size_t)iterations))
+            return 1;
+        d.voltage = v; d.current = c; d.abcv = abc; d.wave_whole = ww; d.wave_half = wh; d.Vtotal = vt; d.Itotal = itot;
+        has_hsrc = has_esrc = true;
+    }
+    if (ntl && upload(&d_tls, h_tls.data(), (size_t)ntl)) return 1;
+    // snapshots
+    snaps.assign(m.snapshots, m.snapshots + m.nsnapshots);
+    snapdev.resize(snaps.size());
+    for (size_t n = 0; n < snaps.size(); ++n) {
+        const gpb_snapshot_t &s = snaps[n];
+        if (s.nx <= 0 || s.ny <= 0 || s.nz <= 0 || s.dx < 1 || s.dy < 1 || s.dz < 1 || s.xs < 0 || s.ys < 0 || s.zs < 0 ||
+            s.xs + s.nx * s.dx > nx || s.ys + s.ny * s.dy > ny || s.zs + s.nz * s.dz > nz)
+            return fail("snapshot %zu does not fit the grid", n);
+        SnapDev<R> &d = snapdev[n];
+        d.xs = s.xs; d.ys = s.ys; d.zs = s.zs; d.dx = s.dx; d.dy = s.dy; d.dz = s.dz; d.nx = s.nx; d.ny = s.ny; d.nz = s.nz;
+        for (int c = 0; c < 6; ++c)
+            if (dalloc(&d.out[c], (size_t)s.nx * s.ny * s.nz)) return 1;
+    }
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::build(const gpb_model_t &m)
+{
+    nx = m.nx; ny = m.ny; nz = m.nz; x_start = m.x_start; nplanes = m.nx_planes;
+    iterations = m.iterations; nmat = m.nmaterials; maxpoles = m.maxpoles;
+    form = m.pml_formulation; order = m.npml ? m.pml_order : 1;
+    if (nx < 1 || ny < 1 || nz < 1) return fail("grid must have at least one cell per axis");
+    if (x_start < 0 || nplanes < 1 || x_start + nplanes > nx + 1) return fail("owned plane range [%d, %d) outside [0, %d]", x_start, x_start + nplanes, nx);
+    if (nmat < 1 || !m.ID || !m.updatecoeffsE || !m.updatecoeffsH) return fail("material tables missing");
+    if (m.npml && (order < 1 || order > 2 || form < 0 || form > 1)) return fail("unsupported PML formulation/order %d/%d", form, order);
+    if (maxpoles < 0 || (maxpoles > 0 && !m.updatecoeffsdispersive)) return fail("dispersive coefficient table missing");
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    pitch = choose_pitch(nz + 1);
+    plane = (long long)(ny + 1) * pitch;
+    narr = plane * (nplanes + 2);
+    idbytes = nmat <= 256 ? 1 : (nmat <= 65536 ? 2 : 4);
+    if (getenv("GPB_ID_BYTES")) idbytes = std::max(idbytes, atoi(getenv("GPB_ID_BYTES")) >= 4 ? 4 : (atoi(getenv("GPB_ID_BYTES")) >= 2 ? 2 : 1));
+    use_graph = !getenv("GPB_NO_GRAPH");
+    for (int c = 0; c < 6; ++c)
+        if (dalloc(&F[c], (size_t)narr)) return 1;
+    if (upload_ids(m)) return 1;
+    // coefficient rows: [CA, CBx, CBy, CBz | srce] (materials.py:200-201)
+    std::vector<Coef4<R>> hE(nmat), hH(nmat);
+    std::vector<R> sE(nmat), sH(nmat);
+    const R *cE = (const R *)m.updatecoeffsE, *cH = (const R *)m.updatecoeffsH;
+    for (int q = 0; q < nmat; ++q) {
+        hE[q].a = cE[5 * q]; hE[q].bx = cE[5 * q + 1]; hE[q].by = cE[5 * q + 2]; hE[q].bz = cE[5 * q + 3]; sE[q] = cE[5 * q + 4];
+        hH[q].a = cH[5 * q]; hH[q].bx = cH[5 * q + 1]; hH[q].by = cH[5 * q + 2]; hH[q].bz = cH[5 * q + 3]; sH[q] = cH[5 * q + 4];
+    }
+    if (upload(&coefE, hE.data(), (size_t)nmat) || upload(&coefH, hH.data(), (size_t)nmat) ||
+        upload(&srcE, sE.data(), (size_t)nmat) || upload(&srcH, sH.data(), (size_t)nmat))
+        return 1;
+    CK(cudaStreamSynchronize(stream));  // host vectors above go out of scope
+    smem_bytes = (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R));
+    tabsmem = smem_bytes <= 96 * 1024;
+    if (!tabsmem) smem_bytes = 0;
+    if (maxpoles) {
+        for (int c = 0; c < 3; ++c)
+            if (dalloc(&T[c], (size_t)narr * maxpoles)) return 1;
+        if (upload(&dcoef, (const Cplx<R> *)m.updatecoeffsdispersive, (size_t)nmat * 3 * maxpoles)) return 1;
+    }
+    if (dalloc(&d_iter, 2)) return 1;
+
+    for (PhaseParams<R> *ph : {&ph_h, &ph_e}) {
+        memset(ph, 0, sizeof *ph);
+        ph->nx = nx; ph->ny = ny; ph->nz = nz; ph->x_start = x_start; ph->nplanes = nplanes;
+        ph->pitch = pitch; ph->plane = plane;
+        ph->Ex = F[0]; ph->Ey = F[1]; ph->Ez = F[2]; ph->Hx = F[3]; ph->Hy = F[4]; ph->Hz = F[5];
+        ph->nmat = nmat; ph->form = form; ph->order = order;
+        ph->p0 = 0; ph->p1 = nplanes;
+    }
+    for (int c = 0; c < 3; ++c) { ph_e.ID[c] = ID[c]; ph_h.ID[c] = ID[3 + c]; }
+    ph_e.coef = coefE; ph_e.src = srcE; ph_h.coef = coefH; ph_h.src = srcH;
+    ph_e.maxpoles = maxpoles; ph_e.dcoef = dcoef; ph_e.tstride = narr;
+    for (int c = 0; c < 3; ++c) ph_e.T[c] = T[c];
+    set_boxes();
+    if (setup_pml(m)) return 1;
+
+    memset(&pp, 0, sizeof pp);
+    pp.x_start = x_start; pp.nplanes = nplanes; pp.ny = ny; pp.nz = nz; pp.pitch = pitch; pp.plane = plane;
+    for (int c = 0; c < 6; ++c) { pp.F[c] = F[c]; pp.ID[c] = ID[c]; }
+    pp.srcE = srcE; pp.srcH = srcH; pp.iter = d_iter; pp.iterations = iterations;
+    pp.dx = (R)m.dx; pp.dy = (R)m.dy; pp.dz = (R)m.dz;
+    if (setup_points(m)) return 1;
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ launches
+template <typename R>
+template <typename IDT>
+int Solver<R>::launch_h(int p0, int p1)
+{
+    PhaseParams<R> p = ph_h;
+    p.p0 = p0; p.p1 = p1;
+    dim3 grid((unsigned)((plane + kThreads - 1) / kThreads), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
+    if (tabsmem) k_update_h<R, IDT, true><<<grid, kThreads, smem_bytes, stream>>>(p);
+    else k_update_h<R, IDT, false><<<grid, kThreads, 0, stream>>>(p);
+    CK(cudaGetLastError());
+    ++launches;
+    return 0;
+}
+
+template <typename R>
+template <typename IDT>
+int Solver<R>::launch_e(int p0, int p1)
+{
+    PhaseParams<R> p = ph_e;
+    p.p0 = p0; p.p1 = p1;
+    dim3 grid((unsigned)((plane + kThreads - 1) / kThreads), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
+    if (maxpoles) {
+        if (tabsmem) k_update_e<R, IDT, true, true><<<grid, kThreads, smem_bytes, stream>>>(p);
+        else k_update_e<R, IDT, false, true><<<grid, kThreads, 0, stream>>>(p);
+    } else {
+        if (tabsmem) k_update_e<R, IDT, true, false><<<grid, kThreads, smem_bytes, stream>>>(p);
+        else k_update_e<R, IDT, false, false><<<grid, kThreads, 0, stream>>>(p);
+    }
+    CK(cudaGetLastError());
+    ++launches;
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::launch_phase(int phase, int p0, int p1)
+{
+    if (p1 <= p0) return 0;
+    if (phase == 0) {
+        if (idbytes == 1) return launch_h<uint8_t>(p0, p1);
+        if (idbytes == 2) return launch_h<uint16_t>(p0, p1);
+        return launch_h<uint32_t>(p0, p1);
+    }
+    if (idbytes == 1) return launch_e<uint8_t>(p0, p1);
+    if (idbytes == 2) return launch_e<uint16_t>(p0, p1);
+    return launch_e<uint32_t>(p0, p1);
+}
+
+template <typename R>
+int Solver<R>::launch_sources(int phase)
+{
+    if (phase == 0 ? !has_hsrc : !has_esrc) return 0;
+    if (idbytes == 1) k_sources<R, uint8_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls);
+    else if (idbytes == 2) k_sources<R, uint16_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls);
+    else k_sources<R, uint32_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls);
+    CK(cudaGetLastError());
+    ++launches;
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::launch_begin()
+{
+    k_step_begin<R><<<1, 128, 0, stream>>>(pp, d_iter, d_iter + 1, nrx, d_rxc, d_rxs, ntl, d_tls);
+    CK(cudaGetLastError());
+    ++launches;
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::launch_snapshots()
+{
+    for (size_t n = 0; n < snaps.size(); ++n) {
+        if (snaps[n].time != iteration + 1) continue;
+        const long long cells = (long long)snaps[n].nx * snaps[n].ny * snaps[n].nz;
+        const int blocks = (int)std::min<long long>((cells + 255) / 256, 148 * 8);
+        k_snapshot<R><<<blocks, 256, 0, stream>>>(pp, snapdev[n]);
+        CK(cudaGetLastError());
+        ++launches;
+    }
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::enqueue_step(bool with_snap)
+{
+    // model_build_run.py:590-696 in order
+    if (launch_begin()) return 1;
+    if (with_snap && launch_snapshots()) return 1;
+    if (launch_phase(0, 0, nplanes)) return 1;
+    if (launch_sources(0)) return 1;
+    if (launch_phase(1, 0, nplanes)) return 1;
+    if (launch_sources(1)) return 1;
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::run(int n)
+{
+    CK(cudaSetDevice(device));
+    if (n < 0 || iteration + n > iterations) return fail("cannot run %d iterations from %d: model has %d", n, iteration, iterations);
+    if (tabsmem && smem_bytes > 48 * 1024) {
+        // opt in to large dynamic shared memory for the coefficient rows
+        cudaFuncSetAttribute(k_update_h<R, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_h<R, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_h<R, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e<R, uint8_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e<R, uint16_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e<R, uint32_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e<R, uint8_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e<R, uint16_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e<R, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    }
+    if (use_graph && !graph && n > 1) {
+        // the step is identical every iteration (the iteration index lives on the device), so it is
+        // captured once and replayed: one graph launch per time step instead of 4-6 kernel launches
+        cudaGraph_t g = nullptr;
+        const uint64_t l0 = launches;
+        CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_step(false);
+        cudaError_t e = cudaStreamEndCapture(stream, &g);
+        launches = l0;
+        if (rc) return 1;
+        if (e != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(e));
+        CK(cudaGraphInstantiate(&graph, g, 0));
+        cudaGraphDestroy(g);
+    }
+    const uint64_t per_step = 2 + 1 + (has_hsrc ? 1 : 0) + (has_esrc ? 1 : 0);
+    CK(cudaEventRecord(ev0, stream));
+    for (int s = 0; s < n; ++s) {
+        if (graph && !snapshot_due(iteration)) {
+            CK(cudaGraphLaunch(graph, stream));
+            launches += per_step;
+        } else if (enqueue_step(true)) {
+            return 1;
+        }
+        ++iteration;
+    }
+    CK(cudaEventRecord(ev1, stream));
+    CK(cudaEventSynchronize(ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    elapsed += ms * 1e-3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Per-kernel device times of `n` iterations launched WITHOUT the graph, CUDA events between the
+// kernels on the launching stream: ms4 = {step prologue, H update, E update, source kernels} summed
+// over the n iterations.  Used by bench.py for the roofline of the dominant kernel.
+template <typename R>
+int Solver<R>::profile(int n, double *ms4)
+{
+    CK(cudaSetDevice(device));
+    if (n < 0 || iteration + n > iterations) return fail("cannot profile %d iterations from %d: model has %d", n, iteration, iterations);
+    cudaEvent_t ev[6];
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    for (int q = 0; q < 4; ++q) ms4[q] = 0;
+    for (int s = 0; s < n; ++s) {
+        CK(cudaEventRecord(ev[0], stream));
+        if (launch_begin() || launch_snapshots()) return 1;
+        CK(cudaEventRecord(ev[1], stream));
+        if (launch_phase(0, 0, nplanes)) return 1;
+        CK(cudaEventRecord(ev[2], stream));
+        if (launch_sources(0)) return 1;
+        CK(cudaEventRecord(ev[3], stream));
+        if (launch_phase(1, 0, nplanes)) return 1;
+        CK(cudaEventRecord(ev[4], stream));
+        if (launch_sources(1)) return 1;
+        CK(cudaEventRecord(ev[5], stream));
+        CK(cudaEventSynchronize(ev[5]));
+        float t01, t12, t23, t34, t45;
+        CK(cudaEventElapsedTime(&t01, ev[0], ev[1]));
+        CK(cudaEventElapsedTime(&t12, ev[1], ev[2]));
+        CK(cudaEventElapsedTime(&t23, ev[2], ev[3]));
+        CK(cudaEventElapsedTime(&t34, ev[3], ev[4]));
+        CK(cudaEventElapsedTime(&t45, ev[4], ev[5]));
+        ms4[0] += t01; ms4[1] += t12; ms4[2] += t34; ms4[3] += t23 + t45;
+        ++iteration;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::half_step(int phase)
+{
+    CK(cudaSetDevice(device));
+    if (phase == 0) {
+        if (iteration >= iterations) return fail("all %d iterations already done", iterations);
+        if (launch_begin() || launch_snapshots()) return 1;
+        // boundary plane first so the host can start the halo transfer while the interior runs
+        if (launch_phase(0, nplanes - 1, nplanes) || launch_phase(0, 0, nplanes - 1) || launch_sources(0)) return 1;
+    } else {
+        if (launch_phase(1, 0, 1) || launch_phase(1, 1, nplanes) || launch_sources(1)) return 1;
+        ++iteration;
+    }
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::reset()
+{
+    CK(cudaSetDevice(device));
+    for (int c = 0; c < 6; ++c) CK(cudaMemsetAsync(F[c], 0, (size_t)narr * sizeof(R), stream));
+    for (int c = 0; c < 3; ++c)
+        if (T[c]) CK(cudaMemsetAsync(T[c], 0, (size_t)narr * maxpoles * sizeof(Cplx<R>), stream));
+    for (auto &ph : phis) CK(cudaMemsetAsync(ph.first, 0, ph.second * sizeof(R), stream));
+    CK(cudaMemsetAsync(d_rxs, 0, (size_t)GPB_NRXOUT * iterations * std::max(nrx, 1) * sizeof(R), stream));
+    CK(cudaMemsetAsync(d_iter, 0, 2 * sizeof(int), stream));
+    for (int t = 0; t < ntl; ++t) {
+        CK(cudaMemcpyAsync(h_tls[t].voltage, tl_v0[t].data(), tl_v0[t].size() * sizeof(R), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(h_tls[t].current, tl_c0[t].data(), tl_c0[t].size() * sizeof(R), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(h_tls[t].abcv, &tl_abc0[2 * t], 2 * sizeof(R), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemsetAsync(h_tls[t].Vtotal, 0, (size_t)iterations * sizeof(R), stream));
+        CK(cudaMemsetAsync(h_tls[t].Itotal, 0, (size_t)iterations * sizeof(R), stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+    iteration = 0;
+    elapsed = 0;
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::get_receivers(void *out, size_t bytes)
+{
+    CK(cudaSetDevice(device));
+    const size_t need = (size_t)GPB_NRXOUT * iterations * nrx * sizeof(R);
+    if (bytes != need) return fail("receiver buffer is %zu bytes, expected %zu", bytes, need);
+    if (need) CK(cudaMemcpyAsync(out, d_rxs, need, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::get_snapshot(int idx, void *out6[6], size_t bytes_each)
+{
+    CK(cudaSetDevice(device));
+    if (idx < 0 || idx >= (int)snaps.size()) return fail("snapshot index %d out of range", idx);
+    const size_t need = (size_t)snaps[idx].nx * snaps[idx].ny * snaps[idx].nz * sizeof(R);
+    if (bytes_each != need) return fail("snapshot buffer is %zu bytes, expected %zu", bytes_each, need);
+    for (int c = 0; c < 6; ++c) CK(cudaMemcpyAsync(out6[c], snapdev[idx].out[c], need, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::get_tline(int idx, void *v, void *i, size_t bytes_each)
+{
+    CK(cudaSetDevice(device));
+    if (idx < 0 || idx >= ntl) return fail("transmission line index %d out of range", idx);
+    const size_t need = (size_t)iterations * sizeof(R);
+    if (bytes_each != need) return fail("transmission line buffer is %zu bytes, expected %zu", bytes_each, need);
+    CK(cudaMemcpyAsync(v, h_tls[idx].Vtotal, need, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(i, h_tls[idx].Itotal, need, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::get_field(int comp, void *out, size_t bytes)
+{
+    CK(cudaSetDevice(device));
+    if (comp < 0 || comp > 5) return fail("field component %d out of range", comp);
+    const size_t row = (size_t)(nz + 1) * sizeof(R), rows = (size_t)nplanes * (ny + 1);
+    if (bytes != row * rows) return fail("field buffer is %zu bytes, expected %zu", bytes, row * rows);
+    CK(cudaMemcpy2DAsync(out, row, F[comp] + plane, (size_t)pitch * sizeof(R), row, rows, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::set_field(int comp, const void *in, size_t bytes)
+{
+    CK(cudaSetDevice(device));
+    if (comp < 0 || comp > 5) return fail("field component %d out of range", comp);
+    const size_t row = (size_t)(nz + 1) * sizeof(R), rows = (size_t)nplanes * (ny + 1);
+    if (bytes != row * rows) return fail("field buffer is %zu bytes, expected %zu", bytes, row * rows);
+    CK(cudaMemcpy2DAsync(F[comp] + plane, (size_t)pitch * sizeof(R), in, row, row, rows, cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::halo(int which, void **a, void **b, size_t *bytes)
+{
+    // E halo: Ey,Ez of the first owned plane go to the left neighbour's ghost plane (x_start+nplanes there);
+    // H halo: Hy,Hz of the last owned plane go to the right neighbour's ghost plane (x_start-1 there).
+    const long long first = plane, last = plane * nplanes, ghost_lo = 0, ghost_hi = plane * (nplanes + 1);
+    switch (which) {
+    case 0: *a = F[1] + first; *b = F[2] + first; break;
+    case 1: *a = F[1] + ghost_hi; *b = F[2] + ghost_hi; break;
+    case 2: *a = F[4] + last; *b = F[5] + last; break;
+    case 3: *a = F[4] + ghost_lo; *b = F[5] + ghost_lo; break;
+    default: return fail("halo selector %d out of range", which);
+    }
+    *bytes = (size_t)plane * sizeof(R);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char *gpb_last_error(void) { return g_err.c_str(); }
+const char *gpb_version(void) { return "gprmax_b200 0.1 (sm_100a)"; }
+
+int gpb_device_count(int *count)
+{
+    if (!count) return fail("null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail("no CUDA device available: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return 0;
+}
+
+int gpb_device_info(int device_id, gpb_device_info_t *out)
+{
+    if (!out) return fail("null argument");
+    cudaDeviceProp pr;
+    CK(cudaGetDeviceProperties(&pr, device_id));
+    memset(out, 0, sizeof *out);
+    out->device_id = device_id;
+    strncpy(out->name, pr.name, sizeof out->name - 1);
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device_id) == cudaSuccess) strncpy(out->pci_bus_id, bus, sizeof out->pci_bus_id - 1);
+    out->total_mem = pr.totalGlobalMem;
+    out->const_mem = pr.totalConstMem;
+    out->sm_count = pr.multiProcessorCount;
+    out->cc_major = pr.major;
+    out->cc_minor = pr.minor;
+    return 0;
+}
+
+int gpb_create(const gpb_model_t *model, int device_id, gpb_handle *out)
+{
+    if (!model || !out) return fail("null argument");
+    *out = nullptr;
+    if (model->abi_version != GPB_ABI_VERSION) return fail("ABI version mismatch: library %d, caller %d", GPB_ABI_VERSION, model->abi_version);
+    int n = 0;
+    if (gpb_device_count(&n)) return 1;
+    if (device_id < 0 || device_id >= n) return fail("GPU with device ID %d does not exist (%d device(s) present)", device_id, n);
+    SolverBase *s = nullptr;
+    int rc;
+    if (model->dtype == GPB_F32) {
+        auto *p = new Solver<float>();
+        p->device = device_id;
+        rc = p->build(*model);
+        s = p;
+    } else if (model->dtype == GPB_F64) {
+        auto *p = new Solver<double>();
+        p->device = device_id;
+        rc = p->build(*model);
+        s = p;
+    } else {
+        return fail("unknown dtype %d", model->dtype);
+    }
+    if (rc) {
+        std::string keep = g_err;
+        delete s;
+        cudaGetLastError();
+        g_err = keep;
+        return 1;
+    }
+    *out = new gpb_solver{s};
+    return 0;
+}
+
+int gpb_destroy(gpb_handle h)
+{
+    if (!h) return 0;
+    delete h->impl;
+    delete h;
+    return 0;
+}
+
+#define NEED(h) if (!(h) || !(h)->impl) return fail("null handle")
+
+int gpb_run(gpb_handle h, int n_iters) { NEED(h); return h->impl->run(n_iters); }
+int gpb_half_step(gpb_handle h, int phase) { NEED(h); if (phase != 0 && phase != 1) return fail("phase must be 0 or 1"); return h->impl->half_step(phase); }
+int gpb_reset(gpb_handle h) { NEED(h); return h->impl->reset(); }
+int gpb_iteration(gpb_handle h, int *it) { NEED(h); if (!it) return fail("null argument"); *it = h->impl->iteration; return 0; }
+int gpb_elapsed_seconds(gpb_handle h, double *s) { NEED(h); if (!s) return fail("null argument"); *s = h->impl->elapsed; return 0; }
+int gpb_mem_used(gpb_handle h, uint64_t *b) { NEED(h); if (!b) return fail("null argument"); *b = h->impl->mem; return 0; }
+int gpb_kernel_launches(gpb_handle h, uint64_t *c) { NEED(h); if (!c) return fail("null argument"); *c = h->impl->launches; return 0; }
+int gpb_get_receivers(gpb_handle h, void *out, size_t bytes) { NEED(h); if (!out && bytes) return fail("null argument"); return h->impl->get_receivers(out, bytes); }
+int gpb_get_snapshot(gpb_handle h, int idx, void *out6[6], size_t bytes_each) { NEED(h); if (!out6) return fail("null argument"); return h->impl->get_snapshot(idx, out6, bytes_each); }
+int gpb_get_tline(gpb_handle h, int idx, void *v, void *i, size_t bytes_each) { NEED(h); if (!v || !i) return fail("null argument"); return h->impl->get_tline(idx, v, i, bytes_each); }
+int gpb_get_field(gpb_handle h, int comp, void *out, size_t bytes) { NEED(h); if (!out) return fail("null argument"); return h->impl->get_field(comp, out, bytes); }
+int gpb_set_field(gpb_handle h, int comp, const void *in, size_t bytes) { NEED(h); if (!in) return fail("null argument"); return h->impl->set_field(comp, in, bytes); }
+int gpb_halo(gpb_handle h, int which, void **a, void **b, size_t *bytes) { NEED(h); if (!a || !b || !bytes) return fail("null argument"); return h->impl->halo(which, a, b, bytes); }
+int gpb_profile(gpb_handle h, int n_iters, double *ms4) { NEED(h); if (!ms4) return fail("null argument"); return h->impl->profile(n_iters, ms4); }
+int gpb_stream(gpb_handle h, void **s) { NEED(h); if (!s) return fail("null argument"); *s = (void *)h->impl->stream; return 0; }
+int gpb_synchronize(gpb_handle h)
+{
+    NEED(h);
+    CK(cudaSetDevice(h->impl->device));
+    CK(cudaStreamSynchronize(h->impl->stream));
+    return 0;
+}
+
+}  // extern "C"

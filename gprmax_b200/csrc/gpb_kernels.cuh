@@ -1,0 +1,614 @@
+// gpb_kernels.cuh -- device side of the B200 FDTD core (sm_100a).
+//
+// Replaces the reference's CUDA-in-Python kernels:
+//   update_e / update_h / update_e_dispersive_A,B   gprMax/fields_updates_gpu.py:40-240
+//   order{1,2}_{x,y,z}{minus,plus} x 4 files         gprMax/pml_updates/*_gpu.py
+//   update_hertzian_dipole / magnetic_dipole / voltage_source   gprMax/source_updates_gpu.py:38-200
+//   store_outputs                                    gprMax/fields_outputs.py:81-105
+//   store_snapshot                                   gprMax/snapshots_gpu.py:31-77
+// with the index ranges and arithmetic of the CPU solver the traces are judged against
+// (fields_updates_ext.pyx, pml_updates/*_ext.pyx, sources.py, snapshots_ext.pyx).
+//
+// Design:
+//   * private device layout: z pitch padded to a multiple of 32 elements, one ghost plane on each
+//     x side (halo for x-slab sharding), material IDs narrowed to u8/u16 when they fit;
+//   * one thread per (j,k) column of a plane, marching XCHUNK planes along x with a register queue
+//     for the i-1 (E phase) / i+1 (H phase) operands -> every operand array is read once per phase;
+//   * the CFS-PML slab corrections are fused into the same pass (no extra sweeps over E/H/ID; the
+//     only extra traffic is the Phi state), applied in G.pmls order exactly like the slab-by-slab
+//     reference sequence;
+//   * dispersive part B of step n is folded into part A of step n+1 (E is untouched in between),
+//     removing one full pass over E, ID and T per step;
+//   * coefficient rows live in shared memory (no constant-cache serialisation with many materials).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpb {
+
+constexpr int kThreads = 256;
+constexpr int kXChunk = 16;
+constexpr int kMaxSlabs = 6;
+
+template <typename R>
+struct alignas(4 * sizeof(R)) Coef4 {
+    R a, bx, by, bz;  // E: CA, CBx, CBy, CBz ; H: DA, DBx, DBy, DBz  (materials.py:200-201)
+};
+
+template <typename R>
+struct Cplx {
+    R re, im;
+};
+
+// One PML slab as seen by one phase (electric or magnetic).
+template <typename R>
+struct SlabDev {
+    int lo[3], hi[3];  // global FIELD-index box [lo, hi) touched in this phase
+    int axis;          // 0 x, 1 y, 2 z
+    int minus;         // 1: depth = dref - idx ; 0: depth = idx - dref
+    int dref;
+    int t;             // thickness = row length of the R tables
+    int n1, n2;        // extents of the box along y and z (Phi is [order][2][n0][n1][n2])
+    long long ostride; // n0*n1*n2 : distance between Phi components / orders
+    R *phi;
+    const R *RA, *RB, *RE, *RF;
+    R d;               // spacing, rounded through float first like the reference's `float d`
+};
+
+struct Box {
+    int lo[3], hi[3];  // global index box in which a component's base update runs
+};
+
+template <typename R>
+struct PhaseParams {
+    // geometry
+    int nx, ny, nz;        // global cells
+    int x_start, nplanes;  // owned node planes
+    int pitch;             // z pitch (elements)
+    long long plane;       // (ny+1)*pitch
+    // fields: pointers to local plane 0 (= ghost plane x_start-1)
+    R *Ex, *Ey, *Ez, *Hx, *Hy, *Hz;
+    const void *ID[3];     // the three ID components of this phase (same layout as fields)
+    const Coef4<R> *coef;  // [nmat]
+    const R *src;          // [nmat] srce / srcm
+    int nmat;
+    Box box[3];
+    int nslabs;
+    int form;              // 0 HORIPML, 1 MRIPML
+    int order;             // 1, 2
+    SlabDev<R> slab[kMaxSlabs];
+    // dispersive (E phase only)
+    int maxpoles;
+    Cplx<R> *T[3];            // [maxpoles][nplanes+2][ny+1][pitch]
+    const Cplx<R> *dcoef;     // [nmat][maxpoles][3]
+    long long tstride;        // elements between poles
+    // sub-range of owned planes processed by this launch (for halo overlap): [p0, p1)
+    int p0, p1;
+};
+
+// ------------------------------------------------------------------------------------------
+// PML recursive-integration term for one component.  Arithmetic follows
+// pml_updates_electric_HORIPML_ext.pyx:69-87 (order 1), :132-157 (order 2) and
+// pml_updates_electric_MRIPML_ext.pyx:68-89, :133-162 (identical in the magnetic files).
+// Returns the bracket that multiplies srce/srcm and advances Phi in place.
+// ------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ R pml_term(int form, int order, const SlabDev<R> &s, int depth, R dF, R *phi0p, long long ostride)
+{
+    const R one = (R)1;
+    R term;
+    if (form == 0) {
+        if (order == 1) {
+            R RA01 = __ldg(s.RA + depth) - one;
+            R RB0 = __ldg(s.RB + depth), RE0 = __ldg(s.RE + depth), RF0 = __ldg(s.RF + depth);
+            R phi0 = *phi0p;
+            term = RA01 * dF + RB0 * phi0;
+            *phi0p = RE0 * phi0 - RF0 * dF;
+        } else {
+            R RA0 = __ldg(s.RA + depth), RA1 = __ldg(s.RA + s.t + depth);
+            R RB0 = __ldg(s.RB + depth), RB1 = __ldg(s.RB + s.t + depth);
+            R RE0 = __ldg(s.RE + depth), RE1 = __ldg(s.RE + s.t + depth);
+            R RF0 = __ldg(s.RF + depth), RF1 = __ldg(s.RF + s.t + depth);
+            R RA01 = RA0 * RA1 - one;
+            R *phi1p = phi0p + 2 * ostride;
+            R phi0 = *phi0p, phi1 = *phi1p;
+            term = RA01 * dF + RA1 * RB0 * phi0 + RB1 * phi1;
+            *phi1p = RE1 * phi1 - RF1 * (RA0 * dF + RB0 * phi0);
+            *phi0p = RE0 * phi0 - RF0 * dF;
+        }
+    } else {
+        if (order == 1) {
+            R RB0 = __ldg(s.RB + depth), RE0 = __ldg(s.RE + depth), RF0 = __ldg(s.RF + depth);
+            R IRA = one / __ldg(s.RA + depth);
+            R IRA1 = IRA - one;
+            R RC0 = IRA * RB0 * RF0;
+            R phi0 = *phi0p;
+            term = IRA1 * dF - IRA * phi0;
+            *phi0p = RE0 * phi0 + RC0 * dF - RC0 * phi0;
+        } else {
+            R RB0 = __ldg(s.RB + depth), RB1 = __ldg(s.RB + s.t + depth);
+            R RE0 = __ldg(s.RE + depth), RE1 = __ldg(s.RE + s.t + depth);
+            R RF0 = __ldg(s.RF + depth), RF1 = __ldg(s.RF + s.t + depth);
+            R IRA = one / (__ldg(s.RA + depth) + __ldg(s.RA + s.t + depth));
+            R IRA1 = IRA - one;
+            R RC0 = IRA * RF0, RC1 = IRA * RF1;
+            R *phi1p = phi0p + 2 * ostride;
+            R phi0 = *phi0p, phi1 = *phi1p;
+            R psi = RB0 * phi0 + RB1 * phi1;
+            term = IRA1 * dF - IRA * psi;
+            *phi1p = RE1 * phi1 + RC1 * (dF - psi);
+            *phi0p = RE0 * phi0 + RC0 * (dF - psi);
+        }
+    }
+    return term;
+}
+
+template <typename R>
+__device__ __forceinline__ bool in_box(const int *lo, const int *hi, int i, int j, int k)
+{
+    return i >= lo[0] && i < hi[0] && j >= lo[1] && j < hi[1] && k >= lo[2] && k < hi[2];
+}
+
+template <typename IDT>
+__device__ __forceinline__ unsigned ld_id(const void *base, long long off)
+{
+    return (unsigned)__ldg(reinterpret_cast<const IDT *>(base) + off);
+}
+
+// Shared-memory staging of the coefficient rows of one phase.
+template <typename R>
+__device__ __forceinline__ void stage_coefs(const PhaseParams<R> &p, Coef4<R> *scoef, R *ssrc)
+{
+    for (int m = threadIdx.x; m < p.nmat; m += blockDim.x) {
+        scoef[m] = p.coef[m];
+        ssrc[m] = p.src[m];
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Magnetic half-step: base update (fields_updates_ext.pyx:352-412) + fused H-PML corrections
+// (pml_updates_magnetic_*_ext.pyx).  Marches +x; queue holds Ey,Ez of the next plane.
+// ------------------------------------------------------------------------------------------
+template <typename R, typename IDT, bool TABSMEM>
+__global__ void __launch_bounds__(kThreads) k_update_h(const PhaseParams<R> p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Coef4<R> *coef = p.coef;
+    const R *srcm = p.src;
+    if (TABSMEM) {
+        Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw);
+        R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
+        stage_coefs(p, scoef, ssrc);
+        coef = scoef;
+        srcm = ssrc;
+    }
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (int)(idx / p.pitch);
+    const int k = (int)(idx - (long long)j * p.pitch);
+    if (j > p.ny || k > p.nz) return;
+    const bool hasj = j < p.ny, hask = k < p.nz;  // rows j+1 / k+1 exist
+    const int l0 = p.p0 + blockIdx.y * kXChunk;
+    const int l1 = min(l0 + kXChunk, p.p1);
+    if (l0 >= l1) return;
+    long long off = (long long)(l0 + 1) * p.plane + idx;  // +1: ghost plane in front
+    R ey_c = p.Ey[off], ez_c = p.Ez[off];
+#pragma unroll 2
+    for (int l = l0; l < l1; ++l, off += p.plane) {
+        const int i = p.x_start + l;
+        const R ey_n = p.Ey[off + p.plane], ez_n = p.Ez[off + p.plane];
+        const R ex_c = p.Ex[off];
+        const R ex_j = hasj ? p.Ex[off + p.pitch] : (R)0;
+        const R ex_k = hask ? p.Ex[off + 1] : (R)0;
+        const R ey_k = hask ? p.Ey[off + 1] : (R)0;
+        const R ez_j = hasj ? p.Ez[off + p.pitch] : (R)0;
+        // the six one-sided differences every update / correction below is built from
+        const R dEz_dy = ez_j - ez_c, dEy_dz = ey_k - ey_c;
+        const R dEx_dz = ex_k - ex_c, dEz_dx = ez_n - ez_c;
+        const R dEy_dx = ey_n - ey_c, dEx_dy = ex_j - ex_c;
+        R hx = p.Hx[off], hy = p.Hy[off], hz = p.Hz[off];
+        bool wx = false, wy = false, wz = false;
+        unsigned mx = 0, my = 0, mz = 0;
+        if (in_box<R>(p.box[0].lo, p.box[0].hi, i, j, k)) {
+            mx = ld_id<IDT>(p.ID[0], off);
+            const Coef4<R> c = coef[mx];
+            hx = c.a * hx - c.by * dEz_dy + c.bz * dEy_dz;
+            wx = true;
+        }
+        if (in_box<R>(p.box[1].lo, p.box[1].hi, i, j, k)) {
+            my = ld_id<IDT>(p.ID[1], off);
+            const Coef4<R> c = coef[my];
+            hy = c.a * hy - c.bz * dEx_dz + c.bx * dEz_dx;
+            wy = true;
+        }
+        if (in_box<R>(p.box[2].lo, p.box[2].hi, i, j, k)) {
+            mz = ld_id<IDT>(p.ID[2], off);
+            const Coef4<R> c = coef[mz];
+            hz = c.a * hz - c.bx * dEy_dx + c.by * dEx_dy;
+            wz = true;
+        }
+        for (int s = 0; s < p.nslabs; ++s) {
+            const SlabDev<R> &sl = p.slab[s];
+            if (!in_box<R>(sl.lo, sl.hi, i, j, k)) continue;
+            const int a = sl.axis;
+            const int pos = (a == 0) ? i : (a == 1) ? j : k;
+            const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
+            R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+            // magnetic x: Hy += , dEz/dx ; Hz -= , dEy/dx   (pml_updates_magnetic_HORIPML_ext.pyx:79-87)
+            // magnetic y: Hx -= , dEz/dy ; Hz += , dEx/dy   (:347-355)
+            // magnetic z: Hx += , dEy/dz ; Hy -= , dEx/dz   (:615-623)
+            if (a == 0) {
+                if (!wy) my = ld_id<IDT>(p.ID[1], off);
+                if (!wz) mz = ld_id<IDT>(p.ID[2], off);
+                hy = hy + srcm[my] * pml_term(p.form, p.order, sl, depth, dEz_dx / sl.d, phi, sl.ostride);
+                hz = hz - srcm[mz] * pml_term(p.form, p.order, sl, depth, dEy_dx / sl.d, phi + sl.ostride, sl.ostride);
+                wy = wz = true;
+            } else if (a == 1) {
+                if (!wx) mx = ld_id<IDT>(p.ID[0], off);
+                if (!wz) mz = ld_id<IDT>(p.ID[2], off);
+                hx = hx - srcm[mx] * pml_term(p.form, p.order, sl, depth, dEz_dy / sl.d, phi, sl.ostride);
+                hz = hz + srcm[mz] * pml_term(p.form, p.order, sl, depth, dEx_dy / sl.d, phi + sl.ostride, sl.ostride);
+                wx = wz = true;
+            } else {
+                if (!wx) mx = ld_id<IDT>(p.ID[0], off);
+                if (!wy) my = ld_id<IDT>(p.ID[1], off);
+                hx = hx + srcm[mx] * pml_term(p.form, p.order, sl, depth, dEy_dz / sl.d, phi, sl.ostride);
+                hy = hy - srcm[my] * pml_term(p.form, p.order, sl, depth, dEx_dz / sl.d, phi + sl.ostride, sl.ostride);
+                wx = wy = true;
+            }
+        }
+        if (wx) p.Hx[off] = hx;
+        if (wy) p.Hy[off] = hy;
+        if (wz) p.Hz[off] = hz;
+        ey_c = ey_n;
+        ez_c = ez_n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Dispersive helper: fold part B of the previous step (fields_updates_ext.pyx:183-235) into part A
+// of this one (:113-179).  `phi` is a float even in the float64 build (:143), reproduced here.
+// ------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ R dispersive_AB(const PhaseParams<R> &p, int comp, unsigned m, long long off, R e_old)
+{
+    float phi = 0;
+    const Cplx<R> *dc = p.dcoef + (long long)m * p.maxpoles * 3;
+    Cplx<R> *T = p.T[comp] + off;
+    for (int q = 0; q < p.maxpoles; ++q, T += p.tstride, dc += 3) {
+        const Cplx<R> c0 = dc[0], c1 = dc[1], c2 = dc[2];
+        Cplx<R> t = *T;
+        // part B of the previous step: T -= c2 * E   (E unchanged since then)
+        t.re = t.re - c2.re * e_old;
+        t.im = t.im - c2.im * e_old;
+        phi = phi + c0.re * t.re;
+        Cplx<R> tn;
+        tn.re = (c1.re * t.re - c1.im * t.im) + c2.re * e_old;
+        tn.im = (c1.re * t.im + c1.im * t.re) + c2.im * e_old;
+        *T = tn;
+    }
+    return (R)phi;
+}
+
+// ------------------------------------------------------------------------------------------
+// Electric half-step: base update (fields_updates_ext.pyx:30-107, dispersive :113-179) + fused
+// E-PML corrections (pml_updates_electric_*_ext.pyx).  Marches +x; queue holds Hy,Hz of plane i-1.
+// ------------------------------------------------------------------------------------------
+template <typename R, typename IDT, bool TABSMEM, bool DISP>
+__global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Coef4<R> *coef = p.coef;
+    const R *srce = p.src;
+    if (TABSMEM) {
+        Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw);
+        R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
+        stage_coefs(p, scoef, ssrc);
+        coef = scoef;
+        srce = ssrc;
+    }
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (int)(idx / p.pitch);
+    const int k = (int)(idx - (long long)j * p.pitch);
+    if (j > p.ny || k > p.nz) return;
+    const bool hasj = j > 0, hask = k > 0;  // rows j-1 / k-1 exist
+    const int l0 = p.p0 + blockIdx.y * kXChunk;
+    const int l1 = min(l0 + kXChunk, p.p1);
+    if (l0 >= l1) return;
+    long long off = (long long)(l0 + 1) * p.plane + idx;
+    R hy_p = p.Hy[off - p.plane], hz_p = p.Hz[off - p.plane];
+#pragma unroll 2
+    for (int l = l0; l < l1; ++l, off += p.plane) {
+        const int i = p.x_start + l;
+        const R hx_c = p.Hx[off], hy_c = p.Hy[off], hz_c = p.Hz[off];
+        const R hx_j = hasj ? p.Hx[off - p.pitch] : (R)0;
+        const R hx_k = hask ? p.Hx[off - 1] : (R)0;
+        const R hy_k = hask ? p.Hy[off - 1] : (R)0;
+        const R hz_j = hasj ? p.Hz[off - p.pitch] : (R)0;
+        const R dHz_dy = hz_c - hz_j, dHy_dz = hy_c - hy_k;
+        const R dHx_dz = hx_c - hx_k, dHz_dx = hz_c - hz_p;
+        const R dHy_dx = hy_c - hy_p, dHx_dy = hx_c - hx_j;
+        R ex = p.Ex[off], ey = p.Ey[off], ez = p.Ez[off];
+        bool wx = false, wy = false, wz = false;
+        unsigned mx = 0, my = 0, mz = 0;
+        if (in_box<R>(p.box[0].lo, p.box[0].hi, i, j, k)) {
+            mx = ld_id<IDT>(p.ID[0], off);
+            const Coef4<R> c = coef[mx];
+            if (DISP) {
+                const R phi = dispersive_AB(p, 0, mx, off, ex);
+                ex = c.a * ex + c.by * dHz_dy - c.bz * dHy_dz - srce[mx] * phi;
+            } else {
+                ex = c.a * ex + c.by * dHz_dy - c.bz * dHy_dz;
+            }
+            wx = true;
+        }
+        if (in_box<R>(p.box[1].lo, p.box[1].hi, i, j, k)) {
+            my = ld_id<IDT>(p.ID[1], off);
+            const Coef4<R> c = coef[my];
+            if (DISP) {
+                const R phi = dispersive_AB(p, 1, my, off, ey);
+                ey = c.a * ey + c.bz * dHx_dz - c.bx * dHz_dx - srce[my] * phi;
+            } else {
+                ey = c.a * ey + c.bz * dHx_dz - c.bx * dHz_dx;
+            }
+            wy = true;
+        }
+        if (in_box<R>(p.box[2].lo, p.box[2].hi, i, j, k)) {
+            mz = ld_id<IDT>(p.ID[2], off);
+            const Coef4<R> c = coef[mz];
+            if (DISP) {
+                const R phi = dispersive_AB(p, 2, mz, off, ez);
+                ez = c.a * ez + c.bx * dHy_dx - c.by * dHx_dy - srce[mz] * phi;
+            } else {
+                ez = c.a * ez + c.bx * dHy_dx - c.by * dHx_dy;
+            }
+            wz = true;
+        }
+        for (int s = 0; s < p.nslabs; ++s) {
+            const SlabDev<R> &sl = p.slab[s];
+            if (!in_box<R>(sl.lo, sl.hi, i, j, k)) continue;
+            const int a = sl.axis;
+            const int pos = (a == 0) ? i : (a == 1) ? j : k;
+            const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
+            R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+            // electric x: Ey -= , dHz/dx ; Ez += , dHy/dx   (pml_updates_electric_HORIPML_ext.pyx:79-87)
+            // electric y: Ex += , dHz/dy ; Ez -= , dHx/dy   (:347-355)
+            // electric z: Ex -= , dHy/dz ; Ey += , dHx/dz   (:615-623)
+            if (a == 0) {
+                if (!wy) my = ld_id<IDT>(p.ID[1], off);
+                if (!wz) mz = ld_id<IDT>(p.ID[2], off);
+                ey = ey - srce[my] * pml_term(p.form, p.order, sl, depth, dHz_dx / sl.d, phi, sl.ostride);
+                ez = ez + srce[mz] * pml_term(p.form, p.order, sl, depth, dHy_dx / sl.d, phi + sl.ostride, sl.ostride);
+                wy = wz = true;
+            } else if (a == 1) {
+                if (!wx) mx = ld_id<IDT>(p.ID[0], off);
+                if (!wz) mz = ld_id<IDT>(p.ID[2], off);
+                ex = ex + srce[mx] * pml_term(p.form, p.order, sl, depth, dHz_dy / sl.d, phi, sl.ostride);
+                ez = ez - srce[mz] * pml_term(p.form, p.order, sl, depth, dHx_dy / sl.d, phi + sl.ostride, sl.ostride);
+                wx = wz = true;
+            } else {
+                if (!wx) mx = ld_id<IDT>(p.ID[0], off);
+                if (!wy) my = ld_id<IDT>(p.ID[1], off);
+                ex = ex - srce[mx] * pml_term(p.form, p.order, sl, depth, dHy_dz / sl.d, phi, sl.ostride);
+                ey = ey + srce[my] * pml_term(p.form, p.order, sl, depth, dHx_dz / sl.d, phi + sl.ostride, sl.ostride);
+                wx = wy = true;
+            }
+        }
+        if (wx) p.Ex[off] = ex;
+        if (wy) p.Ey[off] = ey;
+        if (wz) p.Ez[off] = ez;
+        hy_p = hy_c;
+        hz_p = hz_c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Point sources, receivers, transmission lines, snapshots.
+// ------------------------------------------------------------------------------------------
+template <typename R>
+struct SrcDev {
+    int kind;        // 0 hertzian, 1 magnetic, 2 voltage
+    int i, j, k;     // global
+    int pol;
+    int it_first, it_last;
+    int hard;        // voltage source with zero resistance
+    R f1, f2;        // hertzian: dl, 1/(dx dy dz) ; magnetic: f2 = 1/(dx dy dz) ; voltage: f2 = 1/(R d1 d2) or (hard) d_pol
+    const R *wave;   // [iterations]
+};
+
+template <typename R>
+struct TLDev {
+    int i, j, k, pol;
+    int it_first, it_last;
+    int nl, srcpos, antpos;
+    double coefV;     // resistance * (c dt / dl)
+    double coefI;     // (1/resistance) * (c dt / dl)
+    double cdtdl;     // c dt / dl
+    double h;         // (c dt - dl) / (c dt + dl)
+    R d1, d2, dpol;   // spacings for the current loop (grid.py:413-461) and the E assignment
+    R *voltage, *current;  // [nl]
+    R *abcv;          // [2]
+    const R *wave_whole, *wave_half;
+    R *Vtotal, *Itotal;    // [iterations]
+};
+
+template <typename R>
+struct PointParams {
+    int x_start, nplanes, ny, nz, pitch;
+    long long plane;
+    R *F[6];               // Ex,Ey,Ez,Hx,Hy,Hz (local plane 0 = ghost)
+    const void *ID[6];
+    const R *srcE, *srcH;  // [nmat]
+    const int *iter;       // device iteration counter (current)
+    int iterations;
+    R dx, dy, dz;
+};
+
+template <typename R>
+__device__ __forceinline__ long long pt_off(const PointParams<R> &p, int i, int j, int k)
+{
+    return (long long)(i - p.x_start + 1) * p.plane + (long long)j * p.pitch + k;
+}
+template <typename R>
+__device__ __forceinline__ bool pt_owned(const PointParams<R> &p, int i)
+{
+    return i >= p.x_start && i < p.x_start + p.nplanes;
+}
+
+// I_x, I_y, I_z of grid.py:413-461 at node (i,j,k); needs H one plane back (ghost is valid).
+template <typename R>
+__device__ __forceinline__ R current_at(const PointParams<R> &p, int comp, int i, int j, int k)
+{
+    const long long o = pt_off(p, i, j, k);
+    const R *Hx = p.F[3], *Hy = p.F[4], *Hz = p.F[5];
+    if (comp == 0) {
+        if (j == 0 || k == 0) return (R)0;
+        return p.dy * (Hy[o - 1] - Hy[o]) + p.dz * (Hz[o] - Hz[o - p.pitch]);
+    } else if (comp == 1) {
+        if (i == 0 || k == 0) return (R)0;
+        return p.dx * (Hx[o] - Hx[o - 1]) + p.dz * (Hz[o - p.plane] - Hz[o]);
+    } else {
+        if (i == 0 || j == 0) return (R)0;
+        return p.dx * (Hx[o - p.pitch] - Hx[o]) + p.dy * (Hy[o] - Hy[o - p.plane]);
+    }
+}
+
+// Step prologue: receiver gather (fields_outputs.py:40-64 / :81-105), transmission-line totals
+// (:62-64) and the device iteration counter.  One block; `next` is bumped after every thread read it.
+template <typename R>
+__global__ void k_step_begin(PointParams<R> p, int *iter_cur, int *iter_next, int nrx, const int *rxc, R *rxs,
+                             int ntl, const TLDev<R> *tls)
+{
+    const int it = *iter_next;
+    if (it < p.iterations) {
+        for (int r = threadIdx.x; r < nrx; r += blockDim.x) {
+            const int i = rxc[3 * r], j = rxc[3 * r + 1], k = rxc[3 * r + 2];
+            if (!pt_owned(p, i)) continue;
+            const long long o = pt_off(p, i, j, k);
+            for (int c = 0; c < 6; ++c) rxs[((long long)c * p.iterations + it) * nrx + r] = p.F[c][o];
+            for (int c = 0; c < 3; ++c) rxs[((long long)(6 + c) * p.iterations + it) * nrx + r] = current_at(p, c, i, j, k);
+        }
+        for (int t = threadIdx.x; t < ntl; t += blockDim.x) {
+            tls[t].Vtotal[it] = tls[t].voltage[tls[t].antpos];
+            tls[t].Itotal[it] = tls[t].current[tls[t].antpos];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *iter_cur = it;
+        *iter_next = it + 1;
+    }
+}
+
+// Sources of one phase, applied in array order by a single thread each (order between different
+// sources only matters when two sit on the same edge; then the serial loop keeps the CPU order).
+// phase 0 (after H update + H-PML): transmission lines (current), magnetic dipoles   model_build_run.py:440-442
+// phase 1 (after E update + E-PML): voltage sources, transmission lines (voltage), Hertzian dipoles  :458-461
+template <typename R, typename IDT>
+__global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R> *srcs, int ntl, const TLDev<R> *tls)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int it = *p.iter;
+    if (phase == 0) {
+        for (int t = 0; t < ntl; ++t) {
+            const TLDev<R> &tl = tls[t];
+            if (it < tl.it_first || it > tl.it_last || !pt_owned(p, tl.i)) continue;
+            // update_current, sources.py:379-393 (float64 arithmetic, stored as R)
+            for (int n = 0; n < tl.nl - 1; ++n) {
+                const R dv = tl.voltage[n + 1] - tl.voltage[n];
+                tl.current[n] = (R)((double)tl.current[n] - tl.coefI * (double)dv);
+            }
+            tl.current[tl.srcpos - 1] = (R)((double)tl.current[tl.srcpos - 1] + tl.coefI * (double)tl.wave_half[it]);
+            tl.current[tl.antpos] = current_at(p, tl.pol, tl.i, tl.j, tl.k);  // :444-452
+        }
+        for (int s = 0; s < nsrc; ++s) {
+            const SrcDev<R> &sc = srcs[s];
+            if (sc.kind != 1 || it < sc.it_first || it > sc.it_last || !pt_owned(p, sc.i)) continue;
+            const long long o = pt_off(p, sc.i, sc.j, sc.k);
+            const unsigned m = ld_id<IDT>(p.ID[3 + sc.pol], o);
+            // sources.py:220-232
+            p.F[3 + sc.pol][o] -= p.srcH[m] * sc.wave[it] * sc.f2;
+        }
+    } else {
+        for (int s = 0; s < nsrc; ++s) {
+            const SrcDev<R> &sc = srcs[s];
+            if (sc.kind != 2 || it < sc.it_first || it > sc.it_last || !pt_owned(p, sc.i)) continue;
+            const long long o = pt_off(p, sc.i, sc.j, sc.k);
+            if (sc.hard) {
+                p.F[sc.pol][o] = -sc.wave[it] / sc.f2;  // sources.py:103, 110, 117
+            } else {
+                const unsigned m = ld_id<IDT>(p.ID[sc.pol], o);
+                p.F[sc.pol][o] -= p.srcE[m] * sc.wave[it] * sc.f2;  // sources.py:99-101
+            }
+        }
+        for (int t = 0; t < ntl; ++t) {
+            const TLDev<R> &tl = tls[t];
+            if (it < tl.it_first || it > tl.it_last || !pt_owned(p, tl.i)) continue;
+            // update_voltage, sources.py:360-377
+            for (int n = tl.nl - 1; n >= 1; --n) {
+                const R dc = tl.current[n] - tl.current[n - 1];
+                tl.voltage[n] = (R)((double)tl.voltage[n] - tl.coefV * (double)dc);
+            }
+            tl.voltage[tl.srcpos] = (R)((double)tl.voltage[tl.srcpos] + tl.cdtdl * (double)tl.wave_whole[it]);
+            // update_abc, :348-358
+            const R v0 = (R)(tl.h * (double)(R)(tl.voltage[1] - tl.abcv[0]) + (double)tl.abcv[1]);
+            tl.voltage[0] = v0;
+            tl.abcv[0] = v0;
+            tl.abcv[1] = tl.voltage[1];
+            p.F[tl.pol][pt_off(p, tl.i, tl.j, tl.k)] = -tl.voltage[tl.antpos] / tl.dpol;  // :415-424
+        }
+        for (int s = 0; s < nsrc; ++s) {
+            const SrcDev<R> &sc = srcs[s];
+            if (sc.kind != 0 || it < sc.it_first || it > sc.it_last || !pt_owned(p, sc.i)) continue;
+            const long long o = pt_off(p, sc.i, sc.j, sc.k);
+            const unsigned m = ld_id<IDT>(p.ID[sc.pol], o);
+            // sources.py:181-193
+            p.F[sc.pol][o] -= p.srcE[m] * sc.wave[it] * sc.f1 * sc.f2;
+        }
+    }
+}
+
+// Snapshot: strided cell-centred averages (snapshots.py:87-130, snapshots_ext.pyx:56-80).
+template <typename R>
+struct SnapDev {
+    int xs, ys, zs, dx, dy, dz, nx, ny, nz;
+    R *out[6];  // each [nx][ny][nz]
+};
+
+template <typename R>
+__global__ void k_snapshot(PointParams<R> p, SnapDev<R> s)
+{
+    const long long n = (long long)s.nx * s.ny * s.nz;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(q % s.nz), j = (int)((q / s.nz) % s.ny), i = (int)(q / ((long long)s.nz * s.ny));
+        const int gi = s.xs + i * s.dx, gj = s.ys + j * s.dy, gk = s.zs + k * s.dz;
+        if (!pt_owned(p, gi)) continue;
+        const long long o = pt_off(p, gi, gj, gk);
+        const long long si = (long long)s.dx * p.plane, sj = (long long)s.dy * p.pitch, sk = s.dz;
+        const R *Ex = p.F[0], *Ey = p.F[1], *Ez = p.F[2], *Hx = p.F[3], *Hy = p.F[4], *Hz = p.F[5];
+        s.out[0][q] = (Ex[o] + Ex[o + sj] + Ex[o + sk] + Ex[o + sj + sk]) / 4;
+        s.out[1][q] = (Ey[o] + Ey[o + si] + Ey[o + sk] + Ey[o + si + sk]) / 4;
+        s.out[2][q] = (Ez[o] + Ez[o + si] + Ez[o + sj] + Ez[o + si + sj]) / 4;
+        s.out[3][q] = (Hx[o] + Hx[o + si]) / 2;
+        s.out[4][q] = (Hy[o] + Hy[o + sj]) / 2;
+        s.out[5][q] = (Hz[o] + Hz[o + sk]) / 2;
+    }
+}
+
+// uint32 host IDs -> narrow device IDs with z pitch; records the largest ID seen.
+template <typename IDT>
+__global__ void k_narrow_ids(const uint32_t *src, IDT *dst, long long rows, int nzp1, int pitch, unsigned *maxid)
+{
+    unsigned mx = 0;
+    const long long n = rows * nzp1;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const long long row = q / nzp1;
+        const int k = (int)(q - row * nzp1);
+        const uint32_t v = src[q];
+        dst[row * pitch + k] = (IDT)v;
+        mx = max(mx, v);
+    }
+    if (mx) atomicMax(maxid, mx);
+}
+
+}  // namespace gpb

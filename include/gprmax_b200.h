@@ -1,0 +1,187 @@
+/*
+ * gprmax_b200.h -- C ABI of the B200-native FDTD time-stepping core for gprMax.
+ *
+ * This library replaces the reference's PyCUDA solver path and nothing else:
+ *
+ *   gprMax/model_build_run.py:477-716   solve_gpu()            -> gpb_create / gpb_run / gpb_get_* / gpb_destroy
+ *   gprMax/fields_updates_gpu.py:40-240 update_e / update_h / update_e_dispersive_A,B
+ *   gprMax/pml_updates/pml_updates_{electric,magnetic}_{HORIPML,MRIPML}_gpu.py   (48 slab kernels)
+ *   gprMax/source_updates_gpu.py:38-200 Hertzian dipole / magnetic dipole / voltage source
+ *   gprMax/sources.py:286-452           TransmissionLine (CPU-only in the reference)
+ *   gprMax/fields_outputs.py:67-108     store_outputs (receiver gather, + Ix/Iy/Iz of grid.py:413-461)
+ *   gprMax/snapshots_gpu.py:31-77       store_snapshot (semantics of snapshots.py:87-130 / snapshots_ext.pyx)
+ *   gprMax/grid.py:247-272              FDTDGrid.gpu_* (device arrays, launch geometry)
+ *   gprMax/utilities.py:341-413         GPU / detect_check_gpus -> gpb_device_count / gpb_device_info
+ *
+ * The reference has no FFI for this path (its seam is the Python call
+ * `solve_gpu(currentmodelrun, modelend, G)`); the host side stays Python and binds these entry
+ * points with ctypes (gprmax_b200/_lib.py; INTEGRATION.md shows the two-line patch to the
+ * reference).  Only plain pointers and sizes cross the boundary.
+ *
+ * Conventions
+ *   - All host arrays are C-contiguous and laid out as the reference holds them
+ *     (fields/ID: [nx+1][ny+1][nz+1], z contiguous; grid.py:168-190).  The library copies what it
+ *     needs during gpb_create and keeps no host pointer afterwards.
+ *   - `dtype` selects the floating type R of every `const void*` table and of all outputs:
+ *     GPB_F32 -> float / complex64, GPB_F64 -> double / complex128 (constants.py:36-49).
+ *   - Every function returns 0 on success, non-zero on failure; gpb_last_error() gives the
+ *     message (thread-local).  The library never exits or aborts the process.
+ *   - There is no CPU fallback: without a CUDA device gpb_create fails.
+ *   - x-slab sharding: a handle owns the node planes i in [x_start, x_start + nx_planes) of a
+ *     global grid of nx_global cells; all array arguments then hold ONLY those planes (coordinates
+ *     of sources/receivers/PML slabs stay global).  Single GPU: x_start = 0, nx_planes = nx + 1.
+ */
+#ifndef GPRMAX_B200_H
+#define GPRMAX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPB_ABI_VERSION 1
+
+enum { GPB_F32 = 0, GPB_F64 = 1 };
+enum { GPB_HORIPML = 0, GPB_MRIPML = 1 };                       /* pml.py:155 */
+enum { GPB_XMINUS = 0, GPB_YMINUS, GPB_ZMINUS, GPB_XPLUS, GPB_YPLUS, GPB_ZPLUS }; /* pml.py:163 */
+enum { GPB_SRC_HERTZIAN = 0, GPB_SRC_MAGNETIC = 1, GPB_SRC_VOLTAGE = 2 };
+/* receiver output rows, receivers.py:29 */
+enum { GPB_EX = 0, GPB_EY, GPB_EZ, GPB_HX, GPB_HY, GPB_HZ, GPB_IX, GPB_IY, GPB_IZ, GPB_NRXOUT };
+
+/* utilities.py:341-366 (class GPU) */
+typedef struct gpb_device_info_t {
+    int32_t device_id;
+    char name[256];
+    char pci_bus_id[32];
+    uint64_t total_mem;      /* bytes */
+    uint64_t const_mem;      /* bytes */
+    int32_t sm_count;
+    int32_t cc_major, cc_minor;
+} gpb_device_info_t;
+
+/* One PML slab: pml.py:149-274.  R tables are R[order][thickness]. */
+typedef struct gpb_pml_t {
+    int32_t direction;                 /* GPB_XMINUS .. GPB_ZPLUS */
+    int32_t xs, xf, ys, yf, zs, zf;    /* global cell coordinates of the slab */
+    int32_t thickness;
+    double d;                          /* spacing along the slab axis */
+    const void *ERA, *ERB, *ERE, *ERF;
+    const void *HRA, *HRB, *HRE, *HRF;
+} gpb_pml_t;
+
+/* Point source: source_updates_gpu.py / sources.py:71-232, packed like sources.py:235-283. */
+typedef struct gpb_source_t {
+    int32_t kind;                      /* GPB_SRC_* */
+    int32_t i, j, k;                   /* global node coordinates */
+    int32_t polarisation;              /* 0 x, 1 y, 2 z */
+    int32_t it_first, it_last;         /* inclusive iteration range in which  start <= it*dt <= stop */
+    double param;                      /* Hertzian: dl ; voltage: resistance (0 = hard source) ; magnetic: unused */
+    const void *waveform;              /* R[iterations]: whole-step values (Hertzian, resistive voltage) or
+                                          half-step values (magnetic dipole, hard voltage source) */
+} gpb_source_t;
+
+/* Transmission line: sources.py:286-452, state as left by calculate_incident_V_I (:326-346). */
+typedef struct gpb_tline_t {
+    int32_t i, j, k, polarisation;
+    int32_t it_first, it_last;
+    int32_t nl, srcpos, antpos;
+    double resistance, dl;
+    double abcv0, abcv1;
+    const void *voltage0, *current0;   /* R[nl] initial line state */
+    const void *wave_whole, *wave_half;/* R[iterations] */
+} gpb_tline_t;
+
+/* Snapshot: snapshots.py:28-84.  Output arrays are R[nx][ny][nz] per component. */
+typedef struct gpb_snapshot_t {
+    int32_t xs, ys, zs, xf, yf, zf;
+    int32_t dx, dy, dz;
+    int32_t nx, ny, nz;
+    int32_t time;                      /* taken when time == iteration + 1 (model_build_run.py:430) */
+} gpb_snapshot_t;
+
+typedef struct gpb_model_t {
+    int32_t abi_version;               /* GPB_ABI_VERSION */
+    int32_t dtype;                     /* GPB_F32 / GPB_F64 */
+    int32_t nx, ny, nz;                /* global cells */
+    int32_t x_start, nx_planes;        /* owned node planes (see sharding note above) */
+    double dx, dy, dz, dt;
+    int32_t iterations;
+    int32_t nmaterials;
+    const uint32_t *ID;                /* [6][nx_planes][ny+1][nz+1] */
+    const void *updatecoeffsE;         /* R[nmaterials][5]  materials.py:200 */
+    const void *updatecoeffsH;         /* R[nmaterials][5]  materials.py:201 */
+    int32_t maxpoles;                  /* Material.maxpoles */
+    const void *updatecoeffsdispersive;/* C[nmaterials][3*maxpoles] materials.py:204-208, or NULL */
+    int32_t pml_formulation;           /* GPB_HORIPML / GPB_MRIPML */
+    int32_t pml_order;                 /* len(G.cfs): 1 or 2 */
+    int32_t npml;
+    const gpb_pml_t *pmls;             /* in G.pmls order (x0,y0,z0,xmax,ymax,zmax; grid.py:132-136) */
+    int32_t nsources;
+    const gpb_source_t *sources;       /* applied in array order within each kind */
+    int32_t ntlines;
+    const gpb_tline_t *tlines;
+    int32_t nrx;
+    const int32_t *rxcoords;           /* int32[nrx][3] global node coordinates */
+    int32_t nsnapshots;
+    const gpb_snapshot_t *snapshots;
+} gpb_model_t;
+
+typedef struct gpb_solver *gpb_handle;
+
+/* ---- device discovery (utilities.py:369-413) ---- */
+int gpb_device_count(int *count);
+int gpb_device_info(int device_id, gpb_device_info_t *out);
+
+/* ---- lifetime ---- */
+int gpb_create(const gpb_model_t *model, int device_id, gpb_handle *out);
+int gpb_destroy(gpb_handle h);
+
+/* ---- time loop (model_build_run.py:590-696) ----
+ * gpb_run advances `n_iters` full iterations (rx store, snapshots, H half, E half) starting at the
+ * handle's current iteration; the loop time accumulates in gpb_elapsed_seconds (CUDA events,
+ * as the reference times it, :586-588/:708-710). */
+int gpb_run(gpb_handle h, int n_iters);
+int gpb_iteration(gpb_handle h, int *iteration);
+int gpb_elapsed_seconds(gpb_handle h, double *seconds);
+int gpb_mem_used(gpb_handle h, uint64_t *bytes);        /* device bytes owned by this handle */
+int gpb_kernel_launches(gpb_handle h, uint64_t *count); /* kernels launched by gpb_run/gpb_half_step so far */
+int gpb_reset(gpb_handle h);                            /* zero fields / PML / T / rx, iteration = 0 */
+/* Measurement aid: advance n_iters iterations with plain launches and CUDA events between the
+ * kernels; ms4 = device milliseconds {step prologue, H update, E update, source kernels} summed. */
+int gpb_profile(gpb_handle h, int n_iters, double *ms4);
+
+/* ---- sharded stepping (one handle per x-slab; the host moves the halo planes between calls) ----
+ * phase 0: rx store + snapshots + H half-step (needs the Ey,Ez ghost plane at x_start+nx_planes)
+ * phase 1: E half-step                        (needs the Hy,Hz ghost plane at x_start-1)       */
+int gpb_half_step(gpb_handle h, int phase);
+/* Device pointers (and byte size) of the contiguous halo planes:
+ * which = 0: send  E (Ey then Ez, first owned plane)      -> left neighbour's recv E
+ * which = 1: recv  E (Ey then Ez, ghost plane after last)
+ * which = 2: send  H (Hy then Hz, last owned plane)       -> right neighbour's recv H
+ * which = 3: recv  H (Hy then Hz, ghost plane before first) */
+int gpb_halo(gpb_handle h, int which, void **dptr_a, void **dptr_b, size_t *bytes_each);
+int gpb_stream(gpb_handle h, void **cuda_stream);
+int gpb_synchronize(gpb_handle h);
+
+/* ---- results ---- */
+/* out: R[GPB_NRXOUT][iterations][nrx] (rows of fields_outputs.py:81-105 + Ix,Iy,Iz).  For a shard,
+ * receivers outside the owned planes are left zero. */
+int gpb_get_receivers(gpb_handle h, void *out, size_t out_bytes);
+/* out: 6 arrays R[nx][ny][nz] (Ex,Ey,Ez,Hx,Hy,Hz cell-centred averages) of snapshot `index`. */
+int gpb_get_snapshot(gpb_handle h, int index, void *out6[6], size_t bytes_each);
+/* out: R[iterations] total voltage / current of transmission line `index` (fields_outputs.py:62-64) */
+int gpb_get_tline(gpb_handle h, int index, void *vtotal, void *itotal, size_t bytes_each);
+/* Debug/parity: copy one field component (GPB_EX..GPB_HZ) back in the host layout
+ * R[nx_planes][ny+1][nz+1]; gpb_set_field is the inverse (tests seed random fields). */
+int gpb_get_field(gpb_handle h, int component, void *out, size_t out_bytes);
+int gpb_set_field(gpb_handle h, int component, const void *in, size_t in_bytes);
+
+const char *gpb_last_error(void);
+const char *gpb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPRMAX_B200_H */

@@ -1,0 +1,98 @@
+"""GPU parity: the CUDA core (through the C ABI, via the drop-in solve_gpu) against
+  * the golden vectors written by the UNMODIFIED reference CPU solver (tests/golden/*.npz), and
+  * the CPU oracle run here on the same model.
+Every fixture covers a different part of the hot path: 2-D modes, 3-D,
+HORIPML/MRIPML orders 1-2, dispersive 1-pole/multi-pole, magnetic dipole / voltage sources /
+transmission line, Ix-Iz receivers, snapshots, 50-material fractal soil.
+float64: <= 1e-10 of trace peak.  float32: see parity.compare_f32_with_truth.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, golden_path
+from parity import collect_outputs, compare_f32_with_truth, compare_traces, oracle_outputs_as_golden, tolerance
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(G):
+    from gprmax_b200 import GPU, solve_gpu
+    G.gpu = GPU(0)
+    tsolve, mem = solve_gpu(1, 1, G)
+    assert tsolve > 0 and mem > 0
+    return collect_outputs(G)
+
+
+@pytest.mark.parametrize('name', golden_names('f64'))
+def test_f64_against_reference_golden(name):
+    from gprmax_b200.model_io import load_model
+    G, golden = load_model(golden_path(name, 'f64'))
+    out = _solve(G)
+    worst, rep = compare_traces(out, golden, np.float64, tol=tolerance(G, np.float64))
+    print(rep)
+    assert worst <= 1.0, rep
+
+
+@pytest.mark.parametrize('name', golden_names('f32'))
+def test_f32_against_reference_golden(name):
+    from gprmax_b200.model_io import load_model
+    G, golden = load_model(golden_path(name, 'f32'))
+    out = _solve(G)
+    if os.path.exists(golden_path(name, 'f64')):
+        _, golden64 = load_model(golden_path(name, 'f64'))
+        ok, rep = compare_f32_with_truth(out, golden, golden64)
+        print(rep)
+        assert ok, rep
+    else:
+        worst, rep = compare_traces(out, golden, np.float32)
+        print(rep)
+        assert worst <= 1.0, rep
+
+
+@pytest.mark.parametrize('name,variant', [('pml_HORIPML_1', 'f64'), ('pml_MRIPML_2', 'f64'), ('sources_mixed', 'f64'),
+                                          ('dispersive_multipole', 'f64'), ('cylinder_Ascan_2D', 'f64'),
+                                          ('transmission_line', 'f64'), ('pml_HORIPML_2', 'f32'), ('snapshots', 'f32')])
+def test_against_oracle_run_here(name, variant, oracle_built):
+    """Same model through the CUDA core and through oracle/ on this box (no stored vectors)."""
+    from gprmax_b200.model_io import load_model
+    from oracle.solver import solve_cpu
+    G, _ = load_model(golden_path(name, variant))
+    ref = oracle_outputs_as_golden(G, solve_cpu(G, kernels='oracle'))
+    out = _solve(G)
+    real = np.float64 if variant == 'f64' else np.float32
+    worst, rep = compare_traces(out, ref, real, tol=tolerance(G, real))
+    print(rep)
+    assert worst <= 1.0, rep
+
+
+def test_final_fields_match_oracle(oracle_built):
+    """Whole-volume check (not just receiver points): final E/H of a PML + dielectric model in float64."""
+    from gprmax_b200 import Solver
+    from gprmax_b200.model_io import load_model
+    from oracle.solver import solve_cpu
+    G, _ = load_model(golden_path('pml_MRIPML_2', 'f64'))
+    S = solve_cpu(G, kernels='oracle', keep_state=True)['state']
+    with Solver(G, device_id=0) as sv:
+        sv.run()
+        for c, n in enumerate(('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz')):
+            dev = sv.get_field(c)
+            ref = getattr(S, n)
+            assert np.abs(dev - ref).max() <= 1e-10 * np.abs(ref).max(), n
+
+
+def test_restart_and_chunked_run_bit_identical():
+    """gpb_reset + running in chunks reproduces a single run bit for bit (graph replay vs plain launches)."""
+    from gprmax_b200 import Solver
+    from gprmax_b200.model_io import load_model
+    G, _ = load_model(golden_path('sources_mixed', 'f32'))
+    with Solver(G, device_id=0) as sv:
+        sv.run()
+        a = sv.receivers()
+        sv.reset()
+        for n in (1, 7, 100, G.iterations - 108):
+            sv.run(n)
+        b = sv.receivers()
+        assert sv.kernel_launches > 0
+    assert np.array_equal(a, b)
