@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, 'libgprmax_b200.so')
+LIBPATH = os.environ.get('GPB_LIB') or os.path.join(HERE, 'libgprmax_b200.so')
 
 GPB_ABI_VERSION = 1
 GPB_F32, GPB_F64 = 0, 1

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgprmax_b200.so')
 SOURCES = ['gpb_core.cu']
-DEPS = ['gpb_core.cu', 'gpb_kernels.cuh', os.path.join('..', '..', 'include', 'gprmax_b200.h')]
+DEPS = ['gpb_core.cu', 'gpb_kernels.cuh', 'gpb_kernels_v4.cuh', 'gpb_kernels_tma.cuh', os.path.join('..', '..', 'include', 'gprmax_b200.h')]
 
 
 def nvcc_path():

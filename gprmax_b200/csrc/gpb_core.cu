@@ -6,6 +6,8 @@
 // needs a CUDA device and reports an error otherwise.
 #include "../../include/gprmax_b200.h"
 #include "gpb_kernels.cuh"
+#include "gpb_kernels_v4.cuh"
+#include "gpb_kernels_tma.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -69,6 +71,17 @@ struct Solver : SolverBase {
     long long plane, narr;  // elements per plane / per padded array (nplanes+2 planes)
     int idbytes;
     bool tabsmem;
+    bool use_v4 = false;       // vectorised non-dispersive path (gpb_kernels_v4.cuh)
+    bool use_tma = false;      // TMA-staged path (gpb_kernels_tma.cuh)
+    int tma_ty = 0, tma_tz = 0, tma_stages = 0, tma_xchunk = 16;
+    TmaMaps9 maps_e, maps_h;
+    int setup_tma();
+    template <typename IDT, int TY, int TZ, int S>
+    int launch_tma_cfg(int phase, int p0, int p1);
+    template <typename IDT>
+    int launch_tma(int phase, int p0, int p1);
+    unsigned zslabs_e = 0, zslabs_h = 0;  // z slabs (bit per slab) handled by k_pml_slabs on the v4 path
+    uint64_t graph_launches = 0;
     size_t smem_bytes;
     // device memory
     std::vector<void *> allocs;
@@ -96,6 +109,7 @@ struct Solver : SolverBase {
     PhaseParams<R> ph_h, ph_e;
     PointParams<R> pp;
     std::vector<std::pair<R *, size_t>> phis;
+    bool v4_ok = true;
     // graph
     cudaGraphExec_t graph = nullptr;
     bool use_graph = true;
@@ -167,9 +181,41 @@ struct Solver : SolverBase {
 
 static int choose_pitch(int nzp1)
 {
-    // rows start on a 128-byte line when the row is long enough to make that worthwhile
+    // rows start on a 128-byte line when the row is long enough to make that worthwhile; always a
+    // multiple of 16 elements so that even 1-byte ID rows satisfy the 16-byte stride rule of TMA
     if (nzp1 >= 48) return (nzp1 + 31) / 32 * 32;
-    return (nzp1 + 7) / 8 * 8;
+    return (nzp1 + 15) / 16 * 16;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D map over a padded array [planes][rows][pitch] with a (b0 x b1 x 1) box
+static int make_map(CUtensorMap *out, void *base, CUtensorMapDataType dt, size_t es, int pitch, int rows, int planes, int b0, int b1)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * rows * es};
+    const cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code %d (pitch %d rows %d planes %d box %d x %d)", (int)r, pitch, rows, planes, b0, b1);
+    return 0;
 }
 
 template <typename R>
@@ -283,7 +329,10 @@ int Solver<R>::setup_pml(const gpb_model_t &m)
             if (sd.hi[0] <= sd.lo[0]) continue;
             const long long n0 = sd.hi[0] - sd.lo[0];
             sd.n1 = sd.hi[1] - sd.lo[1];
-            sd.n2 = sd.hi[2] - sd.lo[2];
+            // x / y slabs: Phi rows padded to the field pitch so the vectorised kernels can use aligned
+            // 128-bit accesses; z slabs: compact rows of `thickness` cells
+            sd.n2 = (axis != 2 && sd.lo[2] == 0) ? pitch : sd.hi[2] - sd.lo[2];
+            if (axis != 2 && sd.lo[2] != 0) v4_ok = false;
             sd.ostride = n0 * sd.n1 * sd.n2;
             R *phi = nullptr;
             const size_t nphi = (size_t)sd.ostride * 2 * order;
@@ -453,6 +502,17 @@ int Solver<R>::build(const gpb_model_t &m)
     for (int c = 0; c < 3; ++c) ph_e.T[c] = T[c];
     set_boxes();
     if (setup_pml(m)) return 1;
+    // vectorised path: non-dispersive models (dispersive ones keep the generic scalar kernels)
+    use_v4 = v4_ok && maxpoles == 0 && !getenv("GPB_SCALAR");
+    // TMA-staged path: 3-D grids with reasonably long z rows (2-D / thin grids stay on the flattened v4 path)
+    use_tma = use_v4 && nz + 1 >= 32 && ny + 1 >= 8 && !getenv("GPB_NO_TMA") && (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R)) <= 32 * 1024;
+    if (use_tma && setup_tma()) return 1;
+    if (use_v4) {
+        for (int s = 0; s < ph_e.nslabs; ++s)
+            if (ph_e.slab[s].axis == 2) zslabs_e |= 1u << s;
+        for (int s = 0; s < ph_h.nslabs; ++s)
+            if (ph_h.slab[s].axis == 2) zslabs_h |= 1u << s;
+    }
 
     memset(&pp, 0, sizeof pp);
     pp.x_start = x_start; pp.nplanes = nplanes; pp.ny = ny; pp.nz = nz; pp.pitch = pitch; pp.plane = plane;
@@ -466,11 +526,133 @@ int Solver<R>::build(const gpb_model_t &m)
 
 // ------------------------------------------------------------------------------------------ launches
 template <typename R>
+int Solver<R>::setup_tma()
+{
+    // tile shape: 256 threads x 4 cells; pick the shape that wastes the fewest lanes on this grid
+    const int cand[3][2] = {{32, 32}, {16, 64}, {8, 128}};
+    double best = 1e30;
+    for (auto &c : cand) {
+        const double waste = (double)((ny + 1 + c[0] - 1) / c[0] * c[0]) * ((pitch + c[1] - 1) / c[1] * c[1]) / ((double)(ny + 1) * (nz + 1));
+        if (waste < best - 1e-9) { best = waste; tma_ty = c[0]; tma_tz = c[1]; }
+    }
+    if (getenv("GPB_TMA_TZ")) { tma_tz = atoi(getenv("GPB_TMA_TZ")); tma_ty = 1024 / tma_tz; }
+    tma_stages = getenv("GPB_TMA_STAGES") ? atoi(getenv("GPB_TMA_STAGES")) : 3;
+    const CUtensorMapDataType fdt = sizeof(R) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    const CUtensorMapDataType idt = idbytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (idbytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32);
+    const int rows = ny + 1, planes = nplanes + 2, TY = tma_ty, TZ = tma_tz;
+    // E phase: operands Hx (both halos), Hy (k halo), Hz (j halo); own Ex,Ey,Ez
+    if (make_map(&maps_e.opA, F[3], fdt, sizeof(R), pitch, rows, planes, TZ + 4, TY + 1) ||
+        make_map(&maps_e.opB, F[4], fdt, sizeof(R), pitch, rows, planes, TZ + 4, TY) ||
+        make_map(&maps_e.opC, F[5], fdt, sizeof(R), pitch, rows, planes, TZ, TY + 1) ||
+        make_map(&maps_e.own0, F[0], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_e.own1, F[1], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_e.own2, F[2], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_e.id0, ID[0], idt, idbytes, pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_e.id1, ID[1], idt, idbytes, pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_e.id2, ID[2], idt, idbytes, pitch, rows, planes, TZ, TY))
+        return 1;
+    // H phase: operands Ex, Ey, Ez; own Hx,Hy,Hz
+    if (make_map(&maps_h.opA, F[0], fdt, sizeof(R), pitch, rows, planes, TZ + 4, TY + 1) ||
+        make_map(&maps_h.opB, F[1], fdt, sizeof(R), pitch, rows, planes, TZ + 4, TY) ||
+        make_map(&maps_h.opC, F[2], fdt, sizeof(R), pitch, rows, planes, TZ, TY + 1) ||
+        make_map(&maps_h.own0, F[3], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_h.own1, F[4], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_h.own2, F[5], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_h.id0, ID[3], idt, idbytes, pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_h.id1, ID[4], idt, idbytes, pitch, rows, planes, TZ, TY) ||
+        make_map(&maps_h.id2, ID[5], idt, idbytes, pitch, rows, planes, TZ, TY))
+        return 1;
+    // planes per CTA: short marches (8 planes) measured best on B200 -- many CTAs keep the two resident
+    // CTAs per SM out of phase so one computes while the other's pipeline fills; shorter still when the
+    // grid would otherwise have fewer than ~6 waves
+    cudaDeviceProp pr;
+    CK(cudaGetDeviceProperties(&pr, device));
+    const long long tiles = (long long)((ny + 1 + TY - 1) / TY) * ((pitch + TZ - 1) / TZ);
+    tma_xchunk = 8;
+    while (tma_xchunk > 2 && tiles * ((nplanes + tma_xchunk - 1) / tma_xchunk) < 12ll * pr.multiProcessorCount) tma_xchunk /= 2;
+    if (getenv("GPB_TMA_XCHUNK")) tma_xchunk = std::max(1, atoi(getenv("GPB_TMA_XCHUNK")));
+    return 0;
+}
+
+template <typename R>
+template <typename IDT, int TY, int TZ, int S>
+int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
+{
+    using L = StageLayout<R, IDT, TY, TZ>;
+    PhaseParams<R> p = phase == 0 ? ph_h : ph_e;
+    p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk;
+    const int tiles_k = (pitch + TZ - 1) / TZ, tiles_j = (ny + 1 + TY - 1) / TY;
+    const size_t smem = 128 + (size_t)((nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128) + (size_t)S * L::bytes;
+    dim3 grid((unsigned)(tiles_k * tiles_j), (unsigned)((p1 - p0 + tma_xchunk - 1) / tma_xchunk));
+    if (phase == 0) {
+        auto kern = k_update_tma<R, IDT, TY, TZ, S, 0>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTmaThreads, smem, stream>>>(p, maps_h, tiles_k);
+    } else {
+        auto kern = k_update_tma<R, IDT, TY, TZ, S, 1>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kTmaThreads, smem, stream>>>(p, maps_e, tiles_k);
+    }
+    CK(cudaGetLastError());
+    ++launches;
+    const unsigned zs = phase == 0 ? zslabs_h : zslabs_e;
+    if (zs) {
+        int cells = 0, planes = 0;
+        for (int s = 0; s < p.nslabs; ++s)
+            if ((zs >> s) & 1u) {
+                cells = std::max(cells, (p.slab[s].hi[1] - p.slab[s].lo[1]) * (p.slab[s].hi[2] - p.slab[s].lo[2]));
+                planes = std::max(planes, p.slab[s].hi[0] - p.slab[s].lo[0]);
+            }
+        dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes);
+        k_pml_slabs<R, IDT><<<g2, 256, 0, stream>>>(p, phase, zs, p0, p1);
+        CK(cudaGetLastError());
+        ++launches;
+    }
+    return 0;
+}
+
+template <typename R>
+template <typename IDT>
+int Solver<R>::launch_tma(int phase, int p0, int p1)
+{
+#define GPB_TMA_CASE(TY_, TZ_, S_) if (tma_ty == TY_ && tma_tz == TZ_ && tma_stages == S_) return launch_tma_cfg<IDT, TY_, TZ_, S_>(phase, p0, p1)
+    GPB_TMA_CASE(16, 64, 4);
+    GPB_TMA_CASE(16, 64, 3);
+    GPB_TMA_CASE(16, 64, 6);
+    GPB_TMA_CASE(8, 128, 4);
+    GPB_TMA_CASE(8, 128, 3);
+    GPB_TMA_CASE(32, 32, 4);
+    GPB_TMA_CASE(32, 32, 3);
+#undef GPB_TMA_CASE
+    return fail("no TMA kernel instantiated for tile %d x %d with %d stages", tma_ty, tma_tz, tma_stages);
+}
+
+template <typename R>
 template <typename IDT>
 int Solver<R>::launch_h(int p0, int p1)
 {
     PhaseParams<R> p = ph_h;
     p.p0 = p0; p.p1 = p1;
+    if (use_v4) {
+        dim3 grid((unsigned)((plane / 4 + kThreadsV4 - 1) / kThreadsV4), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
+        if (tabsmem) k_update_h4<R, IDT, true><<<grid, kThreadsV4, smem_bytes, stream>>>(p);
+        else k_update_h4<R, IDT, false><<<grid, kThreadsV4, 0, stream>>>(p);
+        CK(cudaGetLastError());
+        ++launches;
+        if (zslabs_h) {
+            int cells = 0, planes = 0;
+            for (int s = 0; s < p.nslabs; ++s)
+                if ((zslabs_h >> s) & 1u) {
+                    cells = std::max(cells, (p.slab[s].hi[1] - p.slab[s].lo[1]) * (p.slab[s].hi[2] - p.slab[s].lo[2]));
+                    planes = std::max(planes, p.slab[s].hi[0] - p.slab[s].lo[0]);
+                }
+            dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes);
+            k_pml_slabs<R, IDT><<<g2, 256, 0, stream>>>(p, 0, zslabs_h, p0, p1);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        return 0;
+    }
     dim3 grid((unsigned)((plane + kThreads - 1) / kThreads), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
     if (tabsmem) k_update_h<R, IDT, true><<<grid, kThreads, smem_bytes, stream>>>(p);
     else k_update_h<R, IDT, false><<<grid, kThreads, 0, stream>>>(p);
@@ -485,6 +667,26 @@ int Solver<R>::launch_e(int p0, int p1)
 {
     PhaseParams<R> p = ph_e;
     p.p0 = p0; p.p1 = p1;
+    if (use_v4) {
+        dim3 grid((unsigned)((plane / 4 + kThreadsV4 - 1) / kThreadsV4), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
+        if (tabsmem) k_update_e4<R, IDT, true><<<grid, kThreadsV4, smem_bytes, stream>>>(p);
+        else k_update_e4<R, IDT, false><<<grid, kThreadsV4, 0, stream>>>(p);
+        CK(cudaGetLastError());
+        ++launches;
+        if (zslabs_e) {
+            int cells = 0, planes = 0;
+            for (int s = 0; s < p.nslabs; ++s)
+                if ((zslabs_e >> s) & 1u) {
+                    cells = std::max(cells, (p.slab[s].hi[1] - p.slab[s].lo[1]) * (p.slab[s].hi[2] - p.slab[s].lo[2]));
+                    planes = std::max(planes, p.slab[s].hi[0] - p.slab[s].lo[0]);
+                }
+            dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes);
+            k_pml_slabs<R, IDT><<<g2, 256, 0, stream>>>(p, 1, zslabs_e, p0, p1);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        return 0;
+    }
     dim3 grid((unsigned)((plane + kThreads - 1) / kThreads), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
     if (maxpoles) {
         if (tabsmem) k_update_e<R, IDT, true, true><<<grid, kThreads, smem_bytes, stream>>>(p);
@@ -502,6 +704,11 @@ template <typename R>
 int Solver<R>::launch_phase(int phase, int p0, int p1)
 {
     if (p1 <= p0) return 0;
+    if (use_tma) {
+        if (idbytes == 1) return launch_tma<uint8_t>(phase, p0, p1);
+        if (idbytes == 2) return launch_tma<uint16_t>(phase, p0, p1);
+        return launch_tma<uint32_t>(phase, p0, p1);
+    }
     if (phase == 0) {
         if (idbytes == 1) return launch_h<uint8_t>(p0, p1);
         if (idbytes == 2) return launch_h<uint16_t>(p0, p1);
@@ -567,6 +774,12 @@ int Solver<R>::run(int n)
     if (n < 0 || iteration + n > iterations) return fail("cannot run %d iterations from %d: model has %d", n, iteration, iterations);
     if (tabsmem && smem_bytes > 48 * 1024) {
         // opt in to large dynamic shared memory for the coefficient rows
+        cudaFuncSetAttribute(k_update_h4<R, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_h4<R, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_h4<R, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e4<R, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e4<R, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e4<R, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cudaFuncSetAttribute(k_update_h<R, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cudaFuncSetAttribute(k_update_h<R, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cudaFuncSetAttribute(k_update_h<R, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
@@ -585,18 +798,18 @@ int Solver<R>::run(int n)
         CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         int rc = enqueue_step(false);
         cudaError_t e = cudaStreamEndCapture(stream, &g);
+        graph_launches = launches - l0;
         launches = l0;
         if (rc) return 1;
         if (e != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(e));
         CK(cudaGraphInstantiate(&graph, g, 0));
         cudaGraphDestroy(g);
     }
-    const uint64_t per_step = 2 + 1 + (has_hsrc ? 1 : 0) + (has_esrc ? 1 : 0);
     CK(cudaEventRecord(ev0, stream));
     for (int s = 0; s < n; ++s) {
         if (graph && !snapshot_due(iteration)) {
             CK(cudaGraphLaunch(graph, stream));
-            launches += per_step;
+            launches += graph_launches;
         } else if (enqueue_step(true)) {
             return 1;
         }

@@ -84,6 +84,7 @@ struct PhaseParams {
     long long tstride;        // elements between poles
     // sub-range of owned planes processed by this launch (for halo overlap): [p0, p1)
     int p0, p1;
+    int xchunk;               // planes marched by one CTA of the TMA kernels
 };
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,536 @@
+// gpb_kernels_v4.cuh -- vectorised E/H half-step kernels (non-dispersive fast path).
+//
+// Same arithmetic as k_update_e / k_update_h in gpb_kernels.cuh (which remain the generic path for
+// dispersive materials), restructured after the first ncu capture (profiles/r1a_*): the scalar
+// kernels executed ~400 instructions per cell (index decode, 9 box tests and 64-bit addressing per
+// cell) and were issue-bound at 29 % of DRAM bandwidth.  Here
+//   * one thread owns 4 consecutive z cells: every field/ID/Phi access is one 128-bit (fp32) load,
+//     and the index / box / slab logic is paid once per 4 cells;
+//   * the k+-1 operands come from the neighbouring lane by warp shuffle (one scalar load on the
+//     warp-edge lane only);
+//   * the march along x keeps the i+1 (H phase) / i-1 (E phase) operand planes in a register queue;
+//   * x- and y-slab PML corrections are warp-uniform (depth depends on i or j only) and vectorised;
+//     z-slab corrections, which would diverge in every warp (10 cells at both ends of every row), run
+//     in their own small kernel (k_pml_slabs) right after the main one.
+#pragma once
+#include "gpb_kernels.cuh"
+
+namespace gpb {
+
+#ifndef GPB_V4_THREADS
+#define GPB_V4_THREADS 128
+#endif
+#ifndef GPB_V4_MINBLOCKS
+#define GPB_V4_MINBLOCKS 4
+#endif
+#ifndef GPB_V4_UNROLL
+#define GPB_V4_UNROLL 1
+#endif
+constexpr int kThreadsV4 = GPB_V4_THREADS;
+constexpr int kV4Unroll = GPB_V4_UNROLL;
+
+template <typename R>
+struct alignas(4 * sizeof(R)) V4 {
+    R x, y, z, w;
+};
+
+template <typename R>
+__device__ __forceinline__ V4<R> ld4(const R *p)
+{
+    return *reinterpret_cast<const V4<R> *>(p);
+}
+template <typename R>
+__device__ __forceinline__ void st4(R *p, const V4<R> &v)
+{
+    *reinterpret_cast<V4<R> *>(p) = v;
+}
+
+struct Ids4 {
+    unsigned a, b, c, d;
+};
+template <typename IDT>
+__device__ __forceinline__ Ids4 ld_ids4(const void *base, long long off);
+template <>
+__device__ __forceinline__ Ids4 ld_ids4<uint8_t>(const void *base, long long off)
+{
+    const unsigned v = __ldg(reinterpret_cast<const unsigned *>(reinterpret_cast<const uint8_t *>(base) + off));
+    return {v & 0xffu, (v >> 8) & 0xffu, (v >> 16) & 0xffu, v >> 24};
+}
+template <>
+__device__ __forceinline__ Ids4 ld_ids4<uint16_t>(const void *base, long long off)
+{
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(base) + off));
+    return {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16};
+}
+template <>
+__device__ __forceinline__ Ids4 ld_ids4<uint32_t>(const void *base, long long off)
+{
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(base) + off));
+    return {v.x, v.y, v.z, v.w};
+}
+
+// per-thread, loop-invariant description of where its 4 cells sit relative to a box
+struct JK4 {
+    bool j_in;
+    unsigned kmask;  // bit q set: cell k+q inside the box's k range
+};
+__device__ __forceinline__ JK4 jk4_of(const int *lo, const int *hi, int j, int k)
+{
+    JK4 r;
+    r.j_in = j >= lo[1] && j < hi[1];
+    r.kmask = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (k + q >= lo[2] && k + q < hi[2]) r.kmask |= 1u << q;
+    if (!r.j_in) r.kmask = 0;
+    return r;
+}
+
+template <typename R>
+__device__ __forceinline__ R sel(unsigned mask, int q, R a, R b)
+{
+    return (mask >> q) & 1u ? a : b;
+}
+
+// coefficient set of one PML depth, read once per thread (cf. pml_term in gpb_kernels.cuh)
+template <typename R>
+struct PmlCo {
+    R a, b, c, d, e, f, g, h, r;
+};
+template <typename R>
+__device__ __forceinline__ PmlCo<R> pml_load(int form, int order, const SlabDev<R> &s, int depth)
+{
+    PmlCo<R> c;
+    const R one = (R)1;
+    if (form == 0) {
+        if (order == 1) {
+            c.a = __ldg(s.RA + depth) - one;  // RA01
+            c.b = __ldg(s.RB + depth);
+            c.e = __ldg(s.RE + depth);
+            c.f = __ldg(s.RF + depth);
+        } else {
+            const R RA0 = __ldg(s.RA + depth), RA1 = __ldg(s.RA + s.t + depth);
+            c.a = RA0 * RA1 - one;  // RA01
+            c.b = __ldg(s.RB + depth);
+            c.e = __ldg(s.RE + depth);
+            c.f = __ldg(s.RF + depth);
+            c.c = RA0;
+            c.d = RA1;
+            c.g = __ldg(s.RB + s.t + depth);
+            c.h = __ldg(s.RE + s.t + depth);
+            c.r = __ldg(s.RF + s.t + depth);
+        }
+    } else {
+        if (order == 1) {
+            const R IRA = one / __ldg(s.RA + depth);
+            c.a = IRA;
+            c.b = IRA - one;
+            c.c = IRA * __ldg(s.RB + depth) * __ldg(s.RF + depth);  // RC0
+            c.e = __ldg(s.RE + depth);
+        } else {
+            const R IRA = one / (__ldg(s.RA + depth) + __ldg(s.RA + s.t + depth));
+            c.a = IRA;
+            c.b = IRA - one;
+            c.c = IRA * __ldg(s.RF + depth);
+            c.d = IRA * __ldg(s.RF + s.t + depth);
+            c.e = __ldg(s.RE + depth);
+            c.h = __ldg(s.RE + s.t + depth);
+            c.f = __ldg(s.RB + depth);
+            c.g = __ldg(s.RB + s.t + depth);
+        }
+    }
+    return c;
+}
+// same expressions as pml_term(); phi0/phi1 are updated in registers
+template <typename R>
+__device__ __forceinline__ R pml_apply(int form, int order, const PmlCo<R> &c, R dF, R &phi0, R &phi1)
+{
+    R term;
+    if (form == 0) {
+        if (order == 1) {
+            term = c.a * dF + c.b * phi0;
+            phi0 = c.e * phi0 - c.f * dF;
+        } else {
+            term = c.a * dF + c.d * c.b * phi0 + c.g * phi1;
+            phi1 = c.h * phi1 - c.r * (c.c * dF + c.b * phi0);
+            phi0 = c.e * phi0 - c.f * dF;
+        }
+    } else {
+        if (order == 1) {
+            term = c.b * dF - c.a * phi0;
+            phi0 = c.e * phi0 + c.c * dF - c.c * phi0;
+        } else {
+            const R psi = c.f * phi0 + c.g * phi1;
+            term = c.b * dF - c.a * psi;
+            phi1 = c.h * phi1 + c.d * (dF - psi);
+            phi0 = c.e * phi0 + c.c * (dF - psi);
+        }
+    }
+    return term;
+}
+
+// One vectorised PML component: F (4 cells) -= / += src[id] * term(dF / d), Phi advanced.
+// sign = +1 / -1.  `m` = lanes (cells) inside the slab.
+template <typename R>
+__device__ __forceinline__ void pml_comp4(int form, int order, const PmlCo<R> &co, const SlabDev<R> &sl, R *phi, unsigned m,
+                                          const Ids4 &id, const R *src, R sign, const V4<R> &dF, V4<R> &F)
+{
+    V4<R> p0 = ld4(phi), p1 = p0;
+    if (order == 2) p1 = ld4(phi + 2 * sl.ostride);
+    V4<R> q0 = p0, q1 = p1;
+    const R tx = pml_apply(form, order, co, dF.x / sl.d, q0.x, q1.x);
+    const R ty = pml_apply(form, order, co, dF.y / sl.d, q0.y, q1.y);
+    const R tz = pml_apply(form, order, co, dF.z / sl.d, q0.z, q1.z);
+    const R tw = pml_apply(form, order, co, dF.w / sl.d, q0.w, q1.w);
+    if (m & 1u) { F.x = F.x + sign * (src[id.a] * tx); p0.x = q0.x; p1.x = q1.x; }
+    if (m & 2u) { F.y = F.y + sign * (src[id.b] * ty); p0.y = q0.y; p1.y = q1.y; }
+    if (m & 4u) { F.z = F.z + sign * (src[id.c] * tz); p0.z = q0.z; p1.z = q1.z; }
+    if (m & 8u) { F.w = F.w + sign * (src[id.d] * tw); p0.w = q0.w; p1.w = q1.w; }
+    st4(phi, p0);
+    if (order == 2) st4(phi + 2 * sl.ostride, p1);
+}
+
+template <typename R>
+__device__ __forceinline__ void coef4(const Coef4<R> *coef, const Ids4 &id, Coef4<R> &c0, Coef4<R> &c1, Coef4<R> &c2, Coef4<R> &c3)
+{
+    c0 = coef[id.a];
+    if (id.a == id.b && id.a == id.c && id.a == id.d) {
+        c1 = c2 = c3 = c0;
+    } else {
+        c1 = coef[id.b];
+        c2 = coef[id.c];
+        c3 = coef[id.d];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Magnetic half-step, 4 z cells per thread.  Arithmetic: fields_updates_ext.pyx:352-412 and
+// pml_updates_magnetic_*_ext.pyx (x and y slabs).
+// ------------------------------------------------------------------------------------------
+template <typename R, typename IDT, bool TABSMEM>
+__global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(const PhaseParams<R> p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Coef4<R> *coef = p.coef;
+    const R *srcm = p.src;
+    if (TABSMEM) {
+        Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw);
+        R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
+        stage_coefs(p, scoef, ssrc);
+        coef = scoef;
+        srcm = ssrc;
+    }
+    const long long idx4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e0 = idx4 * 4;
+    const bool valid = e0 < p.plane;
+    const long long eoff = valid ? e0 : 0;
+    const int j = (int)(eoff / p.pitch);
+    const int k = (int)(eoff - (long long)j * p.pitch);
+    const int lane = threadIdx.x & 31;
+    const int l0 = p.p0 + blockIdx.y * kXChunk;
+    const int l1 = min(l0 + kXChunk, p.p1);
+    if (l0 >= l1) return;
+    const JK4 bx = jk4_of(p.box[0].lo, p.box[0].hi, j, k), by = jk4_of(p.box[1].lo, p.box[1].hi, j, k), bz = jk4_of(p.box[2].lo, p.box[2].hi, j, k);
+    // x / y slabs: which of my cells lie in the slab's (j,k) footprint (z slabs are handled by k_pml_slabs)
+    unsigned smask = 0;  // 4 bits per slab
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s)
+        if (s < p.nslabs && p.slab[s].axis != 2 && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
+    const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u);
+
+    // E is read-only in this phase and never aliases H: tell the compiler so that the loads of the
+    // next plane can be hoisted above the stores of this one
+    const R *__restrict__ Ex = p.Ex;
+    const R *__restrict__ Ey = p.Ey;
+    const R *__restrict__ Ez = p.Ez;
+    R *__restrict__ Hx = p.Hx;
+    R *__restrict__ Hy = p.Hy;
+    R *__restrict__ Hz = p.Hz;
+    long long off = (long long)(l0 + 1) * p.plane + eoff;
+    V4<R> ey_c = ld4(Ey + off), ez_c = ld4(Ez + off);
+#pragma unroll kV4Unroll
+    for (int l = l0; l < l1; ++l, off += p.plane) {
+        const int i = p.x_start + l;
+        const V4<R> ey_n = ld4(Ey + off + p.plane), ez_n = ld4(Ez + off + p.plane);
+        const V4<R> ex_c = ld4(Ex + off);
+        const V4<R> ex_j = ld4(Ex + off + p.pitch), ez_j = ld4(Ez + off + p.pitch);
+        // k+1 operands: next lane's .x (scalar load on the warp-edge lane)
+        R ex_k4 = __shfl_down_sync(0xffffffffu, ex_c.x, 1), ey_k4 = __shfl_down_sync(0xffffffffu, ey_c.x, 1);
+        if (lane == 31) {
+            ex_k4 = Ex[off + 4];
+            ey_k4 = Ey[off + 4];
+        }
+        if (any) {
+            const V4<R> dEz_dy = {ez_j.x - ez_c.x, ez_j.y - ez_c.y, ez_j.z - ez_c.z, ez_j.w - ez_c.w};
+            const V4<R> dEy_dz = {ey_c.y - ey_c.x, ey_c.z - ey_c.y, ey_c.w - ey_c.z, ey_k4 - ey_c.w};
+            const V4<R> dEx_dz = {ex_c.y - ex_c.x, ex_c.z - ex_c.y, ex_c.w - ex_c.z, ex_k4 - ex_c.w};
+            const V4<R> dEz_dx = {ez_n.x - ez_c.x, ez_n.y - ez_c.y, ez_n.z - ez_c.z, ez_n.w - ez_c.w};
+            const V4<R> dEy_dx = {ey_n.x - ey_c.x, ey_n.y - ey_c.y, ey_n.z - ey_c.z, ey_n.w - ey_c.w};
+            const V4<R> dEx_dy = {ex_j.x - ex_c.x, ex_j.y - ex_c.y, ex_j.z - ex_c.z, ex_j.w - ex_c.w};
+            const unsigned mx = (i >= p.box[0].lo[0] && i < p.box[0].hi[0]) ? bx.kmask : 0u;
+            const unsigned my = (i >= p.box[1].lo[0] && i < p.box[1].hi[0]) ? by.kmask : 0u;
+            const unsigned mz = (i >= p.box[2].lo[0] && i < p.box[2].hi[0]) ? bz.kmask : 0u;
+            unsigned pm = 0;  // slabs active on this plane for this thread
+#pragma unroll
+            for (int s = 0; s < kMaxSlabs; ++s)
+                if (((smask >> (4 * s)) & 0xfu) && i >= p.slab[s].lo[0] && i < p.slab[s].hi[0]) pm |= 1u << s;
+            bool wx = mx != 0, wy = my != 0, wz = mz != 0;
+            V4<R> hx, hy, hz;
+            Ids4 idx_, idy_, idz_;
+            const bool needx = wx || (pm != 0), needy = wy || (pm != 0), needz = wz || (pm != 0);
+            if (needx) {
+                hx = ld4(Hx + off);
+                idx_ = ld_ids4<IDT>(p.ID[0], off);
+            }
+            if (needy) {
+                hy = ld4(Hy + off);
+                idy_ = ld_ids4<IDT>(p.ID[1], off);
+            }
+            if (needz) {
+                hz = ld4(Hz + off);
+                idz_ = ld_ids4<IDT>(p.ID[2], off);
+            }
+            if (mx) {
+                Coef4<R> c0, c1, c2, c3;
+                coef4(coef, idx_, c0, c1, c2, c3);
+                hx.x = sel(mx, 0, c0.a * hx.x - c0.by * dEz_dy.x + c0.bz * dEy_dz.x, hx.x);
+                hx.y = sel(mx, 1, c1.a * hx.y - c1.by * dEz_dy.y + c1.bz * dEy_dz.y, hx.y);
+                hx.z = sel(mx, 2, c2.a * hx.z - c2.by * dEz_dy.z + c2.bz * dEy_dz.z, hx.z);
+                hx.w = sel(mx, 3, c3.a * hx.w - c3.by * dEz_dy.w + c3.bz * dEy_dz.w, hx.w);
+            }
+            if (my) {
+                Coef4<R> c0, c1, c2, c3;
+                coef4(coef, idy_, c0, c1, c2, c3);
+                hy.x = sel(my, 0, c0.a * hy.x - c0.bz * dEx_dz.x + c0.bx * dEz_dx.x, hy.x);
+                hy.y = sel(my, 1, c1.a * hy.y - c1.bz * dEx_dz.y + c1.bx * dEz_dx.y, hy.y);
+                hy.z = sel(my, 2, c2.a * hy.z - c2.bz * dEx_dz.z + c2.bx * dEz_dx.z, hy.z);
+                hy.w = sel(my, 3, c3.a * hy.w - c3.bz * dEx_dz.w + c3.bx * dEz_dx.w, hy.w);
+            }
+            if (mz) {
+                Coef4<R> c0, c1, c2, c3;
+                coef4(coef, idz_, c0, c1, c2, c3);
+                hz.x = sel(mz, 0, c0.a * hz.x - c0.bx * dEy_dx.x + c0.by * dEx_dy.x, hz.x);
+                hz.y = sel(mz, 1, c1.a * hz.y - c1.bx * dEy_dx.y + c1.by * dEx_dy.y, hz.y);
+                hz.z = sel(mz, 2, c2.a * hz.z - c2.bx * dEy_dx.z + c2.by * dEx_dy.z, hz.z);
+                hz.w = sel(mz, 3, c3.a * hz.w - c3.bx * dEy_dx.w + c3.by * dEx_dy.w, hz.w);
+            }
+            if (pm) {
+                for (int s = 0; s < p.nslabs; ++s) {
+                    if (!((pm >> s) & 1u)) continue;
+                    const SlabDev<R> &sl = p.slab[s];
+                    const int pos = sl.axis == 0 ? i : j;
+                    const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
+                    const PmlCo<R> co = pml_load(p.form, p.order, sl, depth);
+                    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+                    const unsigned m = (smask >> (4 * s)) & 0xfu;
+                    if (sl.axis == 0) {  // Hy += , dEz/dx ; Hz -= , dEy/dx
+                        pml_comp4(p.form, p.order, co, sl, phi, m, idy_, srcm, (R)1, dEz_dx, hy);
+                        pml_comp4(p.form, p.order, co, sl, phi + sl.ostride, m, idz_, srcm, (R)-1, dEy_dx, hz);
+                        wy = wz = true;
+                    } else {  // Hx -= , dEz/dy ; Hz += , dEx/dy
+                        pml_comp4(p.form, p.order, co, sl, phi, m, idx_, srcm, (R)-1, dEz_dy, hx);
+                        pml_comp4(p.form, p.order, co, sl, phi + sl.ostride, m, idz_, srcm, (R)1, dEx_dy, hz);
+                        wx = wz = true;
+                    }
+                }
+            }
+            if (wx) st4(Hx + off, hx);
+            if (wy) st4(Hy + off, hy);
+            if (wz) st4(Hz + off, hz);
+        }
+        ey_c = ey_n;
+        ez_c = ez_n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Electric half-step, 4 z cells per thread.  Arithmetic: fields_updates_ext.pyx:30-107 and
+// pml_updates_electric_*_ext.pyx (x and y slabs).
+// ------------------------------------------------------------------------------------------
+template <typename R, typename IDT, bool TABSMEM>
+__global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(const PhaseParams<R> p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Coef4<R> *coef = p.coef;
+    const R *srce = p.src;
+    if (TABSMEM) {
+        Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw);
+        R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
+        stage_coefs(p, scoef, ssrc);
+        coef = scoef;
+        srce = ssrc;
+    }
+    const long long idx4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e0 = idx4 * 4;
+    const bool valid = e0 < p.plane;
+    const long long eoff = valid ? e0 : 4;  // 4: keeps the k-1 load of lane 0 inside the allocation
+    const int j = (int)(eoff / p.pitch);
+    const int k = (int)(eoff - (long long)j * p.pitch);
+    const int lane = threadIdx.x & 31;
+    const int l0 = p.p0 + blockIdx.y * kXChunk;
+    const int l1 = min(l0 + kXChunk, p.p1);
+    if (l0 >= l1) return;
+    const JK4 bx = jk4_of(p.box[0].lo, p.box[0].hi, j, k), by = jk4_of(p.box[1].lo, p.box[1].hi, j, k), bz = jk4_of(p.box[2].lo, p.box[2].hi, j, k);
+    unsigned smask = 0;  // 4 bits per slab
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s)
+        if (s < p.nslabs && p.slab[s].axis != 2 && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
+    const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u);
+
+    const R *__restrict__ Hx = p.Hx;
+    const R *__restrict__ Hy = p.Hy;
+    const R *__restrict__ Hz = p.Hz;
+    R *__restrict__ Ex = p.Ex;
+    R *__restrict__ Ey = p.Ey;
+    R *__restrict__ Ez = p.Ez;
+    long long off = (long long)(l0 + 1) * p.plane + eoff;
+    V4<R> hy_p = ld4(Hy + off - p.plane), hz_p = ld4(Hz + off - p.plane);
+#pragma unroll kV4Unroll
+    for (int l = l0; l < l1; ++l, off += p.plane) {
+        const int i = p.x_start + l;
+        const V4<R> hx_c = ld4(Hx + off), hy_c = ld4(Hy + off), hz_c = ld4(Hz + off);
+        const V4<R> hx_j = ld4(Hx + off - p.pitch), hz_j = ld4(Hz + off - p.pitch);
+        // k-1 operands: previous lane's .w (scalar load on the warp-edge lane)
+        R hx_km = __shfl_up_sync(0xffffffffu, hx_c.w, 1), hy_km = __shfl_up_sync(0xffffffffu, hy_c.w, 1);
+        if (lane == 0) {
+            hx_km = Hx[off - 1];
+            hy_km = Hy[off - 1];
+        }
+        if (any) {
+            const V4<R> dHz_dy = {hz_c.x - hz_j.x, hz_c.y - hz_j.y, hz_c.z - hz_j.z, hz_c.w - hz_j.w};
+            const V4<R> dHy_dz = {hy_c.x - hy_km, hy_c.y - hy_c.x, hy_c.z - hy_c.y, hy_c.w - hy_c.z};
+            const V4<R> dHx_dz = {hx_c.x - hx_km, hx_c.y - hx_c.x, hx_c.z - hx_c.y, hx_c.w - hx_c.z};
+            const V4<R> dHz_dx = {hz_c.x - hz_p.x, hz_c.y - hz_p.y, hz_c.z - hz_p.z, hz_c.w - hz_p.w};
+            const V4<R> dHy_dx = {hy_c.x - hy_p.x, hy_c.y - hy_p.y, hy_c.z - hy_p.z, hy_c.w - hy_p.w};
+            const V4<R> dHx_dy = {hx_c.x - hx_j.x, hx_c.y - hx_j.y, hx_c.z - hx_j.z, hx_c.w - hx_j.w};
+            const unsigned mx = (i >= p.box[0].lo[0] && i < p.box[0].hi[0]) ? bx.kmask : 0u;
+            const unsigned my = (i >= p.box[1].lo[0] && i < p.box[1].hi[0]) ? by.kmask : 0u;
+            const unsigned mz = (i >= p.box[2].lo[0] && i < p.box[2].hi[0]) ? bz.kmask : 0u;
+            unsigned pm = 0;
+#pragma unroll
+            for (int s = 0; s < kMaxSlabs; ++s)
+                if (((smask >> (4 * s)) & 0xfu) && i >= p.slab[s].lo[0] && i < p.slab[s].hi[0]) pm |= 1u << s;
+            bool wx = mx != 0, wy = my != 0, wz = mz != 0;
+            V4<R> ex, ey, ez;
+            Ids4 idx_, idy_, idz_;
+            const bool needx = wx || (pm != 0), needy = wy || (pm != 0), needz = wz || (pm != 0);
+            if (needx) {
+                ex = ld4(Ex + off);
+                idx_ = ld_ids4<IDT>(p.ID[0], off);
+            }
+            if (needy) {
+                ey = ld4(Ey + off);
+                idy_ = ld_ids4<IDT>(p.ID[1], off);
+            }
+            if (needz) {
+                ez = ld4(Ez + off);
+                idz_ = ld_ids4<IDT>(p.ID[2], off);
+            }
+            if (mx) {
+                Coef4<R> c0, c1, c2, c3;
+                coef4(coef, idx_, c0, c1, c2, c3);
+                ex.x = sel(mx, 0, c0.a * ex.x + c0.by * dHz_dy.x - c0.bz * dHy_dz.x, ex.x);
+                ex.y = sel(mx, 1, c1.a * ex.y + c1.by * dHz_dy.y - c1.bz * dHy_dz.y, ex.y);
+                ex.z = sel(mx, 2, c2.a * ex.z + c2.by * dHz_dy.z - c2.bz * dHy_dz.z, ex.z);
+                ex.w = sel(mx, 3, c3.a * ex.w + c3.by * dHz_dy.w - c3.bz * dHy_dz.w, ex.w);
+            }
+            if (my) {
+                Coef4<R> c0, c1, c2, c3;
+                coef4(coef, idy_, c0, c1, c2, c3);
+                ey.x = sel(my, 0, c0.a * ey.x + c0.bz * dHx_dz.x - c0.bx * dHz_dx.x, ey.x);
+                ey.y = sel(my, 1, c1.a * ey.y + c1.bz * dHx_dz.y - c1.bx * dHz_dx.y, ey.y);
+                ey.z = sel(my, 2, c2.a * ey.z + c2.bz * dHx_dz.z - c2.bx * dHz_dx.z, ey.z);
+                ey.w = sel(my, 3, c3.a * ey.w + c3.bz * dHx_dz.w - c3.bx * dHz_dx.w, ey.w);
+            }
+            if (mz) {
+                Coef4<R> c0, c1, c2, c3;
+                coef4(coef, idz_, c0, c1, c2, c3);
+                ez.x = sel(mz, 0, c0.a * ez.x + c0.bx * dHy_dx.x - c0.by * dHx_dy.x, ez.x);
+                ez.y = sel(mz, 1, c1.a * ez.y + c1.bx * dHy_dx.y - c1.by * dHx_dy.y, ez.y);
+                ez.z = sel(mz, 2, c2.a * ez.z + c2.bx * dHy_dx.z - c2.by * dHx_dy.z, ez.z);
+                ez.w = sel(mz, 3, c3.a * ez.w + c3.bx * dHy_dx.w - c3.by * dHx_dy.w, ez.w);
+            }
+            if (pm) {
+                for (int s = 0; s < p.nslabs; ++s) {
+                    if (!((pm >> s) & 1u)) continue;
+                    const SlabDev<R> &sl = p.slab[s];
+                    const int pos = sl.axis == 0 ? i : j;
+                    const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
+                    const PmlCo<R> co = pml_load(p.form, p.order, sl, depth);
+                    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+                    const unsigned m = (smask >> (4 * s)) & 0xfu;
+                    if (sl.axis == 0) {  // Ey -= , dHz/dx ; Ez += , dHy/dx
+                        pml_comp4(p.form, p.order, co, sl, phi, m, idy_, srce, (R)-1, dHz_dx, ey);
+                        pml_comp4(p.form, p.order, co, sl, phi + sl.ostride, m, idz_, srce, (R)1, dHy_dx, ez);
+                        wy = wz = true;
+                    } else {  // Ex += , dHz/dy ; Ez -= , dHx/dy
+                        pml_comp4(p.form, p.order, co, sl, phi, m, idx_, srce, (R)1, dHz_dy, ex);
+                        pml_comp4(p.form, p.order, co, sl, phi + sl.ostride, m, idz_, srce, (R)-1, dHx_dy, ez);
+                        wx = wz = true;
+                    }
+                }
+            }
+            if (wx) st4(Ex + off, ex);
+            if (wy) st4(Ey + off, ey);
+            if (wz) st4(Ez + off, ez);
+        }
+        hy_p = hy_c;
+        hz_p = hz_c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Slab-wise PML correction, one thread per slab cell (both components).  Used for the z slabs of
+// the vectorised path: the 10 cells at either end of every z row would diverge in every warp of the
+// main kernel.  `phase` 0 = magnetic, 1 = electric.  Grid: x = cells of one plane of the slab box,
+// y = planes.
+// ------------------------------------------------------------------------------------------
+template <typename R, typename IDT>
+__global__ void __launch_bounds__(256) k_pml_slabs(const PhaseParams<R> p, int phase, unsigned slabsel, int p0, int p1)
+{
+    for (int s = 0; s < p.nslabs; ++s) {
+        if (!((slabsel >> s) & 1u)) continue;
+        const SlabDev<R> &sl = p.slab[s];
+        const int n1 = sl.hi[1] - sl.lo[1], n2 = sl.hi[2] - sl.lo[2];
+        const int i = sl.lo[0] + blockIdx.y;
+        if (i >= sl.hi[0] || i < p.x_start + p0 || i >= p.x_start + p1) continue;
+        const int q = blockIdx.x * blockDim.x + threadIdx.x;
+        if (q >= n1 * n2) continue;
+        const int j = sl.lo[1] + q / n2, k = sl.lo[2] + q % n2;
+        const int a = sl.axis;
+        const int pos = a == 0 ? i : (a == 1 ? j : k);
+        const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
+        const long long off = (long long)(i - p.x_start + 1) * p.plane + (long long)j * p.pitch + k;
+        R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+        const long long st = a == 0 ? p.plane : (a == 1 ? p.pitch : 1);
+        const R *src = p.src;
+        if (phase == 1) {
+            // electric: backward differences of H along the slab axis
+            R *Fa, *Fb;
+            const R *Ga, *Gb;
+            R sa, sb;
+            int ca, cb;
+            if (a == 0) { Fa = p.Ey; Ga = p.Hz; sa = -1; ca = 1; Fb = p.Ez; Gb = p.Hy; sb = 1; cb = 2; }
+            else if (a == 1) { Fa = p.Ex; Ga = p.Hz; sa = 1; ca = 0; Fb = p.Ez; Gb = p.Hx; sb = -1; cb = 2; }
+            else { Fa = p.Ex; Ga = p.Hy; sa = -1; ca = 0; Fb = p.Ey; Gb = p.Hx; sb = 1; cb = 1; }
+            const R dA = (Ga[off] - Ga[off - st]) / sl.d, dB = (Gb[off] - Gb[off - st]) / sl.d;
+            const unsigned ma = ld_id<IDT>(p.ID[ca], off), mb = ld_id<IDT>(p.ID[cb], off);
+            Fa[off] = Fa[off] + sa * (src[ma] * pml_term(p.form, p.order, sl, depth, dA, phi, sl.ostride));
+            Fb[off] = Fb[off] + sb * (src[mb] * pml_term(p.form, p.order, sl, depth, dB, phi + sl.ostride, sl.ostride));
+        } else {
+            R *Fa, *Fb;
+            const R *Ga, *Gb;
+            R sa, sb;
+            int ca, cb;
+            if (a == 0) { Fa = p.Hy; Ga = p.Ez; sa = 1; ca = 1; Fb = p.Hz; Gb = p.Ey; sb = -1; cb = 2; }
+            else if (a == 1) { Fa = p.Hx; Ga = p.Ez; sa = -1; ca = 0; Fb = p.Hz; Gb = p.Ex; sb = 1; cb = 2; }
+            else { Fa = p.Hx; Ga = p.Ey; sa = 1; ca = 0; Fb = p.Hy; Gb = p.Ex; sb = -1; cb = 1; }
+            const R dA = (Ga[off + st] - Ga[off]) / sl.d, dB = (Gb[off + st] - Gb[off]) / sl.d;
+            const unsigned ma = ld_id<IDT>(p.ID[ca], off), mb = ld_id<IDT>(p.ID[cb], off);
+            Fa[off] = Fa[off] + sa * (src[ma] * pml_term(p.form, p.order, sl, depth, dA, phi, sl.ostride));
+            Fb[off] = Fb[off] + sb * (src[mb] * pml_term(p.form, p.order, sl, depth, dB, phi + sl.ostride, sl.ostride));
+        }
+    }
+}
+
+}  // namespace gpb

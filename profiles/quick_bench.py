@@ -1,0 +1,15 @@
+"""Quick device-side timing of the 300^3 benchmark loop (no CPU baseline, no e2e): prints Mcells/s and per-kernel ms."""
+import sys
+sys.path.insert(0, ".")
+from gprmax_b200 import Solver
+from gprmax_b200.synthetic import bench_model
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+its = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+G = bench_model(size, iterations=its)
+sv = Solver(G, device_id=0)
+sv.run(); sv.reset(); sv.run()
+t = sv.elapsed
+print('size %d its %d: %.1f Mcells/s  (%.3f ms/iteration)' % (size, its, size**3 * its / t / 1e6, t / its * 1e3))
+sv.reset(); sv.profile(20); pr = sv.profile(100)
+print({k: round(v / 100, 4) for k, v in pr.items()})
+sv.close()

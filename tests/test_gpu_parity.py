@@ -53,7 +53,7 @@ def test_f32_against_reference_golden(name):
 
 @pytest.mark.parametrize('name,variant', [('pml_HORIPML_1', 'f64'), ('pml_MRIPML_2', 'f64'), ('sources_mixed', 'f64'),
                                           ('dispersive_multipole', 'f64'), ('cylinder_Ascan_2D', 'f64'),
-                                          ('transmission_line', 'f64'), ('pml_HORIPML_2', 'f32'), ('snapshots', 'f32')])
+                                          ('transmission_line', 'f64'), ('pml_HORIPML_2', 'f64'), ('snapshots', 'f64'), ('heterogeneous_soil_small', 'f64')])
 def test_against_oracle_run_here(name, variant, oracle_built):
     """Same model through the CUDA core and through oracle/ on this box (no stored vectors)."""
     from gprmax_b200.model_io import load_model
