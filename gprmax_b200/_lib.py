@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.environ.get('GPB_LIB') or os.path.join(HERE, 'libgprmax_b200.so')
 
-GPB_ABI_VERSION = 1
+GPB_ABI_VERSION = 2
 GPB_F32, GPB_F64 = 0, 1
 GPB_HORIPML, GPB_MRIPML = 0, 1
 GPB_SRC_HERTZIAN, GPB_SRC_MAGNETIC, GPB_SRC_VOLTAGE = 0, 1, 2
@@ -61,7 +61,7 @@ class Model(C.Structure):
                 ('x_start', C.c_int32), ('nx_planes', C.c_int32),
                 ('dx', C.c_double), ('dy', C.c_double), ('dz', C.c_double), ('dt', C.c_double),
                 ('iterations', C.c_int32), ('nmaterials', C.c_int32),
-                ('ID', C.c_void_p), ('updatecoeffsE', C.c_void_p), ('updatecoeffsH', C.c_void_p),
+                ('ID', C.c_void_p), ('uniform_id', C.c_int32), ('updatecoeffsE', C.c_void_p), ('updatecoeffsH', C.c_void_p),
                 ('maxpoles', C.c_int32), ('updatecoeffsdispersive', C.c_void_p),
                 ('pml_formulation', C.c_int32), ('pml_order', C.c_int32),
                 ('npml', C.c_int32), ('pmls', C.POINTER(Pml)),
@@ -91,7 +91,7 @@ def lib():
     L.gpb_create.argtypes = [C.POINTER(Model), C.c_int, C.POINTER(H)]
     L.gpb_destroy.argtypes = [H]
     L.gpb_run.argtypes = [H, C.c_int]
-    L.gpb_half_step.argtypes = [H, C.c_int]
+    L.gpb_half_step.argtypes = [H, C.c_int, C.c_int]
     L.gpb_reset.argtypes = [H]
     L.gpb_profile.argtypes = [H, C.c_int, C.POINTER(C.c_double)]
     L.gpb_iteration.argtypes = [H, C.POINTER(C.c_int)]

@@ -43,7 +43,7 @@ static int fail(const char *fmt, ...)
 struct SolverBase {
     virtual ~SolverBase() {}
     virtual int run(int n) = 0;
-    virtual int half_step(int phase) = 0;
+    virtual int half_step(int phase, int part) = 0;
     virtual int reset() = 0;
     virtual int get_receivers(void *out, size_t bytes) = 0;
     virtual int get_snapshot(int idx, void *out6[6], size_t bytes_each) = 0;
@@ -74,6 +74,7 @@ struct Solver : SolverBase {
     bool use_v4 = false;       // vectorised non-dispersive path (gpb_kernels_v4.cuh)
     bool use_tma = false;      // TMA-staged path (gpb_kernels_tma.cuh)
     int tma_ty = 0, tma_tz = 0, tma_stages = 0, tma_xchunk = 16;
+    bool tma_zfused = false, tma_ztail = true;
     TmaMaps9 maps_e, maps_h;
     int setup_tma();
     template <typename IDT, int TY, int TZ, int S>
@@ -168,7 +169,7 @@ struct Solver : SolverBase {
     }
 
     int run(int n) override;
-    int half_step(int phase) override;
+    int half_step(int phase, int part) override;
     int reset() override;
     int get_receivers(void *out, size_t bytes) override;
     int get_snapshot(int idx, void *out6[6], size_t bytes_each) override;
@@ -221,6 +222,24 @@ static int make_map(CUtensorMap *out, void *base, CUtensorMapDataType dt, size_t
 template <typename R>
 int Solver<R>::upload_ids(const gpb_model_t &m)
 {
+    if (!m.ID) {
+        // homogeneous domain: every edge carries the same material
+        if (m.uniform_id < 0 || m.uniform_id >= nmat) return fail("uniform_id %d outside the %d materials", m.uniform_id, nmat);
+        for (int c = 0; c < 6; ++c) {
+            void *dst = nullptr;
+            size_t bytes = (size_t)narr * idbytes;
+            CK(cudaMalloc(&dst, bytes));
+            allocs.push_back(dst);
+            mem += bytes;
+            ID[c] = dst;
+            if (idbytes == 1) k_fill_ids<uint8_t><<<148 * 8, 256, 0, stream>>>((uint8_t *)dst, narr, (uint8_t)m.uniform_id);
+            else if (idbytes == 2) k_fill_ids<uint16_t><<<148 * 8, 256, 0, stream>>>((uint16_t *)dst, narr, (uint16_t)m.uniform_id);
+            else k_fill_ids<uint32_t><<<148 * 8, 256, 0, stream>>>((uint32_t *)dst, narr, (uint32_t)m.uniform_id);
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(stream));
+        return 0;
+    }
     // stage uint32 planes through a bounded device buffer and narrow on the device
     const long long rows_per_plane = ny + 1;
     const long long plane_src = rows_per_plane * (nz + 1);
@@ -450,7 +469,7 @@ int Solver<R>::build(const gpb_model_t &m)
     form = m.pml_formulation; order = m.npml ? m.pml_order : 1;
     if (nx < 1 || ny < 1 || nz < 1) return fail("grid must have at least one cell per axis");
     if (x_start < 0 || nplanes < 1 || x_start + nplanes > nx + 1) return fail("owned plane range [%d, %d) outside [0, %d]", x_start, x_start + nplanes, nx);
-    if (nmat < 1 || !m.ID || !m.updatecoeffsE || !m.updatecoeffsH) return fail("material tables missing");
+    if (nmat < 1 || !m.updatecoeffsE || !m.updatecoeffsH) return fail("material tables missing");
     if (m.npml && (order < 1 || order > 2 || form < 0 || form > 1)) return fail("unsupported PML formulation/order %d/%d", form, order);
     if (maxpoles < 0 || (maxpoles > 0 && !m.updatecoeffsdispersive)) return fail("dispersive coefficient table missing");
     CK(cudaSetDevice(device));
@@ -507,6 +526,10 @@ int Solver<R>::build(const gpb_model_t &m)
     // TMA-staged path: 3-D grids with reasonably long z rows (2-D / thin grids stay on the flattened v4 path)
     use_tma = use_v4 && nz + 1 >= 32 && ny + 1 >= 8 && !getenv("GPB_NO_TMA") && (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R)) <= 32 * 1024;
     if (use_tma && setup_tma()) return 1;
+    // z-slab PML: default = per-CTA tail inside the TMA kernel; GPB_TMA_ZSPLIT = separate k_pml_slabs launch;
+    // GPB_TMA_ZFUSE = inside the main loop (divergent scalar terms, measured slower)
+    tma_zfused = getenv("GPB_TMA_ZFUSE") != nullptr;
+    tma_ztail = !tma_zfused && !getenv("GPB_TMA_ZSPLIT");
     if (use_v4) {
         for (int s = 0; s < ph_e.nslabs; ++s)
             if (ph_e.slab[s].axis == 2) zslabs_e |= 1u << s;
@@ -529,11 +552,12 @@ template <typename R>
 int Solver<R>::setup_tma()
 {
     // tile shape: 256 threads x 4 cells; pick the shape that wastes the fewest lanes on this grid
-    const int cand[3][2] = {{32, 32}, {16, 64}, {8, 128}};
+    // (16 x 64 measured fastest on B200; another shape only when it wastes >8 % fewer lanes)
+    const int cand[3][2] = {{16, 64}, {32, 32}, {8, 128}};
     double best = 1e30;
     for (auto &c : cand) {
         const double waste = (double)((ny + 1 + c[0] - 1) / c[0] * c[0]) * ((pitch + c[1] - 1) / c[1] * c[1]) / ((double)(ny + 1) * (nz + 1));
-        if (waste < best - 1e-9) { best = waste; tma_ty = c[0]; tma_tz = c[1]; }
+        if (waste < best * 0.92) { best = waste; tma_ty = c[0]; tma_tz = c[1]; }
     }
     if (getenv("GPB_TMA_TZ")) { tma_tz = atoi(getenv("GPB_TMA_TZ")); tma_ty = 1024 / tma_tz; }
     tma_stages = getenv("GPB_TMA_STAGES") ? atoi(getenv("GPB_TMA_STAGES")) : 3;
@@ -580,7 +604,7 @@ int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
 {
     using L = StageLayout<R, IDT, TY, TZ>;
     PhaseParams<R> p = phase == 0 ? ph_h : ph_e;
-    p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk;
+    p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk; p.zfused = tma_zfused ? 1 : 0; p.ztail = tma_ztail ? 1 : 0;
     const int tiles_k = (pitch + TZ - 1) / TZ, tiles_j = (ny + 1 + TY - 1) / TY;
     const size_t smem = 128 + (size_t)((nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128) + (size_t)S * L::bytes;
     dim3 grid((unsigned)(tiles_k * tiles_j), (unsigned)((p1 - p0 + tma_xchunk - 1) / tma_xchunk));
@@ -595,7 +619,7 @@ int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
     }
     CK(cudaGetLastError());
     ++launches;
-    const unsigned zs = phase == 0 ? zslabs_h : zslabs_e;
+    const unsigned zs = (tma_zfused || tma_ztail) ? 0u : (phase == 0 ? zslabs_h : zslabs_e);
     if (zs) {
         int cells = 0, planes = 0;
         for (int s = 0; s < p.nslabs; ++s)
@@ -862,17 +886,25 @@ int Solver<R>::profile(int n, double *ms4)
 }
 
 template <typename R>
-int Solver<R>::half_step(int phase)
+int Solver<R>::half_step(int phase, int part)
 {
     CK(cudaSetDevice(device));
+    const bool first = part != 1, second = part != 0;
     if (phase == 0) {
-        if (iteration >= iterations) return fail("all %d iterations already done", iterations);
-        if (launch_begin() || launch_snapshots()) return 1;
-        // boundary plane first so the host can start the halo transfer while the interior runs
-        if (launch_phase(0, nplanes - 1, nplanes) || launch_phase(0, 0, nplanes - 1) || launch_sources(0)) return 1;
+        if (first) {
+            if (iteration >= iterations) return fail("all %d iterations already done", iterations);
+            if (launch_begin() || launch_snapshots()) return 1;
+            // boundary plane first (its Hy,Hz feed the right neighbour) so the host can start the halo
+            // transfer while the interior runs
+            if (launch_phase(0, nplanes - 1, nplanes)) return 1;
+        }
+        if (second && (launch_phase(0, 0, nplanes - 1) || launch_sources(0))) return 1;
     } else {
-        if (launch_phase(1, 0, 1) || launch_phase(1, 1, nplanes) || launch_sources(1)) return 1;
-        ++iteration;
+        if (first && launch_phase(1, 0, 1)) return 1;  // first owned plane: its Ey,Ez feed the left neighbour
+        if (second) {
+            if (launch_phase(1, 1, nplanes) || launch_sources(1)) return 1;
+            ++iteration;
+        }
     }
     return 0;
 }
@@ -1060,7 +1092,7 @@ int gpb_destroy(gpb_handle h)
 #define NEED(h) if (!(h) || !(h)->impl) return fail("null handle")
 
 int gpb_run(gpb_handle h, int n_iters) { NEED(h); return h->impl->run(n_iters); }
-int gpb_half_step(gpb_handle h, int phase) { NEED(h); if (phase != 0 && phase != 1) return fail("phase must be 0 or 1"); return h->impl->half_step(phase); }
+int gpb_half_step(gpb_handle h, int phase, int part) { NEED(h); if (phase != 0 && phase != 1) return fail("phase must be 0 or 1"); if (part < -1 || part > 1) return fail("part must be -1, 0 or 1"); return h->impl->half_step(phase, part); }
 int gpb_reset(gpb_handle h) { NEED(h); return h->impl->reset(); }
 int gpb_iteration(gpb_handle h, int *it) { NEED(h); if (!it) return fail("null argument"); *it = h->impl->iteration; return 0; }
 int gpb_elapsed_seconds(gpb_handle h, double *s) { NEED(h); if (!s) return fail("null argument"); *s = h->impl->elapsed; return 0; }

@@ -85,6 +85,8 @@ struct PhaseParams {
     // sub-range of owned planes processed by this launch (for halo overlap): [p0, p1)
     int p0, p1;
     int xchunk;               // planes marched by one CTA of the TMA kernels
+    int zfused;               // TMA kernels: apply z-slab PML inside the main loop (divergent; measured slower)
+    int ztail;                // TMA kernels: apply z-slab PML as a per-CTA tail after the march
 };
 
 // ------------------------------------------------------------------------------------------
@@ -610,6 +612,12 @@ __global__ void k_narrow_ids(const uint32_t *src, IDT *dst, long long rows, int 
         mx = max(mx, v);
     }
     if (mx) atomicMax(maxid, mx);
+}
+
+template <typename IDT>
+__global__ void k_fill_ids(IDT *dst, long long n, IDT v)
+{
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) dst[q] = v;
 }
 
 }  // namespace gpb

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
     unsigned smask = 0;
 #pragma unroll
     for (int s = 0; s < kMaxSlabs; ++s)
-        if (s < p.nslabs && p.slab[s].axis != 2 && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
+        if (s < p.nslabs && (p.slab[s].axis != 2 || p.zfused) && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
     const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u);
 
     // fields this phase writes / queue operands (the operand arrays are read-only in this phase)
@@ -316,11 +316,32 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
                 for (int s = 0; s < p.nslabs; ++s) {
                     if (!((pm >> s) & 1u)) continue;
                     const SlabDev<R> &sl = p.slab[s];
+                    const unsigned m = (smask >> (4 * s)) & 0xfu;
+                    if (sl.axis == 2) {
+                        // z slab: every cell of the thread has its own depth; scalar terms on the (few) lanes
+                        // that sit in the first / last `thickness` cells of a z row.
+                        // E phase: Ex -= , dHy/dz ; Ey += , dHx/dz   H phase: Hx += , dEy/dz ; Hy -= , dEx/dz
+                        R *phirow = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 - sl.lo[2];
+                        const R s0 = PHASE == 1 ? (R)-1 : (R)1, s1 = -s0;
+#define GPB_ZCELL(q, comp, idq)                                                                                                   \
+    if ((m >> q) & 1u) {                                                                                                          \
+        const int kq = k + q;                                                                                                     \
+        const int depth = sl.minus ? (sl.dref - kq) : (kq - sl.dref);                                                             \
+        f0.comp = f0.comp + s0 * (ssrc[id0.idq] * pml_term(p.form, p.order, sl, depth, dB_dz.comp / sl.d, phirow + kq, sl.ostride)); \
+        f1.comp = f1.comp + s1 * (ssrc[id1.idq] * pml_term(p.form, p.order, sl, depth, dA_dz.comp / sl.d, phirow + kq + sl.ostride, sl.ostride)); \
+    }
+                        GPB_ZCELL(0, x, a)
+                        GPB_ZCELL(1, y, b)
+                        GPB_ZCELL(2, z, c)
+                        GPB_ZCELL(3, w, d)
+#undef GPB_ZCELL
+                        w0 = w1 = true;
+                        continue;
+                    }
                     const int pos = sl.axis == 0 ? i : j;
                     const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
                     const PmlCo<R> co = pml_load(p.form, p.order, sl, depth);
                     R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
-                    const unsigned m = (smask >> (4 * s)) & 0xfu;
                     if (PHASE == 1) {
                         if (sl.axis == 0) {  // Ey -= , dHz/dx ; Ez += , dHy/dx
                             pml_comp4(p.form, p.order, co, sl, phi, m, id1, ssrc, (R)-1, dC_dx, f1);
@@ -351,6 +372,31 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
         }
         qb = b_c;
         qc = c_c;
+    }
+
+    // z-slab PML tail: the z-slab cells of this CTA's tile x march (first / last `thickness` cells of
+    // its z rows) are corrected here by all 256 threads, one cell each per round, right after the CTA
+    // wrote them -- the lines are still in L2, and the main loop above stays divergence-free.
+    if (p.ztail) {
+        bool mine = false;
+        for (int s = 0; s < p.nslabs; ++s)
+            if (p.slab[s].axis == 2 && p.slab[s].lo[2] < k0 + TZ && p.slab[s].hi[2] > k0) mine = true;
+        if (mine) {
+            __syncthreads();  // this CTA's stores of the march are visible to all of its threads
+            for (int s = 0; s < p.nslabs; ++s) {
+                const SlabDev<R> &sl = p.slab[s];
+                if (sl.axis != 2) continue;
+                const int ka = max(sl.lo[2], k0), kb = min(sl.hi[2], k0 + TZ);
+                const int ja = max(sl.lo[1], j0), jb = min(sl.hi[1], j0 + TY);
+                const int ia = max(sl.lo[0], p.x_start + l0), ib = min(sl.hi[0], p.x_start + l1);
+                const int nk = kb - ka, nj = jb - ja, ni = ib - ia;
+                if (nk <= 0 || nj <= 0 || ni <= 0) continue;
+                for (int t = tid; t < ni * nj * nk; t += kTmaThreads) {
+                    const int kk = t % nk, jj = (t / nk) % nj, ii = t / (nk * nj);
+                    pml_slab_cell<R, IDT>(p, PHASE, sl, ia + ii, ja + jj, ka + kk);
+                }
+            }
+        }
     }
 }
 

@@ -485,6 +485,46 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
 // main kernel.  `phase` 0 = magnetic, 1 = electric.  Grid: x = cells of one plane of the slab box,
 // y = planes.
 // ------------------------------------------------------------------------------------------
+// one slab cell, both components; `phase` 0 = magnetic, 1 = electric
+template <typename R, typename IDT>
+__device__ __forceinline__ void pml_slab_cell(const PhaseParams<R> &p, int phase, const SlabDev<R> &sl, int i, int j, int k)
+{
+    const int a = sl.axis;
+    const int pos = a == 0 ? i : (a == 1 ? j : k);
+    const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
+    const long long off = (long long)(i - p.x_start + 1) * p.plane + (long long)j * p.pitch + k;
+    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+    const long long st = a == 0 ? p.plane : (a == 1 ? p.pitch : 1);
+    const R *src = p.src;
+    R *Fa, *Fb;
+    const R *Ga, *Gb;
+    R sa, sb, dA, dB;
+    int ca, cb;
+    if (phase == 1) {
+        // electric: backward differences of H along the slab axis
+        if (a == 0) { Fa = p.Ey; Ga = p.Hz; sa = -1; ca = 1; Fb = p.Ez; Gb = p.Hy; sb = 1; cb = 2; }
+        else if (a == 1) { Fa = p.Ex; Ga = p.Hz; sa = 1; ca = 0; Fb = p.Ez; Gb = p.Hx; sb = -1; cb = 2; }
+        else { Fa = p.Ex; Ga = p.Hy; sa = -1; ca = 0; Fb = p.Ey; Gb = p.Hx; sb = 1; cb = 1; }
+        dA = (Ga[off] - Ga[off - st]) / sl.d;
+        dB = (Gb[off] - Gb[off - st]) / sl.d;
+    } else {
+        // magnetic: forward differences of E along the slab axis
+        if (a == 0) { Fa = p.Hy; Ga = p.Ez; sa = 1; ca = 1; Fb = p.Hz; Gb = p.Ey; sb = -1; cb = 2; }
+        else if (a == 1) { Fa = p.Hx; Ga = p.Ez; sa = -1; ca = 0; Fb = p.Hz; Gb = p.Ex; sb = 1; cb = 2; }
+        else { Fa = p.Hx; Ga = p.Ey; sa = 1; ca = 0; Fb = p.Hy; Gb = p.Ex; sb = -1; cb = 1; }
+        dA = (Ga[off + st] - Ga[off]) / sl.d;
+        dB = (Gb[off + st] - Gb[off]) / sl.d;
+    }
+    const unsigned ma = ld_id<IDT>(p.ID[ca], off), mb = ld_id<IDT>(p.ID[cb], off);
+    Fa[off] = Fa[off] + sa * (src[ma] * pml_term(p.form, p.order, sl, depth, dA, phi, sl.ostride));
+    Fb[off] = Fb[off] + sb * (src[mb] * pml_term(p.form, p.order, sl, depth, dB, phi + sl.ostride, sl.ostride));
+}
+
+// ------------------------------------------------------------------------------------------
+// Slab-wise PML correction, one thread per slab cell (both components).  Used for the z slabs of
+// the vectorised path: the 10 cells at either end of every z row would diverge in every warp of the
+// main kernel.  Grid: x = cells of one plane of the slab box, y = planes.
+// ------------------------------------------------------------------------------------------
 template <typename R, typename IDT>
 __global__ void __launch_bounds__(256) k_pml_slabs(const PhaseParams<R> p, int phase, unsigned slabsel, int p0, int p1)
 {
@@ -496,40 +536,7 @@ __global__ void __launch_bounds__(256) k_pml_slabs(const PhaseParams<R> p, int p
         if (i >= sl.hi[0] || i < p.x_start + p0 || i >= p.x_start + p1) continue;
         const int q = blockIdx.x * blockDim.x + threadIdx.x;
         if (q >= n1 * n2) continue;
-        const int j = sl.lo[1] + q / n2, k = sl.lo[2] + q % n2;
-        const int a = sl.axis;
-        const int pos = a == 0 ? i : (a == 1 ? j : k);
-        const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
-        const long long off = (long long)(i - p.x_start + 1) * p.plane + (long long)j * p.pitch + k;
-        R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
-        const long long st = a == 0 ? p.plane : (a == 1 ? p.pitch : 1);
-        const R *src = p.src;
-        if (phase == 1) {
-            // electric: backward differences of H along the slab axis
-            R *Fa, *Fb;
-            const R *Ga, *Gb;
-            R sa, sb;
-            int ca, cb;
-            if (a == 0) { Fa = p.Ey; Ga = p.Hz; sa = -1; ca = 1; Fb = p.Ez; Gb = p.Hy; sb = 1; cb = 2; }
-            else if (a == 1) { Fa = p.Ex; Ga = p.Hz; sa = 1; ca = 0; Fb = p.Ez; Gb = p.Hx; sb = -1; cb = 2; }
-            else { Fa = p.Ex; Ga = p.Hy; sa = -1; ca = 0; Fb = p.Ey; Gb = p.Hx; sb = 1; cb = 1; }
-            const R dA = (Ga[off] - Ga[off - st]) / sl.d, dB = (Gb[off] - Gb[off - st]) / sl.d;
-            const unsigned ma = ld_id<IDT>(p.ID[ca], off), mb = ld_id<IDT>(p.ID[cb], off);
-            Fa[off] = Fa[off] + sa * (src[ma] * pml_term(p.form, p.order, sl, depth, dA, phi, sl.ostride));
-            Fb[off] = Fb[off] + sb * (src[mb] * pml_term(p.form, p.order, sl, depth, dB, phi + sl.ostride, sl.ostride));
-        } else {
-            R *Fa, *Fb;
-            const R *Ga, *Gb;
-            R sa, sb;
-            int ca, cb;
-            if (a == 0) { Fa = p.Hy; Ga = p.Ez; sa = 1; ca = 1; Fb = p.Hz; Gb = p.Ey; sb = -1; cb = 2; }
-            else if (a == 1) { Fa = p.Hx; Ga = p.Ez; sa = -1; ca = 0; Fb = p.Hz; Gb = p.Ex; sb = 1; cb = 2; }
-            else { Fa = p.Hx; Ga = p.Ey; sa = 1; ca = 0; Fb = p.Hy; Gb = p.Ex; sb = -1; cb = 1; }
-            const R dA = (Ga[off + st] - Ga[off]) / sl.d, dB = (Gb[off + st] - Gb[off]) / sl.d;
-            const unsigned ma = ld_id<IDT>(p.ID[ca], off), mb = ld_id<IDT>(p.ID[cb], off);
-            Fa[off] = Fa[off] + sa * (src[ma] * pml_term(p.form, p.order, sl, depth, dA, phi, sl.ostride));
-            Fb[off] = Fb[off] + sb * (src[mb] * pml_term(p.form, p.order, sl, depth, dB, phi + sl.ostride, sl.ostride));
-        }
+        pml_slab_cell<R, IDT>(p, phase, sl, i, sl.lo[1] + q / n2, sl.lo[2] + q % n2);
     }
 }
 

@@ -58,11 +58,17 @@ class PackedModel(object):
         m.nx_planes = int(G.nx + 1 if nx_planes is None else nx_planes)
         m.dx, m.dy, m.dz, m.dt = float(G.dx), float(G.dy), float(G.dz), float(G.dt)
         m.iterations = int(G.iterations)
-        ID = G.ID if ID is None else ID
-        want = (6, m.nx_planes, m.ny + 1, m.nz + 1)
-        if tuple(ID.shape) != want:
-            raise GeneralError('ID array has shape {}, expected {}'.format(tuple(ID.shape), want))
-        m.ID = _ptr(self._hold(ID, np.uint32))
+        if ID is None:
+            ID = getattr(G, 'ID', None)
+        if ID is None:
+            # homogeneous synthetic domain (synthetic.homogeneous_model(build_id=False)): no ID array at all
+            m.ID = None
+            m.uniform_id = int(G.fill_id)
+        else:
+            want = (6, m.nx_planes, m.ny + 1, m.nz + 1)
+            if tuple(ID.shape) != want:
+                raise GeneralError('ID array has shape {}, expected {}'.format(tuple(ID.shape), want))
+            m.ID = _ptr(self._hold(ID, np.uint32))
         cE = self._hold(G.updatecoeffsE, real)
         cH = self._hold(G.updatecoeffsH, real)
         m.nmaterials = int(cE.shape[0])
@@ -193,8 +199,8 @@ class Solver(object):
     def run(self, n=None):
         self._ck(self.L.gpb_run(self.h, int(self.iterations - self.iteration if n is None else n)))
 
-    def half_step(self, phase):
-        self._ck(self.L.gpb_half_step(self.h, int(phase)))
+    def half_step(self, phase, part=-1):
+        self._ck(self.L.gpb_half_step(self.h, int(phase), int(part)))
 
     def profile(self, n):
         """Device milliseconds {prologue, H update, E update, sources} over n plain-launch iterations."""

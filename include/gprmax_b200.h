@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GPB_ABI_VERSION 1
+#define GPB_ABI_VERSION 2
 
 enum { GPB_F32 = 0, GPB_F64 = 1 };
 enum { GPB_HORIPML = 0, GPB_MRIPML = 1 };                       /* pml.py:155 */
@@ -109,7 +109,8 @@ typedef struct gpb_model_t {
     double dx, dy, dz, dt;
     int32_t iterations;
     int32_t nmaterials;
-    const uint32_t *ID;                /* [6][nx_planes][ny+1][nz+1] */
+    const uint32_t *ID;                /* [6][nx_planes][ny+1][nz+1]; NULL = homogeneous: every edge is `uniform_id` */
+    int32_t uniform_id;                /* used only when ID == NULL (synthetic multi-billion-cell domains) */
     const void *updatecoeffsE;         /* R[nmaterials][5]  materials.py:200 */
     const void *updatecoeffsH;         /* R[nmaterials][5]  materials.py:201 */
     int32_t maxpoles;                  /* Material.maxpoles */
@@ -154,8 +155,13 @@ int gpb_profile(gpb_handle h, int n_iters, double *ms4);
 
 /* ---- sharded stepping (one handle per x-slab; the host moves the halo planes between calls) ----
  * phase 0: rx store + snapshots + H half-step (needs the Ey,Ez ghost plane at x_start+nx_planes)
- * phase 1: E half-step                        (needs the Hy,Hz ghost plane at x_start-1)       */
-int gpb_half_step(gpb_handle h, int phase);
+ * phase 1: E half-step                        (needs the Hy,Hz ghost plane at x_start-1)
+ * part  0: step prologue (phase 0 only) and the ONE plane whose result the neighbour needs
+ *          (phase 0: last owned plane, phase 1: first owned plane) -- after this call the send halo
+ *          of gpb_halo() is final (unless a point source sits on that plane; then send after part 1)
+ * part  1: all remaining planes and the point sources of the phase
+ * part -1: both.  All launches go to the handle's stream (gpb_stream); nothing here synchronises. */
+int gpb_half_step(gpb_handle h, int phase, int part);
 /* Device pointers (and byte size) of the contiguous halo planes:
  * which = 0: send  E (Ey then Ez, first owned plane)      -> left neighbour's recv E
  * which = 1: recv  E (Ey then Ez, ghost plane after last)
