@@ -181,8 +181,13 @@ def run_single_gpu(args):
         alg_bytes = cells * b_alg / 2.0  # one half-step
         achieved = alg_bytes / t_launch / 1e9
         share = prof[dom] / max(sum(prof.values()), 1e-30)
-        roof = {'bound': 'hbm', 'kernel': 'k_' + dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'alg_bytes_per_launch': alg_bytes, 'launch_ms': t_launch * 1e3,
+        # DRAM bytes per launch from the committed ncu --set full capture of the same workload (profiles/README.md):
+        # k_update_tma 818+319 MB and its k_pml_slabs 141+16 MB at 300^3; only quoted for that exact workload
+        traffic = 1.294e9 if N == 300 else None
+        roof = {'bound': 'hbm', 'kernel': 'half-step launch pair: k_update_tma<PHASE={}> + k_pml_slabs ({})'.format(1 if dom == 'update_e' else 0, dom),
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': traffic, 'traffic_source': 'profiles/r1e_main_raw.csv + r1e_pml_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum)',
+                'peak_source': peak_src, 'alg_bytes_per_launch': alg_bytes, 'launch_ms': t_launch * 1e3,
                 'share_of_step': share, 'whole_step_frac': value * 1e6 * b_alg / 1e9 / peak,
                 'kernel_ms_per_iteration': {k: v / nprof_timed for k, v in prof.items()}}
 

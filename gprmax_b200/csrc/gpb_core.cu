@@ -74,7 +74,7 @@ struct Solver : SolverBase {
     bool use_v4 = false;       // vectorised non-dispersive path (gpb_kernels_v4.cuh)
     bool use_tma = false;      // TMA-staged path (gpb_kernels_tma.cuh)
     int tma_ty = 0, tma_tz = 0, tma_stages = 0, tma_xchunk = 16;
-    bool tma_zfused = false, tma_ztail = true;
+    bool tma_zfused = false, tma_ztail = false;
     TmaMaps9 maps_e, maps_h;
     int setup_tma();
     template <typename IDT, int TY, int TZ, int S>
@@ -526,10 +526,10 @@ int Solver<R>::build(const gpb_model_t &m)
     // TMA-staged path: 3-D grids with reasonably long z rows (2-D / thin grids stay on the flattened v4 path)
     use_tma = use_v4 && nz + 1 >= 32 && ny + 1 >= 8 && !getenv("GPB_NO_TMA") && (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R)) <= 32 * 1024;
     if (use_tma && setup_tma()) return 1;
-    // z-slab PML: default = per-CTA tail inside the TMA kernel; GPB_TMA_ZSPLIT = separate k_pml_slabs launch;
+    // z-slab PML: default = separate k_pml_slabs launch (measured fastest); GPB_TMA_ZTAIL = per-CTA tail in the TMA kernel;
     // GPB_TMA_ZFUSE = inside the main loop (divergent scalar terms, measured slower)
     tma_zfused = getenv("GPB_TMA_ZFUSE") != nullptr;
-    tma_ztail = !tma_zfused && !getenv("GPB_TMA_ZSPLIT");
+    tma_ztail = !tma_zfused && getenv("GPB_TMA_ZTAIL") != nullptr;
     if (use_v4) {
         for (int s = 0; s < ph_e.nslabs; ++s)
             if (ph_e.slab[s].axis == 2) zslabs_e |= 1u << s;
