@@ -238,13 +238,20 @@ def main():
     ap.add_argument('--iters', type=int, default=None, help='iterations per step (default: the model\'s own 1559)')
     ap.add_argument('--cpu-iters', type=int, default=40, help='iterations of the CPU baseline sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--workload', default='auto', choices=['auto', 'slab'], help="'slab' at N=1: run the sharded runs' per-GPU slab on one GPU")
     ap.add_argument('--e2e-full', action='store_true', help='run the e2e leg warmup+steps times instead of 1+2')
     args = ap.parse_args()
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     if args.impl == 'reference':
         return run_reference_arm(args)
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    if args.gpus > 1 or world > 1:
+    if args.gpus > 1 or world > 1 or args.workload == 'slab':
+        # N = 1 with --workload slab: the per-GPU slab of the sharded runs on one GPU (weak-scaling baseline)
+        if world == 1 and args.gpus == 1:
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            os.environ.setdefault('MASTER_PORT', '29517')
+            os.environ.setdefault('RANK', '0')
+            os.environ.setdefault('WORLD_SIZE', '1')
         from gprmax_b200.sharded import bench_sharded
         return bench_sharded(args)
     return run_single_gpu(args)

@@ -74,7 +74,8 @@ struct Solver : SolverBase {
     bool use_v4 = false;       // vectorised non-dispersive path (gpb_kernels_v4.cuh)
     bool use_tma = false;      // TMA-staged path (gpb_kernels_tma.cuh)
     int tma_ty = 0, tma_tz = 0, tma_stages = 0, tma_xchunk = 16;
-    bool tma_zfused = false, tma_ztail = false;
+    bool tma_zcoop = false;    // z-slab PML inside the TMA kernels (cooperative, through shared memory)
+    size_t tma_zbytes = 0;
     TmaMaps9 maps_e, maps_h;
     int setup_tma();
     template <typename IDT, int TY, int TZ, int S>
@@ -213,8 +214,10 @@ static int make_map(CUtensorMap *out, void *base, CUtensorMapDataType dt, size_t
     const cuuint64_t strides[2] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * rows * es};
     const cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char *e = getenv("GPB_TMA_L2")) promo = atoi(e) == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (atoi(e) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (atoi(e) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo));
     CUresult r = fn(out, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code %d (pitch %d rows %d planes %d box %d x %d)", (int)r, pitch, rows, planes, b0, b1);
     return 0;
 }
@@ -526,10 +529,28 @@ int Solver<R>::build(const gpb_model_t &m)
     // TMA-staged path: 3-D grids with reasonably long z rows (2-D / thin grids stay on the flattened v4 path)
     use_tma = use_v4 && nz + 1 >= 32 && ny + 1 >= 8 && !getenv("GPB_NO_TMA") && (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R)) <= 32 * 1024;
     if (use_tma && setup_tma()) return 1;
-    // z-slab PML: default = separate k_pml_slabs launch (measured fastest); GPB_TMA_ZTAIL = per-CTA tail in the TMA kernel;
-    // GPB_TMA_ZFUSE = inside the main loop (divergent scalar terms, measured slower)
-    tma_zfused = getenv("GPB_TMA_ZFUSE") != nullptr;
-    tma_ztail = !tma_zfused && getenv("GPB_TMA_ZTAIL") != nullptr;
+    // z-slab PML on the TMA path: in the same pass, handed to all threads of a CTA through shared memory
+    // (gpb_kernels_tma.cuh), when every k-tile meets at most one z slab with at most 16 of its cells and the
+    // march is short enough for the Phi prefetch buffer.  Opt-in (GPB_TMA_ZCOOP): measured 45.0 vs 47.1
+    // Gcells/s for the separate k_pml_slabs launch at 300^3 (the k-end CTAs become the critical path).
+    tma_zcoop = false;
+    if (use_tma && getenv("GPB_TMA_ZCOOP") && tma_xchunk <= 8) {
+        bool ok = true, anyz = false;
+        for (const PhaseParams<R> *ph : {&ph_e, &ph_h})
+            for (int k0 = 0; k0 < pitch; k0 += tma_tz) {
+                int cnt = 0;
+                for (int s = 0; s < ph->nslabs; ++s) {
+                    const SlabDev<R> &sl = ph->slab[s];
+                    if (sl.axis != 2 || sl.lo[2] >= k0 + tma_tz || sl.hi[2] <= k0) continue;
+                    ++cnt;
+                    anyz = true;
+                    if (std::min(sl.hi[2], k0 + tma_tz) - std::max(sl.lo[2], k0) > 16) ok = false;
+                }
+                if (cnt > 1) ok = false;
+            }
+        tma_zcoop = ok && anyz;
+        tma_zbytes = tma_zcoop ? (size_t)tma_ty * 16 * (4 * sizeof(R) + 8 + (size_t)tma_xchunk * 2 * order * sizeof(R)) + 16 * sizeof(PmlCo<R>) : 0;
+    }
     if (use_v4) {
         for (int s = 0; s < ph_e.nslabs; ++s)
             if (ph_e.slab[s].axis == 2) zslabs_e |= 1u << s;
@@ -560,6 +581,7 @@ int Solver<R>::setup_tma()
         if (waste < best * 0.92) { best = waste; tma_ty = c[0]; tma_tz = c[1]; }
     }
     if (getenv("GPB_TMA_TZ")) { tma_tz = atoi(getenv("GPB_TMA_TZ")); tma_ty = 1024 / tma_tz; }
+    if (getenv("GPB_TMA_TY")) tma_ty = atoi(getenv("GPB_TMA_TY"));
     tma_stages = getenv("GPB_TMA_STAGES") ? atoi(getenv("GPB_TMA_STAGES")) : 3;
     const CUtensorMapDataType fdt = sizeof(R) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
     const CUtensorMapDataType idt = idbytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (idbytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32);
@@ -604,22 +626,31 @@ int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
 {
     using L = StageLayout<R, IDT, TY, TZ>;
     PhaseParams<R> p = phase == 0 ? ph_h : ph_e;
-    p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk; p.zfused = tma_zfused ? 1 : 0; p.ztail = tma_ztail ? 1 : 0;
+    p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk; p.zcoop = tma_zcoop ? 1 : 0;
+    // planes on which a thread whose 4 cells are interior in (j,k) needs no mask / slab logic at all
+    p.fast_i0 = std::max(p.box[0].lo[0], std::max(p.box[1].lo[0], p.box[2].lo[0]));
+    p.fast_i1 = std::min(p.box[0].hi[0], std::min(p.box[1].hi[0], p.box[2].hi[0]));
+    for (int s = 0; s < p.nslabs; ++s)
+        if (p.slab[s].axis == 0) {
+            if (p.slab[s].minus) p.fast_i0 = std::max(p.fast_i0, p.slab[s].hi[0]);
+            else p.fast_i1 = std::min(p.fast_i1, p.slab[s].lo[0]);
+        }
+    if (getenv("GPB_TMA_NOFAST")) p.fast_i1 = p.fast_i0;
     const int tiles_k = (pitch + TZ - 1) / TZ, tiles_j = (ny + 1 + TY - 1) / TY;
-    const size_t smem = 128 + (size_t)((nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128) + (size_t)S * L::bytes;
+    const size_t smem = 128 + (size_t)((nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128) + (size_t)S * L::bytes + tma_zbytes;
     dim3 grid((unsigned)(tiles_k * tiles_j), (unsigned)((p1 - p0 + tma_xchunk - 1) / tma_xchunk));
     if (phase == 0) {
         auto kern = k_update_tma<R, IDT, TY, TZ, S, 0>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kTmaThreads, smem, stream>>>(p, maps_h, tiles_k);
+        kern<<<grid, TY * TZ / 4, smem, stream>>>(p, maps_h, tiles_k);
     } else {
         auto kern = k_update_tma<R, IDT, TY, TZ, S, 1>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kTmaThreads, smem, stream>>>(p, maps_e, tiles_k);
+        kern<<<grid, TY * TZ / 4, smem, stream>>>(p, maps_e, tiles_k);
     }
     CK(cudaGetLastError());
     ++launches;
-    const unsigned zs = (tma_zfused || tma_ztail) ? 0u : (phase == 0 ? zslabs_h : zslabs_e);
+    const unsigned zs = tma_zcoop ? 0u : (phase == 0 ? zslabs_h : zslabs_e);
     if (zs) {
         int cells = 0, planes = 0;
         for (int s = 0; s < p.nslabs; ++s)
@@ -627,7 +658,7 @@ int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
                 cells = std::max(cells, (p.slab[s].hi[1] - p.slab[s].lo[1]) * (p.slab[s].hi[2] - p.slab[s].lo[2]));
                 planes = std::max(planes, p.slab[s].hi[0] - p.slab[s].lo[0]);
             }
-        dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes);
+        dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes, (unsigned)__builtin_popcount(zs));
         k_pml_slabs<R, IDT><<<g2, 256, 0, stream>>>(p, phase, zs, p0, p1);
         CK(cudaGetLastError());
         ++launches;
@@ -640,13 +671,15 @@ template <typename IDT>
 int Solver<R>::launch_tma(int phase, int p0, int p1)
 {
 #define GPB_TMA_CASE(TY_, TZ_, S_) if (tma_ty == TY_ && tma_tz == TZ_ && tma_stages == S_) return launch_tma_cfg<IDT, TY_, TZ_, S_>(phase, p0, p1)
-    GPB_TMA_CASE(16, 64, 4);
     GPB_TMA_CASE(16, 64, 3);
-    GPB_TMA_CASE(16, 64, 6);
-    GPB_TMA_CASE(8, 128, 4);
+    GPB_TMA_CASE(16, 64, 4);
     GPB_TMA_CASE(8, 128, 3);
-    GPB_TMA_CASE(32, 32, 4);
     GPB_TMA_CASE(32, 32, 3);
+    GPB_TMA_CASE(8, 64, 4);
+    GPB_TMA_CASE(8, 64, 5);
+    GPB_TMA_CASE(8, 64, 6);
+    GPB_TMA_CASE(4, 128, 5);
+    GPB_TMA_CASE(4, 128, 6);
 #undef GPB_TMA_CASE
     return fail("no TMA kernel instantiated for tile %d x %d with %d stages", tma_ty, tma_tz, tma_stages);
 }
@@ -670,7 +703,7 @@ int Solver<R>::launch_h(int p0, int p1)
                     cells = std::max(cells, (p.slab[s].hi[1] - p.slab[s].lo[1]) * (p.slab[s].hi[2] - p.slab[s].lo[2]));
                     planes = std::max(planes, p.slab[s].hi[0] - p.slab[s].lo[0]);
                 }
-            dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes);
+            dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes, (unsigned)__builtin_popcount(zslabs_h));
             k_pml_slabs<R, IDT><<<g2, 256, 0, stream>>>(p, 0, zslabs_h, p0, p1);
             CK(cudaGetLastError());
             ++launches;
@@ -704,7 +737,7 @@ int Solver<R>::launch_e(int p0, int p1)
                     cells = std::max(cells, (p.slab[s].hi[1] - p.slab[s].lo[1]) * (p.slab[s].hi[2] - p.slab[s].lo[2]));
                     planes = std::max(planes, p.slab[s].hi[0] - p.slab[s].lo[0]);
                 }
-            dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes);
+            dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes, (unsigned)__builtin_popcount(zslabs_e));
             k_pml_slabs<R, IDT><<<g2, 256, 0, stream>>>(p, 1, zslabs_e, p0, p1);
             CK(cudaGetLastError());
             ++launches;

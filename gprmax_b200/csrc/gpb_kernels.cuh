@@ -85,8 +85,8 @@ struct PhaseParams {
     // sub-range of owned planes processed by this launch (for halo overlap): [p0, p1)
     int p0, p1;
     int xchunk;               // planes marched by one CTA of the TMA kernels
-    int zfused;               // TMA kernels: apply z-slab PML inside the main loop (divergent; measured slower)
-    int ztail;                // TMA kernels: apply z-slab PML as a per-CTA tail after the march
+    int fast_i0, fast_i1;     // TMA kernels: planes between the x slabs and inside all three update boxes
+    int zcoop;                // TMA kernels: apply z-slab PML in the same pass, cooperatively through shared memory
 };
 
 // ------------------------------------------------------------------------------------------

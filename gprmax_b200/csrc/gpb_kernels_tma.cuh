@@ -13,7 +13,8 @@
 //     kStages planes (~30 KB each) are in flight per CTA regardless of register pressure;
 //   * the x-neighbour plane (i-1 for E, i+1 for H) rides in a register queue as before;
 //   * results go straight from registers to global memory with 128-bit stores.
-// x / y PML slabs are applied in the same pass (vectorised, warp-uniform); z slabs by k_pml_slabs.
+// x / y PML slabs are applied in the same pass (vectorised, warp-uniform); z slabs either by k_pml_slabs
+// or (p.zcoop) in the same pass, handed to all threads of the CTA through shared memory.
 #pragma once
 #include <cuda.h>
 
@@ -21,7 +22,6 @@
 
 namespace gpb {
 
-constexpr int kTmaThreads = 256;
 
 struct TmaMaps9 {
     CUtensorMap opA;   // operand with both halos   (E phase: Hx ; H phase: Ex)  box (TZ+4) x (TY+1)
@@ -42,6 +42,10 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -113,12 +117,14 @@ __device__ __forceinline__ Ids4 lds_ids4<uint32_t>(const unsigned char *base, in
 // Shared memory: [kStages mbarriers][coefficient rows][kStages stages]
 // ------------------------------------------------------------------------------------------
 template <typename R, typename IDT, int TY, int TZ, int kStages, int PHASE>
-__global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int tiles_k)
+__global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? 512 / (TY * TZ / 4) : 1)) k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int tiles_k)
 {
-    static_assert(TY * TZ / 4 == kTmaThreads, "tile must give every thread 4 cells");
+    constexpr int kTmaThreads = TY * TZ / 4;  // every thread owns 4 consecutive z cells of the tile
+    static_assert(kTmaThreads % 32 == 0 && kTmaThreads <= 256, "tile shape");
     using L = StageLayout<R, IDT, TY, TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);   // [kStages] TMA bytes landed
+    uint64_t *empty = full + kStages;                           // [kStages] all 8 warps have read the stage
     Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw + 128);
     R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
     const int coef_bytes = (int)((p.nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128);
@@ -135,7 +141,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
     const int nl = l1 - l0;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, kTmaThreads / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&maps.opA);
         tma_prefetch_desc(&maps.opB);
@@ -180,8 +189,63 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
     unsigned smask = 0;
 #pragma unroll
     for (int s = 0; s < kMaxSlabs; ++s)
-        if (s < p.nslabs && (p.slab[s].axis != 2 || p.zfused) && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
-    const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u);
+        if (s < p.nslabs && p.slab[s].axis != 2 && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
+
+    // ---- cooperative z-slab PML (p.zcoop): the z-slab cells of this tile (first / last `thickness` cells
+    // of its z rows, at most kZC per row) are handed through shared memory to ALL threads of the CTA, one
+    // slab cell per thread, instead of diverging in the few lanes that own them.  Phi of those cells for the
+    // whole march is prefetched into shared memory with cp.async while the TMA pipeline fills.
+    constexpr int kZC = 16;
+    int zs = -1, ka = 0, kb = 0, zja = 0, zjb = 0;
+    if (p.zcoop)
+        for (int s = 0; s < p.nslabs; ++s)
+            if (p.slab[s].axis == 2 && p.slab[s].lo[2] < k0 + TZ && p.slab[s].hi[2] > k0) {
+                zs = s;
+                ka = max(p.slab[s].lo[2], k0);
+                kb = min(p.slab[s].hi[2], k0 + TZ);
+                zja = max(p.slab[s].lo[1], j0);
+                zjb = min(p.slab[s].hi[1], j0 + TY);
+            }
+    const bool zwork = zs >= 0 && kb > ka && zjb > zja;
+    unsigned zmask = 0;  // my cells inside the CTA's z-slab footprint
+    if (zwork && valid && j >= zja && j < zjb)
+        for (int q = 0; q < 4; ++q)
+            if (k + q >= ka && k + q < kb) zmask |= 1u << q;
+    const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u || zmask != 0u);
+    // fast path: all 4 cells inside all three update boxes and outside every y/z-slab footprint; then on
+    // the planes between the x slabs (p.fast_i0 <= i < p.fast_i1) the update is straight-line code
+    unsigned yfoot = 0;
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s)
+        if (s < p.nslabs && p.slab[s].axis == 1) yfoot |= (smask >> (4 * s)) & 0xfu;
+    const bool fast_jk = valid && bx.kmask == 0xfu && by.kmask == 0xfu && bz.kmask == 0xfu && yfoot == 0u && zmask == 0u;
+    // scratch after the stages: 4 value tiles + 2 id tiles [TY][kZC], then Phi [xchunk][2*order][TY][kZC]
+    R *zF0 = reinterpret_cast<R *>(stages + (size_t)kStages * L::bytes);
+    R *zF1 = zF0 + TY * kZC, *zDB = zF1 + TY * kZC, *zDA = zDB + TY * kZC;
+    unsigned *zI0 = reinterpret_cast<unsigned *>(zDA + TY * kZC), *zI1 = zI0 + TY * kZC;
+    PmlCo<R> *zCo = reinterpret_cast<PmlCo<R> *>(zI1 + TY * kZC);   // one coefficient set per slab depth
+    R *zPhi = reinterpret_cast<R *>(zCo + kZC);
+    const int nphi = 2 * p.order;
+    if (zwork) {
+        const SlabDev<R> &sl = p.slab[zs];
+        if (tid < kb - ka) {
+            const int kq = ka + tid;
+            zCo[tid] = pml_load(p.form, p.order, sl, sl.minus ? (sl.dref - kq) : (kq - sl.dref));
+        }
+        for (int t = tid; t < nl * nphi * TY * kZC; t += kTmaThreads) {
+            const int cc = t % kZC, rr = (t / kZC) % TY, v = (t / (kZC * TY)) % nphi, n = t / (kZC * TY * nphi);
+            const int jj = j0 + rr, kq = ka + cc;
+            const int ii = p.x_start + (PHASE == 1 ? (l0 + n) : (l1 - 1 - n));
+            if (jj >= zja && jj < zjb && kq < kb && ii >= sl.lo[0] && ii < sl.hi[0]) {
+                const R *src = sl.phi + (long long)v * sl.ostride + ((long long)(ii - sl.lo[0]) * sl.n1 + (jj - sl.lo[1])) * sl.n2 + (kq - sl.lo[2]);
+                if (sizeof(R) == 4)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zPhi + t)), "l"(src) : "memory");
+                else
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(zPhi + t)), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     // fields this phase writes / queue operands (the operand arrays are read-only in this phase)
     R *__restrict__ F0 = PHASE == 1 ? p.Ex : p.Hx;
@@ -193,6 +257,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
     // x-neighbour plane of the first processed plane: i-1 (E phase) / i+1 (H phase)
     V4<R> qb = ld4(QB + (long long)(PHASE == 1 ? plane_of(0) - 1 : plane_of(0) + 1) * p.plane + eoff);
     V4<R> qc = ld4(QC + (long long)(PHASE == 1 ? plane_of(0) - 1 : plane_of(0) + 1) * p.plane + eoff);
+    if (zwork) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+    }
 
     for (int n = 0; n < nl; ++n) {
         const int pl = plane_of(n);
@@ -236,23 +304,76 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
         V4<R> f1 = ld4(reinterpret_cast<const R *>(st + L::oO1) + e);
         V4<R> f2 = ld4(reinterpret_cast<const R *>(st + L::oO2) + e);
         const Ids4 id0 = lds_ids4<IDT>(st + L::oI0, e), id1 = lds_ids4<IDT>(st + L::oI1, e), id2 = lds_ids4<IDT>(st + L::oI2, e);
-        __syncthreads();  // every thread has taken what it needs from this stage
-        if (tid == 0 && n + kStages < nl) issue(n + kStages);
+        // this warp has taken what it needs from the stage.  No CTA-wide barrier: warps drift freely (the
+        // first ncu capture showed barrier stalls on top); the refill is issued by thread 0 once all 8
+        // warps have arrived on the stage's `empty` mbarrier (after its own compute, below).
+        if (p.zcoop) {
+            __syncthreads();
+            if (tid == 0 && n + kStages < nl) issue(n + kStages);
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + (n % kStages));
+        }
 
-        if (any) {
-            // one-sided differences.  E phase: backward (c - neighbour); H phase: forward (neighbour - c)
-            V4<R> dA_dy, dA_dz, dB_dz, dB_dx, dC_dx, dC_dy;
+        bool w0 = false, w1 = false, w2 = false;
+        // one-sided differences along z (also needed by the z-slab hand-off below)
+        V4<R> dA_dz, dB_dz;
+        if (PHASE == 1) {
+            dA_dz = {a_c.x - a_k, a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z};       // dHx/dz
+            dB_dz = {b_c.x - b_k, b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z};       // dHy/dz
+        } else {
+            dA_dz = {a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z, a_k - a_c.w};       // dEx/dz
+            dB_dz = {b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z, b_k - b_c.w};       // dEy/dz
+        }
+        if (fast_jk && i >= p.fast_i0 && i < p.fast_i1) {
+            Coef4<R> q0, q1, q2, q3;
+            coef4(scoef, id0, q0, q1, q2, q3);
+            if (PHASE == 1) {
+                f0.x = q0.a * f0.x + q0.by * (c_c.x - c_j.x) - q0.bz * dB_dz.x;
+                f0.y = q1.a * f0.y + q1.by * (c_c.y - c_j.y) - q1.bz * dB_dz.y;
+                f0.z = q2.a * f0.z + q2.by * (c_c.z - c_j.z) - q2.bz * dB_dz.z;
+                f0.w = q3.a * f0.w + q3.by * (c_c.w - c_j.w) - q3.bz * dB_dz.w;
+            } else {
+                f0.x = q0.a * f0.x - q0.by * (c_j.x - c_c.x) + q0.bz * dB_dz.x;
+                f0.y = q1.a * f0.y - q1.by * (c_j.y - c_c.y) + q1.bz * dB_dz.y;
+                f0.z = q2.a * f0.z - q2.by * (c_j.z - c_c.z) + q2.bz * dB_dz.z;
+                f0.w = q3.a * f0.w - q3.by * (c_j.w - c_c.w) + q3.bz * dB_dz.w;
+            }
+            coef4(scoef, id1, q0, q1, q2, q3);
+            if (PHASE == 1) {
+                f1.x = q0.a * f1.x + q0.bz * dA_dz.x - q0.bx * (c_c.x - qc.x);
+                f1.y = q1.a * f1.y + q1.bz * dA_dz.y - q1.bx * (c_c.y - qc.y);
+                f1.z = q2.a * f1.z + q2.bz * dA_dz.z - q2.bx * (c_c.z - qc.z);
+                f1.w = q3.a * f1.w + q3.bz * dA_dz.w - q3.bx * (c_c.w - qc.w);
+            } else {
+                f1.x = q0.a * f1.x - q0.bz * dA_dz.x + q0.bx * (qc.x - c_c.x);
+                f1.y = q1.a * f1.y - q1.bz * dA_dz.y + q1.bx * (qc.y - c_c.y);
+                f1.z = q2.a * f1.z - q2.bz * dA_dz.z + q2.bx * (qc.z - c_c.z);
+                f1.w = q3.a * f1.w - q3.bz * dA_dz.w + q3.bx * (qc.w - c_c.w);
+            }
+            coef4(scoef, id2, q0, q1, q2, q3);
+            if (PHASE == 1) {
+                f2.x = q0.a * f2.x + q0.bx * (b_c.x - qb.x) - q0.by * (a_c.x - a_j.x);
+                f2.y = q1.a * f2.y + q1.bx * (b_c.y - qb.y) - q1.by * (a_c.y - a_j.y);
+                f2.z = q2.a * f2.z + q2.bx * (b_c.z - qb.z) - q2.by * (a_c.z - a_j.z);
+                f2.w = q3.a * f2.w + q3.bx * (b_c.w - qb.w) - q3.by * (a_c.w - a_j.w);
+            } else {
+                f2.x = q0.a * f2.x - q0.bx * (qb.x - b_c.x) + q0.by * (a_j.x - a_c.x);
+                f2.y = q1.a * f2.y - q1.bx * (qb.y - b_c.y) + q1.by * (a_j.y - a_c.y);
+                f2.z = q2.a * f2.z - q2.bx * (qb.z - b_c.z) + q2.by * (a_j.z - a_c.z);
+                f2.w = q3.a * f2.w - q3.bx * (qb.w - b_c.w) + q3.by * (a_j.w - a_c.w);
+            }
+            w0 = w1 = w2 = true;
+        } else if (any) {
+            // E phase: backward differences (c - neighbour); H phase: forward (neighbour - c)
+            V4<R> dA_dy, dB_dx, dC_dx, dC_dy;
             if (PHASE == 1) {
                 dA_dy = {a_c.x - a_j.x, a_c.y - a_j.y, a_c.z - a_j.z, a_c.w - a_j.w};   // dHx/dy
-                dA_dz = {a_c.x - a_k, a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z};       // dHx/dz
-                dB_dz = {b_c.x - b_k, b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z};       // dHy/dz
                 dB_dx = {b_c.x - qb.x, b_c.y - qb.y, b_c.z - qb.z, b_c.w - qb.w};         // dHy/dx
                 dC_dx = {c_c.x - qc.x, c_c.y - qc.y, c_c.z - qc.z, c_c.w - qc.w};         // dHz/dx
                 dC_dy = {c_c.x - c_j.x, c_c.y - c_j.y, c_c.z - c_j.z, c_c.w - c_j.w};   // dHz/dy
             } else {
                 dA_dy = {a_j.x - a_c.x, a_j.y - a_c.y, a_j.z - a_c.z, a_j.w - a_c.w};   // dEx/dy
-                dA_dz = {a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z, a_k - a_c.w};       // dEx/dz
-                dB_dz = {b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z, b_k - b_c.w};       // dEy/dz
                 dB_dx = {qb.x - b_c.x, qb.y - b_c.y, qb.z - b_c.z, qb.w - b_c.w};         // dEy/dx
                 dC_dx = {qc.x - c_c.x, qc.y - c_c.y, qc.z - c_c.z, qc.w - c_c.w};         // dEz/dx
                 dC_dy = {c_j.x - c_c.x, c_j.y - c_c.y, c_j.z - c_c.z, c_j.w - c_c.w};   // dEz/dy
@@ -264,7 +385,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
 #pragma unroll
             for (int s = 0; s < kMaxSlabs; ++s)
                 if (((smask >> (4 * s)) & 0xfu) && i >= p.slab[s].lo[0] && i < p.slab[s].hi[0]) pm |= 1u << s;
-            bool w0 = m0 != 0, w1 = m1 != 0, w2 = m2 != 0;
+            w0 = m0 != 0; w1 = m1 != 0; w2 = m2 != 0;
             // E phase: Ex = CA Ex + CBy dHz/dy - CBz dHy/dz ; Ey = CA Ey + CBz dHx/dz - CBx dHz/dx ; Ez = CA Ez + CBx dHy/dx - CBy dHx/dy
             // H phase: Hx = DA Hx - DBy dEz/dy + DBz dEy/dz ; Hy = DA Hy - DBz dEx/dz + DBx dEz/dx ; Hz = DA Hz - DBx dEy/dx + DBy dEx/dy
             if (m0) {
@@ -317,27 +438,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
                     if (!((pm >> s) & 1u)) continue;
                     const SlabDev<R> &sl = p.slab[s];
                     const unsigned m = (smask >> (4 * s)) & 0xfu;
-                    if (sl.axis == 2) {
-                        // z slab: every cell of the thread has its own depth; scalar terms on the (few) lanes
-                        // that sit in the first / last `thickness` cells of a z row.
-                        // E phase: Ex -= , dHy/dz ; Ey += , dHx/dz   H phase: Hx += , dEy/dz ; Hy -= , dEx/dz
-                        R *phirow = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 - sl.lo[2];
-                        const R s0 = PHASE == 1 ? (R)-1 : (R)1, s1 = -s0;
-#define GPB_ZCELL(q, comp, idq)                                                                                                   \
-    if ((m >> q) & 1u) {                                                                                                          \
-        const int kq = k + q;                                                                                                     \
-        const int depth = sl.minus ? (sl.dref - kq) : (kq - sl.dref);                                                             \
-        f0.comp = f0.comp + s0 * (ssrc[id0.idq] * pml_term(p.form, p.order, sl, depth, dB_dz.comp / sl.d, phirow + kq, sl.ostride)); \
-        f1.comp = f1.comp + s1 * (ssrc[id1.idq] * pml_term(p.form, p.order, sl, depth, dA_dz.comp / sl.d, phirow + kq + sl.ostride, sl.ostride)); \
-    }
-                        GPB_ZCELL(0, x, a)
-                        GPB_ZCELL(1, y, b)
-                        GPB_ZCELL(2, z, c)
-                        GPB_ZCELL(3, w, d)
-#undef GPB_ZCELL
-                        w0 = w1 = true;
-                        continue;
-                    }
                     const int pos = sl.axis == 0 ? i : j;
                     const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
                     const PmlCo<R> co = pml_load(p.form, p.order, sl, depth);
@@ -365,38 +465,59 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_update_tma(const PhaseParams
                     }
                 }
             }
+        }
+
+        if (any) {
             const long long off = (long long)pl * p.plane + eoff;
             if (w0) st4(F0 + off, f0);
             if (w1) st4(F1 + off, f1);
             if (w2) st4(F2 + off, f2);
         }
-        qb = b_c;
-        qc = c_c;
-    }
+        if (!p.zcoop && tid == 0 && n + kStages < nl) {
+            mbar_wait(empty + (n % kStages), (uint32_t)((n / kStages) & 1));
+            issue(n + kStages);
+        }
 
-    // z-slab PML tail: the z-slab cells of this CTA's tile x march (first / last `thickness` cells of
-    // its z rows) are corrected here by all 256 threads, one cell each per round, right after the CTA
-    // wrote them -- the lines are still in L2, and the main loop above stays divergence-free.
-    if (p.ztail) {
-        bool mine = false;
-        for (int s = 0; s < p.nslabs; ++s)
-            if (p.slab[s].axis == 2 && p.slab[s].lo[2] < k0 + TZ && p.slab[s].hi[2] > k0) mine = true;
-        if (mine) {
-            __syncthreads();  // this CTA's stores of the march are visible to all of its threads
-            for (int s = 0; s < p.nslabs; ++s) {
-                const SlabDev<R> &sl = p.slab[s];
-                if (sl.axis != 2) continue;
-                const int ka = max(sl.lo[2], k0), kb = min(sl.hi[2], k0 + TZ);
-                const int ja = max(sl.lo[1], j0), jb = min(sl.hi[1], j0 + TY);
-                const int ia = max(sl.lo[0], p.x_start + l0), ib = min(sl.hi[0], p.x_start + l1);
-                const int nk = kb - ka, nj = jb - ja, ni = ib - ia;
-                if (nk <= 0 || nj <= 0 || ni <= 0) continue;
-                for (int t = tid; t < ni * nj * nk; t += kTmaThreads) {
-                    const int kk = t % nk, jj = (t / nk) % nj, ii = t / (nk * nj);
-                    pml_slab_cell<R, IDT>(p, PHASE, sl, ia + ii, ja + jj, ka + kk);
-                }
+        // ---- cooperative z-slab PML for this plane (CTA-uniform condition).  The owners hand the values of
+        // their z-slab cells over through shared memory; after one barrier every thread corrects one slab cell
+        // and overwrites it in global memory (ordered after the owner's 128-bit store by the barrier).
+        if (zwork && i >= p.slab[zs].lo[0] && i < p.slab[zs].hi[0]) {
+            const SlabDev<R> &sl = p.slab[zs];
+            if (zmask) {
+#define GPB_ZPUT(q, comp, idq)                                   \
+    if ((zmask >> q) & 1u) {                                     \
+        const int o = r * kZC + (k + q - ka);                    \
+        zF0[o] = f0.comp; zF1[o] = f1.comp;                      \
+        zDB[o] = dB_dz.comp; zDA[o] = dA_dz.comp;                \
+        zI0[o] = id0.idq; zI1[o] = id1.idq;                      \
+    }
+                GPB_ZPUT(0, x, a) GPB_ZPUT(1, y, b) GPB_ZPUT(2, z, c) GPB_ZPUT(3, w, d)
+#undef GPB_ZPUT
+            }
+            __syncthreads();
+            // E phase: Ex -= , dHy/dz (Phi1) ; Ey += , dHx/dz (Phi2)   H phase: Hx += , dEy/dz ; Hy -= , dEx/dz
+            const R s0 = PHASE == 1 ? (R)-1 : (R)1, s1 = -s0;
+            for (int t = tid; t < TY * kZC; t += kTmaThreads) {
+                const int cc = t % kZC, rr = t / kZC;
+                const int jj = j0 + rr, kq = ka + cc;
+                if (jj < zja || jj >= zjb || kq >= kb) continue;
+                const PmlCo<R> co = zCo[cc];
+                R *sp = zPhi + ((size_t)n * nphi) * TY * kZC + t;   // [n][v][rr][cc], v = comp + 2*order_index
+                R *gp = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (jj - sl.lo[1])) * sl.n2 + (kq - sl.lo[2]);
+                R p10 = sp[0], p20 = sp[TY * kZC], p11 = 0, p21 = 0;
+                if (p.order == 2) { p11 = sp[2 * TY * kZC]; p21 = sp[3 * TY * kZC]; }
+                const R t0 = pml_apply(p.form, p.order, co, zDB[t] / sl.d, p10, p11);
+                const R t1 = pml_apply(p.form, p.order, co, zDA[t] / sl.d, p20, p21);
+                const long long go = (long long)pl * p.plane + (long long)jj * p.pitch + kq;
+                F0[go] = zF0[t] + s0 * (ssrc[zI0[t]] * t0);
+                F1[go] = zF1[t] + s1 * (ssrc[zI1[t]] * t1);
+                gp[0] = p10;
+                gp[sl.ostride] = p20;
+                if (p.order == 2) { gp[2 * sl.ostride] = p11; gp[3 * sl.ostride] = p21; }
             }
         }
+        qb = b_c;
+        qc = c_c;
     }
 }
 

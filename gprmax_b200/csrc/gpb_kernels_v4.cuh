@@ -528,16 +528,21 @@ __device__ __forceinline__ void pml_slab_cell(const PhaseParams<R> &p, int phase
 template <typename R, typename IDT>
 __global__ void __launch_bounds__(256) k_pml_slabs(const PhaseParams<R> p, int phase, unsigned slabsel, int p0, int p1)
 {
-    for (int s = 0; s < p.nslabs; ++s) {
-        if (!((slabsel >> s) & 1u)) continue;
-        const SlabDev<R> &sl = p.slab[s];
-        const int n1 = sl.hi[1] - sl.lo[1], n2 = sl.hi[2] - sl.lo[2];
-        const int i = sl.lo[0] + blockIdx.y;
-        if (i >= sl.hi[0] || i < p.x_start + p0 || i >= p.x_start + p1) continue;
-        const int q = blockIdx.x * blockDim.x + threadIdx.x;
-        if (q >= n1 * n2) continue;
-        pml_slab_cell<R, IDT>(p, phase, sl, i, sl.lo[1] + q / n2, sl.lo[2] + q % n2);
-    }
+    // blockIdx.z selects the n-th slab of `slabsel`: the slabs run side by side instead of back to back
+    int s = -1;
+    for (int q = 0, n = 0; q < p.nslabs; ++q)
+        if ((slabsel >> q) & 1u) {
+            if (n == (int)blockIdx.z) s = q;
+            ++n;
+        }
+    if (s < 0) return;
+    const SlabDev<R> &sl = p.slab[s];
+    const int n1 = sl.hi[1] - sl.lo[1], n2 = sl.hi[2] - sl.lo[2];
+    const int i = sl.lo[0] + blockIdx.y;
+    if (i >= sl.hi[0] || i < p.x_start + p0 || i >= p.x_start + p1) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n1 * n2) return;
+    pml_slab_cell<R, IDT>(p, phase, sl, i, sl.lo[1] + q / n2, sl.lo[2] + q % n2);
 }
 
 }  // namespace gpb
