@@ -96,3 +96,41 @@ def test_restart_and_chunked_run_bit_identical():
         b = sv.receivers()
         assert sv.kernel_launches > 0
     assert np.array_equal(a, b)
+
+
+def test_config4_gssi_bscan_trace(tmp_path):
+    """BASELINE.json configs[3]: user_models/cylinder_Bscan_GSSI_1500.in, trace 1 of the B-scan at full size
+    (480 x 148 x 235 cells, 3117 iterations, GSSI 1.5 GHz antenna model: 24 materials, PEC plates, a 230-ohm
+    voltage source, one Ey receiver).  Golden = the unmodified reference CPU solver (408 s on 8 cores here)."""
+    import time
+    from gprmax_b200.model_io import load_model
+    path = golden_path('bscan_gssi_trace1', 'f32')
+    if not os.path.exists(path):
+        pytest.skip('fixture not present')
+    G, golden = load_model(path)
+    t0 = time.perf_counter()
+    out = _solve(G)
+    print('config 4 trace: {:.2f} s end to end, {} cells x {} iterations'.format(time.perf_counter() - t0, G.nx * G.ny * G.nz, G.iterations))
+    worst, rep = compare_traces(out, golden, np.float32)
+    print(rep)
+    assert worst <= 1.0, rep
+
+
+def test_config3_heterogeneous_soil_full_size():
+    """BASELINE.json configs[2] at full size with explicit fractal seeds: 150 x 150 x 100 cells, 3117 iterations,
+    50-bin Peplinski soil (1-pole Debye everywhere), rough surface, 6 PML slabs -- the dispersive update path."""
+    from gprmax_b200.model_io import load_model
+    p32 = golden_path('heterogeneous_soil_full', 'f32')
+    p64 = p32.replace('_f32.npz', '_f64_truth.npz')   # float64 reference traces only (no second copy of the 8 MB ID array)
+    if not (os.path.exists(p32) and os.path.exists(p64)):
+        pytest.skip('fixture not present')
+    import time
+    G, golden = load_model(p32)
+    z = np.load(p64)
+    golden64 = {k[len('golden_'):]: z[k] for k in z.files}
+    t0 = time.perf_counter()
+    out = _solve(G)
+    print('config 3: {:.2f} s end to end, {} cells x {} iterations, {} materials'.format(time.perf_counter() - t0, G.nx * G.ny * G.nz, G.iterations, G.updatecoeffsE.shape[0]))
+    ok, rep = compare_f32_with_truth(out, golden, golden64)
+    print(rep)
+    assert ok, rep
