@@ -73,6 +73,7 @@ struct Solver : SolverBase {
     bool tabsmem;
     bool use_v4 = false;       // vectorised non-dispersive path (gpb_kernels_v4.cuh)
     bool use_tma = false;      // TMA-staged path (gpb_kernels_tma.cuh)
+    int v4_xchunk = 16;        // planes marched by one thread of the v4 kernels
     int tma_ty = 0, tma_tz = 0, tma_stages = 0, tma_xchunk = 16;
     bool tma_zcoop = false;    // z-slab PML inside the TMA kernels (cooperative, through shared memory)
     size_t tma_zbytes = 0;
@@ -525,9 +526,21 @@ int Solver<R>::build(const gpb_model_t &m)
     set_boxes();
     if (setup_pml(m)) return 1;
     // vectorised path: non-dispersive models (dispersive ones keep the generic scalar kernels)
-    use_v4 = v4_ok && maxpoles == 0 && !getenv("GPB_SCALAR");
+    // vectorised path (dispersive E updates included; GPB_SCALAR forces the generic scalar kernels)
+    use_v4 = v4_ok && !getenv("GPB_SCALAR");
+    // small planes (2-D models, small 3-D grids): shorter marches so that there are enough blocks to fill the
+    // GPU and the per-thread chain of dependent plane loads stays short
+    {
+        const long long bpp = (plane / 4 + kThreadsV4 - 1) / kThreadsV4;
+        v4_xchunk = 16;
+        while (v4_xchunk > 1 && bpp * ((nplanes + v4_xchunk - 1) / v4_xchunk) < 148ll * 8) v4_xchunk /= 2;
+        if (getenv("GPB_V4_XCHUNK")) v4_xchunk = std::max(1, atoi(getenv("GPB_V4_XCHUNK")));
+    }
     // TMA-staged path: 3-D grids with reasonably long z rows (2-D / thin grids stay on the flattened v4 path)
-    use_tma = use_v4 && nz + 1 >= 32 && ny + 1 >= 8 && !getenv("GPB_NO_TMA") && (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R)) <= 32 * 1024;
+    // (below ~2.5 M nodes the pipeline fill of the TMA kernels costs more than it hides: 120^3 v4 22.7 vs TMA 20.2,
+    //  150^3 v4 21.6 vs TMA 23.5 Gcells/s)
+    use_tma = use_v4 && nz + 1 >= 32 && ny + 1 >= 8 && !getenv("GPB_NO_TMA") && (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R)) <= 32 * 1024 &&
+              ((long long)nplanes * plane >= 2500000ll || getenv("GPB_FORCE_TMA"));
     if (use_tma && setup_tma()) return 1;
     // z-slab PML on the TMA path: in the same pass, handed to all threads of a CTA through shared memory
     // (gpb_kernels_tma.cuh), when every k-tile meets at most one z slab with at most 16 of its cells and the
@@ -689,9 +702,9 @@ template <typename IDT>
 int Solver<R>::launch_h(int p0, int p1)
 {
     PhaseParams<R> p = ph_h;
-    p.p0 = p0; p.p1 = p1;
+    p.p0 = p0; p.p1 = p1; p.xchunk = v4_xchunk;
     if (use_v4) {
-        dim3 grid((unsigned)((plane / 4 + kThreadsV4 - 1) / kThreadsV4), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
+        dim3 grid((unsigned)((plane / 4 + kThreadsV4 - 1) / kThreadsV4), (unsigned)((p1 - p0 + v4_xchunk - 1) / v4_xchunk));
         if (tabsmem) k_update_h4<R, IDT, true><<<grid, kThreadsV4, smem_bytes, stream>>>(p);
         else k_update_h4<R, IDT, false><<<grid, kThreadsV4, 0, stream>>>(p);
         CK(cudaGetLastError());
@@ -723,11 +736,16 @@ template <typename IDT>
 int Solver<R>::launch_e(int p0, int p1)
 {
     PhaseParams<R> p = ph_e;
-    p.p0 = p0; p.p1 = p1;
+    p.p0 = p0; p.p1 = p1; p.xchunk = v4_xchunk;
     if (use_v4) {
-        dim3 grid((unsigned)((plane / 4 + kThreadsV4 - 1) / kThreadsV4), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
-        if (tabsmem) k_update_e4<R, IDT, true><<<grid, kThreadsV4, smem_bytes, stream>>>(p);
-        else k_update_e4<R, IDT, false><<<grid, kThreadsV4, 0, stream>>>(p);
+        dim3 grid((unsigned)((plane / 4 + kThreadsV4 - 1) / kThreadsV4), (unsigned)((p1 - p0 + v4_xchunk - 1) / v4_xchunk));
+        if (maxpoles) {
+            if (tabsmem) k_update_e4<R, IDT, true, true><<<grid, kThreadsV4, smem_bytes, stream>>>(p);
+            else k_update_e4<R, IDT, false, true><<<grid, kThreadsV4, 0, stream>>>(p);
+        } else {
+            if (tabsmem) k_update_e4<R, IDT, true, false><<<grid, kThreadsV4, smem_bytes, stream>>>(p);
+            else k_update_e4<R, IDT, false, false><<<grid, kThreadsV4, 0, stream>>>(p);
+        }
         CK(cudaGetLastError());
         ++launches;
         if (zslabs_e) {
@@ -761,7 +779,7 @@ template <typename R>
 int Solver<R>::launch_phase(int phase, int p0, int p1)
 {
     if (p1 <= p0) return 0;
-    if (use_tma) {
+    if (use_tma && !(phase == 1 && maxpoles)) {   // dispersive E half-step: register-vectorised kernel (T arrays are not TMA-staged)
         if (idbytes == 1) return launch_tma<uint8_t>(phase, p0, p1);
         if (idbytes == 2) return launch_tma<uint16_t>(phase, p0, p1);
         return launch_tma<uint32_t>(phase, p0, p1);
@@ -834,9 +852,12 @@ int Solver<R>::run(int n)
         cudaFuncSetAttribute(k_update_h4<R, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cudaFuncSetAttribute(k_update_h4<R, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cudaFuncSetAttribute(k_update_h4<R, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e4<R, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e4<R, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e4<R, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e4<R, uint8_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e4<R, uint16_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e4<R, uint32_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e4<R, uint8_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e4<R, uint16_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaFuncSetAttribute(k_update_e4<R, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cudaFuncSetAttribute(k_update_h<R, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cudaFuncSetAttribute(k_update_h<R, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cudaFuncSetAttribute(k_update_h<R, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);

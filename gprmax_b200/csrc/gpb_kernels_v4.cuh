@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(cons
     const int j = (int)(eoff / p.pitch);
     const int k = (int)(eoff - (long long)j * p.pitch);
     const int lane = threadIdx.x & 31;
-    const int l0 = p.p0 + blockIdx.y * kXChunk;
-    const int l1 = min(l0 + kXChunk, p.p1);
+    const int l0 = p.p0 + blockIdx.y * p.xchunk;
+    const int l1 = min(l0 + p.xchunk, p.p1);
     if (l0 >= l1) return;
     const JK4 bx = jk4_of(p.box[0].lo, p.box[0].hi, j, k), by = jk4_of(p.box[1].lo, p.box[1].hi, j, k), bz = jk4_of(p.box[2].lo, p.box[2].hi, j, k);
     // x / y slabs: which of my cells lie in the slab's (j,k) footprint (z slabs are handled by k_pml_slabs)
@@ -343,11 +343,41 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(cons
     }
 }
 
+// Dispersive sum for 4 cells of one component: part B of the previous step folded into part A of this one,
+// same arithmetic as dispersive_AB() in gpb_kernels.cuh (fields_updates_ext.pyx:113-235; `phi` is a C float
+// there even in the float64 build).  T is complex[pole][cells]; 4 cells = two 128-bit (fp32) accesses.
+template <typename R>
+__device__ __forceinline__ void disp4(const PhaseParams<R> &p, int comp, const Ids4 &id, long long off, unsigned m, const V4<R> &e, V4<R> &phi)
+{
+    float ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0;
+    R *T = reinterpret_cast<R *>(p.T[comp] + off);
+    for (int q = 0; q < p.maxpoles; ++q, T += 2 * p.tstride) {
+        V4<R> t01 = ld4(T), t23 = ld4(T + 4);
+#define GPB_DCELL(bit, idv, ev, tre, tim, ph)                                              \
+    if ((m >> bit) & 1u) {                                                                 \
+        const Cplx<R> *dc = p.dcoef + ((long long)(idv) * p.maxpoles + q) * 3;             \
+        const Cplx<R> c0 = dc[0], c1 = dc[1], c2 = dc[2];                                  \
+        const R re = tre - c2.re * (ev), im = tim - c2.im * (ev);                          \
+        ph = ph + c0.re * re;                                                              \
+        tre = (c1.re * re - c1.im * im) + c2.re * (ev);                                    \
+        tim = (c1.re * im + c1.im * re) + c2.im * (ev);                                    \
+    }
+        GPB_DCELL(0, id.a, e.x, t01.x, t01.y, ph0)
+        GPB_DCELL(1, id.b, e.y, t01.z, t01.w, ph1)
+        GPB_DCELL(2, id.c, e.z, t23.x, t23.y, ph2)
+        GPB_DCELL(3, id.d, e.w, t23.z, t23.w, ph3)
+#undef GPB_DCELL
+        st4(T, t01);
+        st4(T + 4, t23);
+    }
+    phi = {(R)ph0, (R)ph1, (R)ph2, (R)ph3};
+}
+
 // ------------------------------------------------------------------------------------------
 // Electric half-step, 4 z cells per thread.  Arithmetic: fields_updates_ext.pyx:30-107 and
 // pml_updates_electric_*_ext.pyx (x and y slabs).
 // ------------------------------------------------------------------------------------------
-template <typename R, typename IDT, bool TABSMEM>
+template <typename R, typename IDT, bool TABSMEM, bool DISP>
 __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(const PhaseParams<R> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -367,8 +397,8 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
     const int j = (int)(eoff / p.pitch);
     const int k = (int)(eoff - (long long)j * p.pitch);
     const int lane = threadIdx.x & 31;
-    const int l0 = p.p0 + blockIdx.y * kXChunk;
-    const int l1 = min(l0 + kXChunk, p.p1);
+    const int l0 = p.p0 + blockIdx.y * p.xchunk;
+    const int l1 = min(l0 + p.xchunk, p.p1);
     if (l0 >= l1) return;
     const JK4 bx = jk4_of(p.box[0].lo, p.box[0].hi, j, k), by = jk4_of(p.box[1].lo, p.box[1].hi, j, k), bz = jk4_of(p.box[2].lo, p.box[2].hi, j, k);
     unsigned smask = 0;  // 4 bits per slab
@@ -429,26 +459,53 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
             if (mx) {
                 Coef4<R> c0, c1, c2, c3;
                 coef4(coef, idx_, c0, c1, c2, c3);
+                if (DISP) {
+                    V4<R> ph;
+                    disp4(p, 0, idx_, off, mx, ex, ph);
+                    ex.x = sel(mx, 0, c0.a * ex.x + c0.by * dHz_dy.x - c0.bz * dHy_dz.x - srce[idx_.a] * ph.x, ex.x);
+                    ex.y = sel(mx, 1, c1.a * ex.y + c1.by * dHz_dy.y - c1.bz * dHy_dz.y - srce[idx_.b] * ph.y, ex.y);
+                    ex.z = sel(mx, 2, c2.a * ex.z + c2.by * dHz_dy.z - c2.bz * dHy_dz.z - srce[idx_.c] * ph.z, ex.z);
+                    ex.w = sel(mx, 3, c3.a * ex.w + c3.by * dHz_dy.w - c3.bz * dHy_dz.w - srce[idx_.d] * ph.w, ex.w);
+                } else {
                 ex.x = sel(mx, 0, c0.a * ex.x + c0.by * dHz_dy.x - c0.bz * dHy_dz.x, ex.x);
                 ex.y = sel(mx, 1, c1.a * ex.y + c1.by * dHz_dy.y - c1.bz * dHy_dz.y, ex.y);
                 ex.z = sel(mx, 2, c2.a * ex.z + c2.by * dHz_dy.z - c2.bz * dHy_dz.z, ex.z);
                 ex.w = sel(mx, 3, c3.a * ex.w + c3.by * dHz_dy.w - c3.bz * dHy_dz.w, ex.w);
+                }
             }
             if (my) {
                 Coef4<R> c0, c1, c2, c3;
                 coef4(coef, idy_, c0, c1, c2, c3);
+                if (DISP) {
+                    V4<R> ph;
+                    disp4(p, 1, idy_, off, my, ey, ph);
+                    ey.x = sel(my, 0, c0.a * ey.x + c0.bz * dHx_dz.x - c0.bx * dHz_dx.x - srce[idy_.a] * ph.x, ey.x);
+                    ey.y = sel(my, 1, c1.a * ey.y + c1.bz * dHx_dz.y - c1.bx * dHz_dx.y - srce[idy_.b] * ph.y, ey.y);
+                    ey.z = sel(my, 2, c2.a * ey.z + c2.bz * dHx_dz.z - c2.bx * dHz_dx.z - srce[idy_.c] * ph.z, ey.z);
+                    ey.w = sel(my, 3, c3.a * ey.w + c3.bz * dHx_dz.w - c3.bx * dHz_dx.w - srce[idy_.d] * ph.w, ey.w);
+                } else {
                 ey.x = sel(my, 0, c0.a * ey.x + c0.bz * dHx_dz.x - c0.bx * dHz_dx.x, ey.x);
                 ey.y = sel(my, 1, c1.a * ey.y + c1.bz * dHx_dz.y - c1.bx * dHz_dx.y, ey.y);
                 ey.z = sel(my, 2, c2.a * ey.z + c2.bz * dHx_dz.z - c2.bx * dHz_dx.z, ey.z);
                 ey.w = sel(my, 3, c3.a * ey.w + c3.bz * dHx_dz.w - c3.bx * dHz_dx.w, ey.w);
+                }
             }
             if (mz) {
                 Coef4<R> c0, c1, c2, c3;
                 coef4(coef, idz_, c0, c1, c2, c3);
+                if (DISP) {
+                    V4<R> ph;
+                    disp4(p, 2, idz_, off, mz, ez, ph);
+                    ez.x = sel(mz, 0, c0.a * ez.x + c0.bx * dHy_dx.x - c0.by * dHx_dy.x - srce[idz_.a] * ph.x, ez.x);
+                    ez.y = sel(mz, 1, c1.a * ez.y + c1.bx * dHy_dx.y - c1.by * dHx_dy.y - srce[idz_.b] * ph.y, ez.y);
+                    ez.z = sel(mz, 2, c2.a * ez.z + c2.bx * dHy_dx.z - c2.by * dHx_dy.z - srce[idz_.c] * ph.z, ez.z);
+                    ez.w = sel(mz, 3, c3.a * ez.w + c3.bx * dHy_dx.w - c3.by * dHx_dy.w - srce[idz_.d] * ph.w, ez.w);
+                } else {
                 ez.x = sel(mz, 0, c0.a * ez.x + c0.bx * dHy_dx.x - c0.by * dHx_dy.x, ez.x);
                 ez.y = sel(mz, 1, c1.a * ez.y + c1.bx * dHy_dx.y - c1.by * dHx_dy.y, ez.y);
                 ez.z = sel(mz, 2, c2.a * ez.z + c2.bx * dHy_dx.z - c2.by * dHx_dy.z, ez.z);
                 ez.w = sel(mz, 3, c3.a * ez.w + c3.bx * dHy_dx.w - c3.by * dHx_dy.w, ez.w);
+                }
             }
             if (pm) {
                 for (int s = 0; s < p.nslabs; ++s) {
