@@ -24,10 +24,14 @@ def _single(G):
         return sv.receivers(), [sv.get_field(c) for c in range(6)]
 
 
-@pytest.mark.parametrize('name,variant,nshards', [('pml_HORIPML_1', 'f32', 2), ('pml_MRIPML_2', 'f64', 3), ('sources_mixed', 'f32', 4),
-                                                  ('hertzian_dipole_dispersive', 'f32', 3), ('bench_100', 'f32', 5)])
-def test_local_shards_bit_exact(name, variant, nshards):
+@pytest.mark.parametrize('name,variant,nshards,force_tma', [('pml_HORIPML_1', 'f32', 2, False), ('pml_MRIPML_2', 'f64', 3, False),
+                                                            ('sources_mixed', 'f32', 4, False), ('hertzian_dipole_dispersive', 'f32', 3, False),
+                                                            ('bench_100', 'f32', 5, False), ('pml_HORIPML_2', 'f32', 3, True),
+                                                            ('bench_100', 'f32', 4, True), ('dispersive_multipole', 'f64', 2, True)])
+def test_local_shards_bit_exact(name, variant, nshards, force_tma, monkeypatch):
     from gprmax_b200.model_io import load_model
+    if force_tma:   # the TMA-staged kernels are normally only used above 2.5 M nodes
+        monkeypatch.setenv('GPB_FORCE_TMA', '1')
     from gprmax_b200.sharded import GpuShard, run_sharded_local
     G, _ = load_model(golden_path(name, variant))
     G.iterations = min(G.iterations, 150)
