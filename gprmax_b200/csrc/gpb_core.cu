@@ -639,7 +639,7 @@ int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
 {
     using L = StageLayout<R, IDT, TY, TZ>;
     PhaseParams<R> p = phase == 0 ? ph_h : ph_e;
-    p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk; p.zcoop = tma_zcoop ? 1 : 0;
+    p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk; p.zcoop = tma_zcoop ? 1 : 0; p.xreverse = getenv("GPB_TMA_XREV") ? 1 : 0;   // alternate chunk order between phases: no gain measured (the kernels are latency-, not DRAM-bound)
     // planes on which a thread whose 4 cells are interior in (j,k) needs no mask / slab logic at all
     p.fast_i0 = std::max(p.box[0].lo[0], std::max(p.box[1].lo[0], p.box[2].lo[0]));
     p.fast_i1 = std::min(p.box[0].hi[0], std::min(p.box[1].hi[0], p.box[2].hi[0]));
@@ -685,6 +685,7 @@ int Solver<R>::launch_tma(int phase, int p0, int p1)
 {
 #define GPB_TMA_CASE(TY_, TZ_, S_) if (tma_ty == TY_ && tma_tz == TZ_ && tma_stages == S_) return launch_tma_cfg<IDT, TY_, TZ_, S_>(phase, p0, p1)
     GPB_TMA_CASE(16, 64, 3);
+    GPB_TMA_CASE(16, 64, 2);
     GPB_TMA_CASE(16, 64, 4);
     GPB_TMA_CASE(8, 128, 3);
     GPB_TMA_CASE(32, 32, 3);

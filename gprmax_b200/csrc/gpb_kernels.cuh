@@ -85,6 +85,7 @@ struct PhaseParams {
     // sub-range of owned planes processed by this launch (for halo overlap): [p0, p1)
     int p0, p1;
     int xchunk;               // planes marched by one CTA of the TMA kernels
+    int xreverse;             // TMA kernels: E phase visits the x chunks in descending order (L2 reuse across phases)
     int fast_i0, fast_i1;     // TMA kernels: planes between the x slabs and inside all three update boxes
     int zcoop;                // TMA kernels: apply z-slab PML in the same pass, cooperatively through shared memory
 };
@@ -428,7 +429,7 @@ struct TLDev {
     double coefI;     // (1/resistance) * (c dt / dl)
     double cdtdl;     // c dt / dl
     double h;         // (c dt - dl) / (c dt + dl)
-    R d1, d2, dpol;   // spacings for the current loop (grid.py:413-461) and the E assignment
+    R dpol;           // spacing along the polarisation (E assignment, sources.py:415-424)
     R *voltage, *current;  // [nl]
     R *abcv;          // [2]
     const R *wave_whole, *wave_half;

@@ -116,8 +116,11 @@ __device__ __forceinline__ Ids4 lds_ids4<uint32_t>(const unsigned char *base, in
 // Arithmetic identical to k_update_e4 / k_update_h4.
 // Shared memory: [kStages mbarriers][coefficient rows][kStages stages]
 // ------------------------------------------------------------------------------------------
+#ifndef GPB_TMA_CTAS
+#define GPB_TMA_CTAS 2
+#endif
 template <typename R, typename IDT, int TY, int TZ, int kStages, int PHASE>
-__global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? 512 / (TY * TZ / 4) : 1)) k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int tiles_k)
+__global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? GPB_TMA_CTAS * 256 / (TY * TZ / 4) : 1)) k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int tiles_k)
 {
     constexpr int kTmaThreads = TY * TZ / 4;  // every thread owns 4 consecutive z cells of the tile
     static_assert(kTmaThreads % 32 == 0 && kTmaThreads <= 256, "tile shape");
@@ -135,7 +138,10 @@ __global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? 512 / (TY * TZ 
     const int j0 = tj * TY, k0 = tk * TZ;
     const int r = tid / (TZ / 4), c = (tid % (TZ / 4)) * 4;
     const int j = j0 + r, k = k0 + c;
-    const int l0 = p.p0 + blockIdx.y * p.xchunk;
+    // CTAs are dispatched in blockIdx order.  Optionally (p.xreverse) the E phase walks the x chunks downwards so
+    // that each phase starts on the planes the previous one touched last (L2 reuse) -- measured: no gain.
+    const int chunk = (PHASE == 1 && p.xreverse) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int l0 = p.p0 + chunk * p.xchunk;
     const int l1 = min(l0 + p.xchunk, p.p1);
     if (l0 >= l1) return;
     const int nl = l1 - l0;
