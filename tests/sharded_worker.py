@@ -9,13 +9,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def build(spec):
+    """A fixture path, or 'synthetic:nx,ny,nz,iterations' = homogeneous lossy dielectric box (the recipe of the sharded
+    benchmark: er 6, sigma 0.01, z dipole at the centre, one receiver on the middle cut plane, one off-centre)."""
+    from gprmax_b200.model_io import load_model
+    if not spec.startswith('synthetic:'):
+        return load_model(spec)[0]
+    from gprmax_b200.synthetic import homogeneous_model
+    nx, ny, nz, its = [int(v) for v in spec.split(':')[1].split(',')]
+    return homogeneous_model((nx, ny, nz), iterations=its, er=6.0, se=0.01, src=(nx // 2 * 1e-3, ny // 2 * 1e-3, nz // 2 * 1e-3), src_pol='z',
+                             rxs=[((nx // 2 + 1) * 1e-3, (ny // 2 + 9) * 1e-3, nz // 2 * 1e-3), ((nx // 4) * 1e-3, (ny // 3) * 1e-3, (nz // 2 + 5) * 1e-3)])
+
+
 def main():
     import torch.distributed as dist
     from gprmax_b200.model_io import load_model
     from gprmax_b200.sharded import solve_gpu_sharded
     fixture, out, overlap = sys.argv[1], sys.argv[2], sys.argv[3] == '1'
     dist.init_process_group('nccl')
-    G, _ = load_model(fixture)
+    G = build(fixture)
     rxs, seconds = solve_gpu_sharded(G, overlap=overlap)
     if dist.get_rank() == 0:
         np.save(out, rxs)

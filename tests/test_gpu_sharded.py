@@ -70,3 +70,24 @@ def test_nccl_shards_bit_exact(overlap, tmp_path):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert np.array_equal(np.load(out), ref_rx)
+
+
+def test_nccl_shards_bit_exact_tma_path(tmp_path):
+    """Same as above on a synthetic lossy-dielectric box large enough for the TMA-staged kernels (the sharded benchmark's
+    recipe, scaled down): every rank runs boundary-plane-first launches of k_update_tma and exchanges halos over NCCL."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from sharded_worker import build
+    from gprmax_b200.gpu import device_count
+    n = device_count()
+    if n < 2:
+        pytest.skip('needs at least 2 GPUs')
+    world = min(n, 4)
+    spec = 'synthetic:160,144,128,120'
+    ref_rx, _ = _single(build(spec))
+    assert np.abs(ref_rx).max() > 0
+    out = str(tmp_path / 'rx.npy')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr', '127.0.0.1',
+           '--master-port', '29534', os.path.join(ROOT, 'tests', 'sharded_worker.py'), spec, out, '1']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert np.array_equal(np.load(out), ref_rx)
