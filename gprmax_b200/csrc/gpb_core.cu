@@ -75,8 +75,9 @@ struct Solver : SolverBase {
     bool use_tma = false;      // TMA-staged path (gpb_kernels_tma.cuh)
     int v4_xchunk = 16;        // planes marched by one thread of the v4 kernels
     int tma_ty = 0, tma_tz = 0, tma_stages = 0, tma_xchunk = 16;
-    bool tma_zcoop = false;    // z-slab PML inside the TMA kernels (cooperative, through shared memory)
-    size_t tma_zbytes = 0;
+    bool tma_persist = true;   // persistent CTAs with a continuous TMA pipeline across work items
+    int *d_sched = 0;          // [2] work-item scheduler state of the persistent TMA kernels
+    int sm_count = 148;
     TmaMaps9 maps_e, maps_h;
     int setup_tma();
     template <typename IDT, int TY, int TZ, int S>
@@ -542,28 +543,6 @@ int Solver<R>::build(const gpb_model_t &m)
     use_tma = use_v4 && nz + 1 >= 32 && ny + 1 >= 8 && !getenv("GPB_NO_TMA") && (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R)) <= 32 * 1024 &&
               ((long long)nplanes * plane >= 2500000ll || getenv("GPB_FORCE_TMA"));
     if (use_tma && setup_tma()) return 1;
-    // z-slab PML on the TMA path: in the same pass, handed to all threads of a CTA through shared memory
-    // (gpb_kernels_tma.cuh), when every k-tile meets at most one z slab with at most 16 of its cells and the
-    // march is short enough for the Phi prefetch buffer.  Opt-in (GPB_TMA_ZCOOP): measured 45.0 vs 47.1
-    // Gcells/s for the separate k_pml_slabs launch at 300^3 (the k-end CTAs become the critical path).
-    tma_zcoop = false;
-    if (use_tma && getenv("GPB_TMA_ZCOOP") && tma_xchunk <= 8) {
-        bool ok = true, anyz = false;
-        for (const PhaseParams<R> *ph : {&ph_e, &ph_h})
-            for (int k0 = 0; k0 < pitch; k0 += tma_tz) {
-                int cnt = 0;
-                for (int s = 0; s < ph->nslabs; ++s) {
-                    const SlabDev<R> &sl = ph->slab[s];
-                    if (sl.axis != 2 || sl.lo[2] >= k0 + tma_tz || sl.hi[2] <= k0) continue;
-                    ++cnt;
-                    anyz = true;
-                    if (std::min(sl.hi[2], k0 + tma_tz) - std::max(sl.lo[2], k0) > 16) ok = false;
-                }
-                if (cnt > 1) ok = false;
-            }
-        tma_zcoop = ok && anyz;
-        tma_zbytes = tma_zcoop ? (size_t)tma_ty * 16 * (4 * sizeof(R) + 8 + (size_t)tma_xchunk * 2 * order * sizeof(R)) + 16 * sizeof(PmlCo<R>) : 0;
-    }
     if (use_v4) {
         for (int s = 0; s < ph_e.nslabs; ++s)
             if (ph_e.slab[s].axis == 2) zslabs_e |= 1u << s;
@@ -626,6 +605,9 @@ int Solver<R>::setup_tma()
     // grid would otherwise have fewer than ~6 waves
     cudaDeviceProp pr;
     CK(cudaGetDeviceProperties(&pr, device));
+    sm_count = pr.multiProcessorCount;
+    tma_persist = !getenv("GPB_TMA_NOPERSIST");
+    if (dalloc(&d_sched, 2)) return 1;
     const long long tiles = (long long)((ny + 1 + TY - 1) / TY) * ((pitch + TZ - 1) / TZ);
     tma_xchunk = 8;
     while (tma_xchunk > 2 && tiles * ((nplanes + tma_xchunk - 1) / tma_xchunk) < 12ll * pr.multiProcessorCount) tma_xchunk /= 2;
@@ -639,7 +621,8 @@ int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
 {
     using L = StageLayout<R, IDT, TY, TZ>;
     PhaseParams<R> p = phase == 0 ? ph_h : ph_e;
-    p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk; p.zcoop = tma_zcoop ? 1 : 0; p.xreverse = getenv("GPB_TMA_XREV") ? 1 : 0;   // alternate chunk order between phases: no gain measured (the kernels are latency-, not DRAM-bound)
+    p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk; p.persist = tma_persist ? 1 : 0;
+    p.xreverse = 0;
     // planes on which a thread whose 4 cells are interior in (j,k) needs no mask / slab logic at all
     p.fast_i0 = std::max(p.box[0].lo[0], std::max(p.box[1].lo[0], p.box[2].lo[0]));
     p.fast_i1 = std::min(p.box[0].hi[0], std::min(p.box[1].hi[0], p.box[2].hi[0]));
@@ -650,20 +633,23 @@ int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
         }
     if (getenv("GPB_TMA_NOFAST")) p.fast_i1 = p.fast_i0;
     const int tiles_k = (pitch + TZ - 1) / TZ, tiles_j = (ny + 1 + TY - 1) / TY;
-    const size_t smem = 128 + (size_t)((nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128) + (size_t)S * L::bytes + tma_zbytes;
-    dim3 grid((unsigned)(tiles_k * tiles_j), (unsigned)((p1 - p0 + tma_xchunk - 1) / tma_xchunk));
+    const size_t smem = 128 + (size_t)((nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128) + (size_t)S * L::bytes;
+    const int tiles = tiles_k * tiles_j, nchunks = (p1 - p0 + tma_xchunk - 1) / tma_xchunk;
+    // persistent: as many CTAs as fit on the GPU at once (2 per SM for fp32), pulling (tile, chunk) items from d_sched
+    const int resident = (sizeof(R) == 4 ? GPB_TMA_CTAS * 256 / (TY * TZ / 4) : 1) * sm_count;
+    dim3 grid = tma_persist ? dim3((unsigned)std::min(tiles * nchunks, resident)) : dim3((unsigned)tiles, (unsigned)nchunks);
     if (phase == 0) {
         auto kern = k_update_tma<R, IDT, TY, TZ, S, 0>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TY * TZ / 4, smem, stream>>>(p, maps_h, tiles_k);
+        kern<<<grid, TY * TZ / 4, smem, stream>>>(p, maps_h, tiles_k, tiles, nchunks, d_sched);
     } else {
         auto kern = k_update_tma<R, IDT, TY, TZ, S, 1>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TY * TZ / 4, smem, stream>>>(p, maps_e, tiles_k);
+        kern<<<grid, TY * TZ / 4, smem, stream>>>(p, maps_e, tiles_k, tiles, nchunks, d_sched);
     }
     CK(cudaGetLastError());
     ++launches;
-    const unsigned zs = tma_zcoop ? 0u : (phase == 0 ? zslabs_h : zslabs_e);
+    const unsigned zs = phase == 0 ? zslabs_h : zslabs_e;
     if (zs) {
         int cells = 0, planes = 0;
         for (int s = 0; s < p.nslabs; ++s)
@@ -685,15 +671,17 @@ int Solver<R>::launch_tma(int phase, int p0, int p1)
 {
 #define GPB_TMA_CASE(TY_, TZ_, S_) if (tma_ty == TY_ && tma_tz == TZ_ && tma_stages == S_) return launch_tma_cfg<IDT, TY_, TZ_, S_>(phase, p0, p1)
     GPB_TMA_CASE(16, 64, 3);
-    GPB_TMA_CASE(16, 64, 2);
-    GPB_TMA_CASE(16, 64, 4);
     GPB_TMA_CASE(8, 128, 3);
     GPB_TMA_CASE(32, 32, 3);
+#ifdef GPB_TMA_SWEEP   // tile / stage sweep variants of profiles/README.md (not built by default: 3x the compile time)
+    GPB_TMA_CASE(16, 64, 2);
+    GPB_TMA_CASE(16, 64, 4);
     GPB_TMA_CASE(8, 64, 4);
     GPB_TMA_CASE(8, 64, 5);
     GPB_TMA_CASE(8, 64, 6);
     GPB_TMA_CASE(4, 128, 5);
     GPB_TMA_CASE(4, 128, 6);
+#endif
 #undef GPB_TMA_CASE
     return fail("no TMA kernel instantiated for tile %d x %d with %d stages", tma_ty, tma_tz, tma_stages);
 }

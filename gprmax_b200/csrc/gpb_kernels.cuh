@@ -87,7 +87,7 @@ struct PhaseParams {
     int xchunk;               // planes marched by one CTA of the TMA kernels
     int xreverse;             // TMA kernels: E phase visits the x chunks in descending order (L2 reuse across phases)
     int fast_i0, fast_i1;     // TMA kernels: planes between the x slabs and inside all three update boxes
-    int zcoop;                // TMA kernels: apply z-slab PML in the same pass, cooperatively through shared memory
+    int persist;              // TMA kernels: persistent CTAs pulling (tile, x-chunk) items from an atomic counter
 };
 
 // ------------------------------------------------------------------------------------------

@@ -13,8 +13,7 @@
 //     kStages planes (~30 KB each) are in flight per CTA regardless of register pressure;
 //   * the x-neighbour plane (i-1 for E, i+1 for H) rides in a register queue as before;
 //   * results go straight from registers to global memory with 128-bit stores.
-// x / y PML slabs are applied in the same pass (vectorised, warp-uniform); z slabs either by k_pml_slabs
-// or (p.zcoop) in the same pass, handed to all threads of the CTA through shared memory.
+// x / y PML slabs are applied in the same pass (vectorised, warp-uniform); z slabs by k_pml_slabs.
 #pragma once
 #include <cuda.h>
 
@@ -119,32 +118,31 @@ __device__ __forceinline__ Ids4 lds_ids4<uint32_t>(const unsigned char *base, in
 #ifndef GPB_TMA_CTAS
 #define GPB_TMA_CTAS 2
 #endif
+// Work items = (tile, x-chunk) pairs.  Non-persistent launch: one CTA per item.  Persistent launch (p.persist):
+// GPB_TMA_CTAS CTAs per SM pull items from an atomic counter and keep ONE continuous TMA pipeline running across item
+// boundaries, so the ring never drains between marches (the ncu source page showed a quarter of all stall samples on
+// the `full` mbarrier wait while fresh CTAs filled their pipelines).  Every item starts with a pseudo-plane slot that
+// carries only the two x-neighbour operand tiles (register-queue initialisation); a final empty slot carries the
+// end-of-work signal.  sched[0] = next item, sched[1] = finished CTAs (the last one resets both for the next launch).
 template <typename R, typename IDT, int TY, int TZ, int kStages, int PHASE>
-__global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? GPB_TMA_CTAS * 256 / (TY * TZ / 4) : 1)) k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int tiles_k)
+__global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? GPB_TMA_CTAS * 256 / (TY * TZ / 4) : 1))
+k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int tiles_k, int tiles, int nchunks, int *sched)
 {
     constexpr int kTmaThreads = TY * TZ / 4;  // every thread owns 4 consecutive z cells of the tile
     static_assert(kTmaThreads % 32 == 0 && kTmaThreads <= 256, "tile shape");
     using L = StageLayout<R, IDT, TY, TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);   // [kStages] TMA bytes landed
-    uint64_t *empty = full + kStages;                           // [kStages] all 8 warps have read the stage
+    uint64_t *empty = full + kStages;                           // [kStages] all warps have read the stage
+    volatile int *ring = reinterpret_cast<volatile int *>(empty + kStages);  // [4] item ids, producer -> consumers
     Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw + 128);
     R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
     const int coef_bytes = (int)((p.nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128);
     unsigned char *stages = smem_raw + 128 + coef_bytes;
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int tk = blockIdx.x % tiles_k, tj = blockIdx.x / tiles_k;
-    const int j0 = tj * TY, k0 = tk * TZ;
     const int r = tid / (TZ / 4), c = (tid % (TZ / 4)) * 4;
-    const int j = j0 + r, k = k0 + c;
-    // CTAs are dispatched in blockIdx order.  Optionally (p.xreverse) the E phase walks the x chunks downwards so
-    // that each phase starts on the planes the previous one touched last (L2 reuse) -- measured: no gain.
-    const int chunk = (PHASE == 1 && p.xreverse) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
-    const int l0 = p.p0 + chunk * p.xchunk;
-    const int l1 = min(l0 + p.xchunk, p.p1);
-    if (l0 >= l1) return;
-    const int nl = l1 - l0;
+    const int W = tiles * nchunks;
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -164,31 +162,117 @@ __global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? GPB_TMA_CTAS * 
     }
     __syncthreads();
 
-    // local plane index (in the padded array) of the n-th plane this CTA processes
-    auto plane_of = [&](int n) { return PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1); };
-    auto issue = [&](int n) {
-        unsigned char *st = stages + (size_t)(n % kStages) * L::bytes;
-        uint64_t *bar = full + (n % kStages);
-        const int pl = plane_of(n);
-        mbar_expect_tx(bar, (uint32_t)L::tx);
-        if (PHASE == 1) {
-            tma_load_3d(st + L::oA, &maps.opA, bar, k0 - 4, j0 - 1, pl);
-            tma_load_3d(st + L::oB, &maps.opB, bar, k0 - 4, j0, pl);
-            tma_load_3d(st + L::oC, &maps.opC, bar, k0, j0 - 1, pl);
-        } else {
-            tma_load_3d(st + L::oA, &maps.opA, bar, k0, j0, pl);
-            tma_load_3d(st + L::oB, &maps.opB, bar, k0, j0, pl);
-            tma_load_3d(st + L::oC, &maps.opC, bar, k0, j0, pl);
+    // ---------------- producer (thread 0): one slot of the CTA's slot sequence per call
+    int p_item = -1, p_n = -1, p_q = 0, p_g = 0;   // item being loaded, its next plane (-1 = pseudo-plane), item ordinal, slot
+    int p_j0 = 0, p_k0 = 0, p_l0 = 0, p_l1 = 0;
+    bool p_first = true, p_done = false;
+    auto fetch = [&]() {
+        int w;
+        if (p.persist) w = atomicAdd(sched, 1);
+        else w = p_first ? (int)(blockIdx.y * gridDim.x + blockIdx.x) : W;
+        p_first = false;
+        p_item = w < W ? w : -1;
+        if (p_item >= 0) {
+            const int tile = p_item % tiles, chunk = p_item / tiles;
+            p_k0 = (tile % tiles_k) * TZ;
+            p_j0 = (tile / tiles_k) * TY;
+            p_l0 = p.p0 + chunk * p.xchunk;
+            p_l1 = min(p_l0 + p.xchunk, p.p1);
         }
-        tma_load_3d(st + L::oO0, &maps.own0, bar, k0, j0, pl);
-        tma_load_3d(st + L::oO1, &maps.own1, bar, k0, j0, pl);
-        tma_load_3d(st + L::oO2, &maps.own2, bar, k0, j0, pl);
-        tma_load_3d(st + L::oI0, &maps.id0, bar, k0, j0, pl);
-        tma_load_3d(st + L::oI1, &maps.id1, bar, k0, j0, pl);
-        tma_load_3d(st + L::oI2, &maps.id2, bar, k0, j0, pl);
+        p_n = -1;
     };
-    if (tid == 0)
-        for (int n = 0; n < kStages && n < nl; ++n) issue(n);
+    auto produce = [&]() {
+        if (p_done) return;
+        const int stg = p_g % kStages;
+        if (p_g >= kStages) mbar_wait(empty + stg, (uint32_t)(((p_g / kStages) - 1) & 1));
+        unsigned char *st = stages + (size_t)stg * L::bytes;
+        uint64_t *bar = full + stg;
+        if (p_item < 0) {   // end of work: publish the sentinel and complete the phase without bytes
+            ring[p_q & 3] = -1;
+            __threadfence_block();
+            mbar_arrive(bar);
+            p_done = true;
+            ++p_g;
+            return;
+        }
+        if (p_n < 0) {
+            // pseudo-plane: x-neighbour plane (i-1 for E, i+1 for H) of the item's first plane; operand tiles B and C only
+            ring[p_q & 3] = p_item;
+            __threadfence_block();
+            const int pl = PHASE == 1 ? p_l0 : p_l1 + 1;
+            mbar_expect_tx(bar, (uint32_t)((TY * L::PA + (TY + 1) * TZ) * sizeof(R)));
+            if (PHASE == 1) {
+                tma_load_3d(st + L::oB, &maps.opB, bar, p_k0 - 4, p_j0, pl);
+                tma_load_3d(st + L::oC, &maps.opC, bar, p_k0, p_j0 - 1, pl);
+            } else {
+                tma_load_3d(st + L::oB, &maps.opB, bar, p_k0, p_j0, pl);
+                tma_load_3d(st + L::oC, &maps.opC, bar, p_k0, p_j0, pl);
+            }
+        } else {
+            const int pl = PHASE == 1 ? (p_l0 + p_n + 1) : (p_l1 - 1 - p_n + 1);
+            mbar_expect_tx(bar, (uint32_t)L::tx);
+            if (PHASE == 1) {
+                tma_load_3d(st + L::oA, &maps.opA, bar, p_k0 - 4, p_j0 - 1, pl);
+                tma_load_3d(st + L::oB, &maps.opB, bar, p_k0 - 4, p_j0, pl);
+                tma_load_3d(st + L::oC, &maps.opC, bar, p_k0, p_j0 - 1, pl);
+            } else {
+                tma_load_3d(st + L::oA, &maps.opA, bar, p_k0, p_j0, pl);
+                tma_load_3d(st + L::oB, &maps.opB, bar, p_k0, p_j0, pl);
+                tma_load_3d(st + L::oC, &maps.opC, bar, p_k0, p_j0, pl);
+            }
+            tma_load_3d(st + L::oO0, &maps.own0, bar, p_k0, p_j0, pl);
+            tma_load_3d(st + L::oO1, &maps.own1, bar, p_k0, p_j0, pl);
+            tma_load_3d(st + L::oO2, &maps.own2, bar, p_k0, p_j0, pl);
+            tma_load_3d(st + L::oI0, &maps.id0, bar, p_k0, p_j0, pl);
+            tma_load_3d(st + L::oI1, &maps.id1, bar, p_k0, p_j0, pl);
+            tma_load_3d(st + L::oI2, &maps.id2, bar, p_k0, p_j0, pl);
+        }
+        ++p_g;
+        if (++p_n == p_l1 - p_l0) {
+            ++p_q;
+            fetch();
+        }
+    };
+    if (tid == 0) {
+        fetch();
+        for (int s = 0; s < kStages; ++s) produce();
+    }
+
+    // fields this phase writes (the operand arrays are read-only in this phase)
+    R *__restrict__ F0 = PHASE == 1 ? p.Ex : p.Hx;
+    R *__restrict__ F1 = PHASE == 1 ? p.Ey : p.Hy;
+    R *__restrict__ F2 = PHASE == 1 ? p.Ez : p.Hz;
+
+    int g = 0;   // consumer position in the slot sequence
+    for (int q = 0;; ++q) {
+    // ---------------- item prologue: the pseudo-plane slot (or the end-of-work signal)
+    mbar_wait(full + (g % kStages), (uint32_t)((g / kStages) & 1));
+    const int item = ring[q & 3];
+    if (item < 0) break;
+    const int tile = item % tiles, chunkid = item / tiles;
+    const int k0 = (tile % tiles_k) * TZ, j0 = (tile / tiles_k) * TY;
+    const int j = j0 + r, k = k0 + c;
+    const int l0 = p.p0 + chunkid * p.xchunk;
+    const int l1 = min(l0 + p.xchunk, p.p1);
+    const int nl = l1 - l0;
+    auto plane_of = [&](int n) { return PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1); };
+    V4<R> qb, qc;   // register queue: operand B / C of the x-neighbour plane at my cells
+    {
+        const unsigned char *st = stages + (size_t)(g % kStages) * L::bytes;
+        const R *sB = reinterpret_cast<const R *>(st + L::oB);
+        const R *sC = reinterpret_cast<const R *>(st + L::oC);
+        if (PHASE == 1) {
+            qb = ld4(sB + r * L::PA + c + 4);
+            qc = ld4(sC + (r + 1) * TZ + c);
+        } else {
+            qb = ld4(sB + r * L::PA + c);
+            qc = ld4(sC + r * TZ + c);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + (g % kStages));
+        if (tid == 0) produce();
+        ++g;
+    }
 
     const bool valid = j <= p.ny && k <= p.nz;
     const JK4 bx = jk4_of(p.box[0].lo, p.box[0].hi, j, k), by = jk4_of(p.box[1].lo, p.box[1].hi, j, k), bz = jk4_of(p.box[2].lo, p.box[2].hi, j, k);
@@ -196,83 +280,21 @@ __global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? GPB_TMA_CTAS * 
 #pragma unroll
     for (int s = 0; s < kMaxSlabs; ++s)
         if (s < p.nslabs && p.slab[s].axis != 2 && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
-
-    // ---- cooperative z-slab PML (p.zcoop): the z-slab cells of this tile (first / last `thickness` cells
-    // of its z rows, at most kZC per row) are handed through shared memory to ALL threads of the CTA, one
-    // slab cell per thread, instead of diverging in the few lanes that own them.  Phi of those cells for the
-    // whole march is prefetched into shared memory with cp.async while the TMA pipeline fills.
-    constexpr int kZC = 16;
-    int zs = -1, ka = 0, kb = 0, zja = 0, zjb = 0;
-    if (p.zcoop)
-        for (int s = 0; s < p.nslabs; ++s)
-            if (p.slab[s].axis == 2 && p.slab[s].lo[2] < k0 + TZ && p.slab[s].hi[2] > k0) {
-                zs = s;
-                ka = max(p.slab[s].lo[2], k0);
-                kb = min(p.slab[s].hi[2], k0 + TZ);
-                zja = max(p.slab[s].lo[1], j0);
-                zjb = min(p.slab[s].hi[1], j0 + TY);
-            }
-    const bool zwork = zs >= 0 && kb > ka && zjb > zja;
-    unsigned zmask = 0;  // my cells inside the CTA's z-slab footprint
-    if (zwork && valid && j >= zja && j < zjb)
-        for (int q = 0; q < 4; ++q)
-            if (k + q >= ka && k + q < kb) zmask |= 1u << q;
-    const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u || zmask != 0u);
-    // fast path: all 4 cells inside all three update boxes and outside every y/z-slab footprint; then on
-    // the planes between the x slabs (p.fast_i0 <= i < p.fast_i1) the update is straight-line code
+    const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u);
+    // fast path: all 4 cells inside all three update boxes and outside every y-slab footprint; then on the planes
+    // between the x slabs (p.fast_i0 <= i < p.fast_i1) the update is straight-line code
     unsigned yfoot = 0;
 #pragma unroll
     for (int s = 0; s < kMaxSlabs; ++s)
         if (s < p.nslabs && p.slab[s].axis == 1) yfoot |= (smask >> (4 * s)) & 0xfu;
-    const bool fast_jk = valid && bx.kmask == 0xfu && by.kmask == 0xfu && bz.kmask == 0xfu && yfoot == 0u && zmask == 0u;
-    // scratch after the stages: 4 value tiles + 2 id tiles [TY][kZC], then Phi [xchunk][2*order][TY][kZC]
-    R *zF0 = reinterpret_cast<R *>(stages + (size_t)kStages * L::bytes);
-    R *zF1 = zF0 + TY * kZC, *zDB = zF1 + TY * kZC, *zDA = zDB + TY * kZC;
-    unsigned *zI0 = reinterpret_cast<unsigned *>(zDA + TY * kZC), *zI1 = zI0 + TY * kZC;
-    PmlCo<R> *zCo = reinterpret_cast<PmlCo<R> *>(zI1 + TY * kZC);   // one coefficient set per slab depth
-    R *zPhi = reinterpret_cast<R *>(zCo + kZC);
-    const int nphi = 2 * p.order;
-    if (zwork) {
-        const SlabDev<R> &sl = p.slab[zs];
-        if (tid < kb - ka) {
-            const int kq = ka + tid;
-            zCo[tid] = pml_load(p.form, p.order, sl, sl.minus ? (sl.dref - kq) : (kq - sl.dref));
-        }
-        for (int t = tid; t < nl * nphi * TY * kZC; t += kTmaThreads) {
-            const int cc = t % kZC, rr = (t / kZC) % TY, v = (t / (kZC * TY)) % nphi, n = t / (kZC * TY * nphi);
-            const int jj = j0 + rr, kq = ka + cc;
-            const int ii = p.x_start + (PHASE == 1 ? (l0 + n) : (l1 - 1 - n));
-            if (jj >= zja && jj < zjb && kq < kb && ii >= sl.lo[0] && ii < sl.hi[0]) {
-                const R *src = sl.phi + (long long)v * sl.ostride + ((long long)(ii - sl.lo[0]) * sl.n1 + (jj - sl.lo[1])) * sl.n2 + (kq - sl.lo[2]);
-                if (sizeof(R) == 4)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(zPhi + t)), "l"(src) : "memory");
-                else
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(zPhi + t)), "l"(src) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-
-    // fields this phase writes / queue operands (the operand arrays are read-only in this phase)
-    R *__restrict__ F0 = PHASE == 1 ? p.Ex : p.Hx;
-    R *__restrict__ F1 = PHASE == 1 ? p.Ey : p.Hy;
-    R *__restrict__ F2 = PHASE == 1 ? p.Ez : p.Hz;
-    const R *__restrict__ QB = PHASE == 1 ? p.Hy : p.Ey;
-    const R *__restrict__ QC = PHASE == 1 ? p.Hz : p.Ez;
+    const bool fast_jk = valid && bx.kmask == 0xfu && by.kmask == 0xfu && bz.kmask == 0xfu && yfoot == 0u;
     const long long eoff = valid ? ((long long)j * p.pitch + k) : 0;
-    // x-neighbour plane of the first processed plane: i-1 (E phase) / i+1 (H phase)
-    V4<R> qb = ld4(QB + (long long)(PHASE == 1 ? plane_of(0) - 1 : plane_of(0) + 1) * p.plane + eoff);
-    V4<R> qc = ld4(QC + (long long)(PHASE == 1 ? plane_of(0) - 1 : plane_of(0) + 1) * p.plane + eoff);
-    if (zwork) {
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();
-    }
 
-    for (int n = 0; n < nl; ++n) {
+    for (int n = 0; n < nl; ++n, ++g) {
         const int pl = plane_of(n);
         const int i = p.x_start + pl - 1;
-        const unsigned char *st = stages + (size_t)(n % kStages) * L::bytes;
-        mbar_wait(full + (n % kStages), (uint32_t)((n / kStages) & 1));
+        const unsigned char *st = stages + (size_t)(g % kStages) * L::bytes;
+        mbar_wait(full + (g % kStages), (uint32_t)((g / kStages) & 1));
         const R *sA = reinterpret_cast<const R *>(st + L::oA);
         const R *sB = reinterpret_cast<const R *>(st + L::oB);
         const R *sC = reinterpret_cast<const R *>(st + L::oC);
@@ -313,13 +335,8 @@ __global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? GPB_TMA_CTAS * 
         // this warp has taken what it needs from the stage.  No CTA-wide barrier: warps drift freely (the
         // first ncu capture showed barrier stalls on top); the refill is issued by thread 0 once all 8
         // warps have arrived on the stage's `empty` mbarrier (after its own compute, below).
-        if (p.zcoop) {
-            __syncthreads();
-            if (tid == 0 && n + kStages < nl) issue(n + kStages);
-        } else {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + (n % kStages));
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + (g % kStages));
 
         bool w0 = false, w1 = false, w2 = false;
         // one-sided differences along z (also needed by the z-slab hand-off below)
@@ -479,51 +496,21 @@ __global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? GPB_TMA_CTAS * 
             if (w1) st4(F1 + off, f1);
             if (w2) st4(F2 + off, f2);
         }
-        if (!p.zcoop && tid == 0 && n + kStages < nl) {
-            mbar_wait(empty + (n % kStages), (uint32_t)((n / kStages) & 1));
-            issue(n + kStages);
-        }
+        if (tid == 0) produce();   // refill the ring one slot ahead of the oldest stage (waits for all warps' `empty` arrival)
 
-        // ---- cooperative z-slab PML for this plane (CTA-uniform condition).  The owners hand the values of
-        // their z-slab cells over through shared memory; after one barrier every thread corrects one slab cell
-        // and overwrites it in global memory (ordered after the owner's 128-bit store by the barrier).
-        if (zwork && i >= p.slab[zs].lo[0] && i < p.slab[zs].hi[0]) {
-            const SlabDev<R> &sl = p.slab[zs];
-            if (zmask) {
-#define GPB_ZPUT(q, comp, idq)                                   \
-    if ((zmask >> q) & 1u) {                                     \
-        const int o = r * kZC + (k + q - ka);                    \
-        zF0[o] = f0.comp; zF1[o] = f1.comp;                      \
-        zDB[o] = dB_dz.comp; zDA[o] = dA_dz.comp;                \
-        zI0[o] = id0.idq; zI1[o] = id1.idq;                      \
-    }
-                GPB_ZPUT(0, x, a) GPB_ZPUT(1, y, b) GPB_ZPUT(2, z, c) GPB_ZPUT(3, w, d)
-#undef GPB_ZPUT
-            }
-            __syncthreads();
-            // E phase: Ex -= , dHy/dz (Phi1) ; Ey += , dHx/dz (Phi2)   H phase: Hx += , dEy/dz ; Hy -= , dEx/dz
-            const R s0 = PHASE == 1 ? (R)-1 : (R)1, s1 = -s0;
-            for (int t = tid; t < TY * kZC; t += kTmaThreads) {
-                const int cc = t % kZC, rr = t / kZC;
-                const int jj = j0 + rr, kq = ka + cc;
-                if (jj < zja || jj >= zjb || kq >= kb) continue;
-                const PmlCo<R> co = zCo[cc];
-                R *sp = zPhi + ((size_t)n * nphi) * TY * kZC + t;   // [n][v][rr][cc], v = comp + 2*order_index
-                R *gp = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (jj - sl.lo[1])) * sl.n2 + (kq - sl.lo[2]);
-                R p10 = sp[0], p20 = sp[TY * kZC], p11 = 0, p21 = 0;
-                if (p.order == 2) { p11 = sp[2 * TY * kZC]; p21 = sp[3 * TY * kZC]; }
-                const R t0 = pml_apply(p.form, p.order, co, zDB[t] / sl.d, p10, p11);
-                const R t1 = pml_apply(p.form, p.order, co, zDA[t] / sl.d, p20, p21);
-                const long long go = (long long)pl * p.plane + (long long)jj * p.pitch + kq;
-                F0[go] = zF0[t] + s0 * (ssrc[zI0[t]] * t0);
-                F1[go] = zF1[t] + s1 * (ssrc[zI1[t]] * t1);
-                gp[0] = p10;
-                gp[sl.ostride] = p20;
-                if (p.order == 2) { gp[2 * sl.ostride] = p11; gp[3 * sl.ostride] = p21; }
-            }
-        }
         qb = b_c;
         qc = c_c;
+    }
+    }   // items
+
+    // the last CTA to finish re-arms the scheduler for the next launch
+    if (p.persist && tid == 0) {
+        __threadfence();
+        if (atomicAdd(sched + 1, 1) == (int)(gridDim.x * gridDim.y) - 1) {
+            sched[0] = 0;
+            sched[1] = 0;
+            __threadfence();
+        }
     }
 }
 
