@@ -7,7 +7,7 @@
 #include "../../include/gprmax_b200.h"
 #include "gpb_kernels.cuh"
 #include "gpb_kernels_v4.cuh"
-#include "gpb_kernels_tma.cuh"
+#include "gpb_tma.h"
 
 #include <algorithm>
 #include <cmath>
@@ -74,15 +74,12 @@ struct Solver : SolverBase {
     bool use_v4 = false;       // vectorised non-dispersive path (gpb_kernels_v4.cuh)
     bool use_tma = false;      // TMA-staged path (gpb_kernels_tma.cuh)
     int v4_xchunk = 16;        // planes marched by one thread of the v4 kernels
-    int tma_ty = 0, tma_tz = 0, tma_stages = 0, tma_xchunk = 16;
+    int tma_ty = 0, tma_tz = 0, tma_stages = 0, tma_xchunk = 16, tma_pw = 0;   // tile, ring depth, planes per item, dedicated producer warp
     bool tma_persist = true;   // persistent CTAs with a continuous TMA pipeline across work items
     int *d_sched = 0;          // [2] work-item scheduler state of the persistent TMA kernels
     int sm_count = 148;
-    TmaMaps9 maps_e, maps_h;
+    TmaMaps4 maps_e, maps_h;
     int setup_tma();
-    template <typename IDT, int TY, int TZ, int S>
-    int launch_tma_cfg(int phase, int p0, int p1);
-    template <typename IDT>
     int launch_tma(int phase, int p0, int p1);
     unsigned zslabs_e = 0, zslabs_h = 0;  // z slabs (bit per slab) handled by k_pml_slabs on the v4 path
     uint64_t graph_launches = 0;
@@ -207,20 +204,20 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
-// 3-D map over a padded array [planes][rows][pitch] with a (b0 x b1 x 1) box
-static int make_map(CUtensorMap *out, void *base, CUtensorMapDataType dt, size_t es, int pitch, int rows, int planes, int b0, int b1)
+// 4-D map over a component triple [ncomp][planes][rows][pitch] (one allocation) with a (b0 x b1 x 1 x bc) box
+static int make_map(CUtensorMap *out, void *base, CUtensorMapDataType dt, size_t es, int pitch, int rows, int planes, long long comp_stride, int b0, int b1, int bc)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail("cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)planes};
-    const cuuint64_t strides[2] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * rows * es};
-    const cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint64_t dims[4] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)planes, 3};
+    const cuuint64_t strides[3] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * rows * es, (cuuint64_t)comp_stride * es};
+    const cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, 1, (cuuint32_t)bc};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     if (const char *e = getenv("GPB_TMA_L2")) promo = atoi(e) == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (atoi(e) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (atoi(e) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo));
-    CUresult r = fn(out, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    CUresult r = fn(out, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                     promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code %d (pitch %d rows %d planes %d box %d x %d)", (int)r, pitch, rows, planes, b0, b1);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with code %d (pitch %d rows %d planes %d box %d x %d x 1 x %d)", (int)r, pitch, rows, planes, b0, b1, bc);
     return 0;
 }
 
@@ -230,12 +227,12 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
     if (!m.ID) {
         // homogeneous domain: every edge carries the same material
         if (m.uniform_id < 0 || m.uniform_id >= nmat) return fail("uniform_id %d outside the %d materials", m.uniform_id, nmat);
+        void *idbase = nullptr;
+        CK(cudaMalloc(&idbase, (size_t)narr * idbytes * 6));   // one allocation, like F
+        allocs.push_back(idbase);
+        mem += (size_t)narr * idbytes * 6;
         for (int c = 0; c < 6; ++c) {
-            void *dst = nullptr;
-            size_t bytes = (size_t)narr * idbytes;
-            CK(cudaMalloc(&dst, bytes));
-            allocs.push_back(dst);
-            mem += bytes;
+            void *dst = (char *)idbase + (size_t)c * narr * idbytes;
             ID[c] = dst;
             if (idbytes == 1) k_fill_ids<uint8_t><<<148 * 8, 256, 0, stream>>>((uint8_t *)dst, narr, (uint8_t)m.uniform_id);
             else if (idbytes == 2) k_fill_ids<uint16_t><<<148 * 8, 256, 0, stream>>>((uint16_t *)dst, narr, (uint16_t)m.uniform_id);
@@ -254,13 +251,13 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
     CK(cudaMalloc(&stage, (size_t)chunk_planes * plane_src * 4));
     CK(cudaMalloc(&d_max, sizeof(unsigned)));
     CK(cudaMemsetAsync(d_max, 0, sizeof(unsigned), stream));
+    void *idbase = nullptr;
+    CK(cudaMalloc(&idbase, (size_t)narr * idbytes * 6));   // one allocation, like F
+    allocs.push_back(idbase);
+    mem += (size_t)narr * idbytes * 6;
+    CK(cudaMemsetAsync(idbase, 0, (size_t)narr * idbytes * 6, stream));
     for (int c = 0; c < 6; ++c) {
-        void *dst = nullptr;
-        size_t bytes = (size_t)narr * idbytes;
-        CK(cudaMalloc(&dst, bytes));
-        allocs.push_back(dst);
-        mem += bytes;
-        CK(cudaMemsetAsync(dst, 0, bytes, stream));
+        void *dst = (char *)idbase + (size_t)c * narr * idbytes;
         ID[c] = dst;
         for (int p0 = 0; p0 < nplanes; p0 += chunk_planes) {
             const int np = std::min(chunk_planes, nplanes - p0);
@@ -354,8 +351,9 @@ int Solver<R>::setup_pml(const gpb_model_t &m)
             const long long n0 = sd.hi[0] - sd.lo[0];
             sd.n1 = sd.hi[1] - sd.lo[1];
             // x / y slabs: Phi rows padded to the field pitch so the vectorised kernels can use aligned
-            // 128-bit accesses; z slabs: compact rows of `thickness` cells
-            sd.n2 = (axis != 2 && sd.lo[2] == 0) ? pitch : sd.hi[2] - sd.lo[2];
+            // 128-bit accesses; z slabs: rows of `thickness` cells padded to whole 4-cell groups of the field rows
+            sd.ko = axis == 2 ? (sd.lo[2] & ~3) : sd.lo[2];
+            sd.n2 = axis == 2 ? (((sd.hi[2] + 3) & ~3) - sd.ko) : (sd.lo[2] == 0 ? pitch : sd.hi[2] - sd.lo[2]);
             if (axis != 2 && sd.lo[2] != 0) v4_ok = false;
             sd.ostride = n0 * sd.n1 * sd.n2;
             R *phi = nullptr;
@@ -366,6 +364,7 @@ int Solver<R>::setup_pml(const gpb_model_t &m)
             const int o = phase == 0 ? 0 : 4;
             sd.RA = tabs[o]; sd.RB = tabs[o + 1]; sd.RE = tabs[o + 2]; sd.RF = tabs[o + 3];
             sd.d = (R)(float)s.d;  // the reference kernels take `float d` (e.g. pml_updates_electric_HORIPML_ext.pyx:48)
+            sd.inv_d = (R)1 / sd.d;
             PhaseParams<R> &ph = phase == 0 ? ph_e : ph_h;
             ph.slab[ph.nslabs++] = sd;
         }
@@ -487,8 +486,9 @@ int Solver<R>::build(const gpb_model_t &m)
     idbytes = nmat <= 256 ? 1 : (nmat <= 65536 ? 2 : 4);
     if (getenv("GPB_ID_BYTES")) idbytes = std::max(idbytes, atoi(getenv("GPB_ID_BYTES")) >= 4 ? 4 : (atoi(getenv("GPB_ID_BYTES")) >= 2 ? 2 : 1));
     use_graph = !getenv("GPB_NO_GRAPH");
-    for (int c = 0; c < 6; ++c)
-        if (dalloc(&F[c], (size_t)narr)) return 1;
+    // all six components in one allocation: the TMA kernels address a triple (E or H) as one 4-D tensor
+    if (dalloc(&F[0], (size_t)narr * 6)) return 1;
+    for (int c = 1; c < 6; ++c) F[c] = F[0] + (size_t)c * narr;
     if (upload_ids(m)) return 1;
     // coefficient rows: [CA, CBx, CBy, CBz | srce] (materials.py:200-201)
     std::vector<Coef4<R>> hE(nmat), hH(nmat);
@@ -564,42 +564,34 @@ int Solver<R>::build(const gpb_model_t &m)
 template <typename R>
 int Solver<R>::setup_tma()
 {
-    // tile shape: 256 threads x 4 cells; pick the shape that wastes the fewest lanes on this grid
-    // (16 x 64 measured fastest on B200; another shape only when it wastes >8 % fewer lanes)
-    const int cand[3][2] = {{16, 64}, {32, 32}, {8, 128}};
+    // tile shape: 4 cells per thread.  Default 14 x 64 cells = 7 consumer warps + a dedicated producer warp (measured fastest on
+    // B200: 54.5 vs 50.7 Gcells/s at 300^3 for 16 x 64 with thread 0 of the first consumer warp producing); another shape
+    // (producer = thread 0) only when it wastes >8 % fewer lanes on this grid
+    const int cand[3][3] = {{14, 64, 1}, {32, 32, 0}, {8, 128, 0}};
     double best = 1e30;
     for (auto &c : cand) {
         const double waste = (double)((ny + 1 + c[0] - 1) / c[0] * c[0]) * ((pitch + c[1] - 1) / c[1] * c[1]) / ((double)(ny + 1) * (nz + 1));
-        if (waste < best * 0.92) { best = waste; tma_ty = c[0]; tma_tz = c[1]; }
+        if (waste < best * 0.92) { best = waste; tma_ty = c[0]; tma_tz = c[1]; tma_pw = c[2]; }
     }
-    if (getenv("GPB_TMA_TZ")) { tma_tz = atoi(getenv("GPB_TMA_TZ")); tma_ty = 1024 / tma_tz; }
+    if (getenv("GPB_TMA_PW") && atoi(getenv("GPB_TMA_PW")) == 0 && tma_pw) { tma_ty = 16; tma_tz = 64; tma_pw = 0; }
+    if (getenv("GPB_TMA_TZ")) { tma_tz = atoi(getenv("GPB_TMA_TZ")); tma_ty = 1024 / tma_tz; tma_pw = 0; }
     if (getenv("GPB_TMA_TY")) tma_ty = atoi(getenv("GPB_TMA_TY"));
     tma_stages = getenv("GPB_TMA_STAGES") ? atoi(getenv("GPB_TMA_STAGES")) : 3;
     const CUtensorMapDataType fdt = sizeof(R) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
     const CUtensorMapDataType idt = idbytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (idbytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32);
     const int rows = ny + 1, planes = nplanes + 2, TY = tma_ty, TZ = tma_tz;
-    // E phase: operands Hx (both halos), Hy (k halo), Hz (j halo); own Ex,Ey,Ez
-    if (make_map(&maps_e.opA, F[3], fdt, sizeof(R), pitch, rows, planes, TZ + 4, TY + 1) ||
-        make_map(&maps_e.opB, F[4], fdt, sizeof(R), pitch, rows, planes, TZ + 4, TY) ||
-        make_map(&maps_e.opC, F[5], fdt, sizeof(R), pitch, rows, planes, TZ, TY + 1) ||
-        make_map(&maps_e.own0, F[0], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_e.own1, F[1], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_e.own2, F[2], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_e.id0, ID[0], idt, idbytes, pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_e.id1, ID[1], idt, idbytes, pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_e.id2, ID[2], idt, idbytes, pitch, rows, planes, TZ, TY))
-        return 1;
-    // H phase: operands Ex, Ey, Ez; own Hx,Hy,Hz
-    if (make_map(&maps_h.opA, F[0], fdt, sizeof(R), pitch, rows, planes, TZ + 4, TY + 1) ||
-        make_map(&maps_h.opB, F[1], fdt, sizeof(R), pitch, rows, planes, TZ + 4, TY) ||
-        make_map(&maps_h.opC, F[2], fdt, sizeof(R), pitch, rows, planes, TZ, TY + 1) ||
-        make_map(&maps_h.own0, F[3], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_h.own1, F[4], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_h.own2, F[5], fdt, sizeof(R), pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_h.id0, ID[3], idt, idbytes, pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_h.id1, ID[4], idt, idbytes, pitch, rows, planes, TZ, TY) ||
-        make_map(&maps_h.id2, ID[5], idt, idbytes, pitch, rows, planes, TZ, TY))
-        return 1;
+    // E phase: operands Hx,Hy,Hz (F[3..5]), own Ex,Ey,Ez (F[0..2]); H phase the other way round.  F and ID are single
+    // allocations of six components each (build / upload_ids), so a triple is a 4-D tensor with component stride narr.
+    for (int ph = 0; ph < 2; ++ph) {
+        TmaMaps4 &mp = ph == 0 ? maps_h : maps_e;
+        R *op = ph == 0 ? F[0] : F[3], *own = ph == 0 ? F[3] : F[0];
+        void *ids = ph == 0 ? ID[3] : ID[0];
+        if (make_map(&mp.op, op, fdt, sizeof(R), pitch, rows, planes, narr, TZ + 4, TY + 1, 3) ||
+            make_map(&mp.opx, op, fdt, sizeof(R), pitch, rows, planes, narr, TZ + 4, TY + 1, 2) ||
+            make_map(&mp.own, own, fdt, sizeof(R), pitch, rows, planes, narr, TZ, TY, 3) ||
+            make_map(&mp.id, ids, idt, idbytes, pitch, rows, planes, narr, TZ, TY, 3))
+            return 1;
+    }
     // planes per CTA: short marches (8 planes) measured best on B200 -- many CTAs keep the two resident
     // CTAs per SM out of phase so one computes while the other's pipeline fills; shorter still when the
     // grid would otherwise have fewer than ~6 waves
@@ -615,12 +607,13 @@ int Solver<R>::setup_tma()
     return 0;
 }
 
+// E or H half-step of planes [p0, p1) on the TMA-staged kernels (gpb_tma_inst.cu)
 template <typename R>
-template <typename IDT, int TY, int TZ, int S>
-int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
+int Solver<R>::launch_tma(int phase, int p0, int p1)
 {
-    using L = StageLayout<R, IDT, TY, TZ>;
-    PhaseParams<R> p = phase == 0 ? ph_h : ph_e;
+    TmaLaunch<R> a;
+    PhaseParams<R> &p = a.p;
+    p = phase == 0 ? ph_h : ph_e;
     p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk; p.persist = tma_persist ? 1 : 0;
     p.xreverse = 0;
     // planes on which a thread whose 4 cells are interior in (j,k) needs no mask / slab logic at all
@@ -632,24 +625,27 @@ int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
             else p.fast_i1 = std::min(p.fast_i1, p.slab[s].lo[0]);
         }
     if (getenv("GPB_TMA_NOFAST")) p.fast_i1 = p.fast_i0;
-    const int tiles_k = (pitch + TZ - 1) / TZ, tiles_j = (ny + 1 + TY - 1) / TY;
-    const size_t smem = 128 + (size_t)((nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128) + (size_t)S * L::bytes;
-    const int tiles = tiles_k * tiles_j, nchunks = (p1 - p0 + tma_xchunk - 1) / tma_xchunk;
-    // persistent: as many CTAs as fit on the GPU at once (2 per SM for fp32), pulling (tile, chunk) items from d_sched
-    const int resident = (sizeof(R) == 4 ? GPB_TMA_CTAS * 256 / (TY * TZ / 4) : 1) * sm_count;
-    dim3 grid = tma_persist ? dim3((unsigned)std::min(tiles * nchunks, resident)) : dim3((unsigned)tiles, (unsigned)nchunks);
-    if (phase == 0) {
-        auto kern = k_update_tma<R, IDT, TY, TZ, S, 0>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TY * TZ / 4, smem, stream>>>(p, maps_h, tiles_k, tiles, nchunks, d_sched);
-    } else {
-        auto kern = k_update_tma<R, IDT, TY, TZ, S, 1>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TY * TZ / 4, smem, stream>>>(p, maps_e, tiles_k, tiles, nchunks, d_sched);
+    p.zfused = getenv("GPB_TMA_ZSPLIT") ? 0 : 1;
+    a.maps = phase == 0 ? &maps_h : &maps_e;
+    a.phase = phase;
+    a.ty = tma_ty; a.tz = tma_tz; a.stages = tma_stages; a.pw = tma_pw;
+    a.idbytes = idbytes;
+    a.pf_max = getenv("GPB_TMA_PF") ? std::max(0, atoi(getenv("GPB_TMA_PF"))) : 2;
+    a.sm_count = sm_count;
+    a.sched = d_sched;
+    a.stream = stream;
+    std::string err;
+    const int pv = 2 * form + order - 1;
+    int rc;
+    switch (pv) {
+    case 0: rc = tma_launch<R, 0>(a, &err); break;
+    case 1: rc = tma_launch<R, 1>(a, &err); break;
+    case 2: rc = tma_launch<R, 2>(a, &err); break;
+    default: rc = tma_launch<R, 3>(a, &err); break;
     }
-    CK(cudaGetLastError());
+    if (rc) return fail("%s", err.c_str());
     ++launches;
-    const unsigned zs = phase == 0 ? zslabs_h : zslabs_e;
+    const unsigned zs = p.zfused ? 0u : (phase == 0 ? zslabs_h : zslabs_e);
     if (zs) {
         int cells = 0, planes = 0;
         for (int s = 0; s < p.nslabs; ++s)
@@ -658,32 +654,13 @@ int Solver<R>::launch_tma_cfg(int phase, int p0, int p1)
                 planes = std::max(planes, p.slab[s].hi[0] - p.slab[s].lo[0]);
             }
         dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes, (unsigned)__builtin_popcount(zs));
-        k_pml_slabs<R, IDT><<<g2, 256, 0, stream>>>(p, phase, zs, p0, p1);
+        if (idbytes == 1) k_pml_slabs<R, uint8_t><<<g2, 256, 0, stream>>>(p, phase, zs, p0, p1);
+        else if (idbytes == 2) k_pml_slabs<R, uint16_t><<<g2, 256, 0, stream>>>(p, phase, zs, p0, p1);
+        else k_pml_slabs<R, uint32_t><<<g2, 256, 0, stream>>>(p, phase, zs, p0, p1);
         CK(cudaGetLastError());
         ++launches;
     }
     return 0;
-}
-
-template <typename R>
-template <typename IDT>
-int Solver<R>::launch_tma(int phase, int p0, int p1)
-{
-#define GPB_TMA_CASE(TY_, TZ_, S_) if (tma_ty == TY_ && tma_tz == TZ_ && tma_stages == S_) return launch_tma_cfg<IDT, TY_, TZ_, S_>(phase, p0, p1)
-    GPB_TMA_CASE(16, 64, 3);
-    GPB_TMA_CASE(8, 128, 3);
-    GPB_TMA_CASE(32, 32, 3);
-#ifdef GPB_TMA_SWEEP   // tile / stage sweep variants of profiles/README.md (not built by default: 3x the compile time)
-    GPB_TMA_CASE(16, 64, 2);
-    GPB_TMA_CASE(16, 64, 4);
-    GPB_TMA_CASE(8, 64, 4);
-    GPB_TMA_CASE(8, 64, 5);
-    GPB_TMA_CASE(8, 64, 6);
-    GPB_TMA_CASE(4, 128, 5);
-    GPB_TMA_CASE(4, 128, 6);
-#endif
-#undef GPB_TMA_CASE
-    return fail("no TMA kernel instantiated for tile %d x %d with %d stages", tma_ty, tma_tz, tma_stages);
 }
 
 template <typename R>
@@ -769,9 +746,7 @@ int Solver<R>::launch_phase(int phase, int p0, int p1)
 {
     if (p1 <= p0) return 0;
     if (use_tma && !(phase == 1 && maxpoles)) {   // dispersive E half-step: register-vectorised kernel (T arrays are not TMA-staged)
-        if (idbytes == 1) return launch_tma<uint8_t>(phase, p0, p1);
-        if (idbytes == 2) return launch_tma<uint16_t>(phase, p0, p1);
-        return launch_tma<uint32_t>(phase, p0, p1);
+        return launch_tma(phase, p0, p1);
     }
     if (phase == 0) {
         if (idbytes == 1) return launch_h<uint8_t>(p0, p1);

@@ -49,10 +49,14 @@ struct SlabDev {
     int dref;
     int t;             // thickness = row length of the R tables
     int n1, n2;        // extents of the box along y and z (Phi is [order][2][n0][n1][n2])
+    int ko;            // z index of Phi column 0 (x/y slabs: lo[2]; z slabs: lo[2] rounded down to a multiple of 4, rows padded
+                       // to a multiple of 4 so that the 4-cell threads of the vectorised kernels use aligned 128-bit accesses)
     long long ostride; // n0*n1*n2 : distance between Phi components / orders
     R *phi;
     const R *RA, *RB, *RE, *RF;
     R d;               // spacing, rounded through float first like the reference's `float d`
+    R inv_d;           // 1 / d (TMA kernels multiply: the IEEE division's slow path, taken for the denormal field tails that
+                       // fill most of a PML, made up 17 % of all executed instructions -- profiles/README.md r1h)
 };
 
 struct Box {
@@ -87,6 +91,9 @@ struct PhaseParams {
     int xchunk;               // planes marched by one CTA of the TMA kernels
     int xreverse;             // TMA kernels: E phase visits the x chunks in descending order (L2 reuse across phases)
     int fast_i0, fast_i1;     // TMA kernels: planes between the x slabs and inside all three update boxes
+    int zfused;               // TMA kernels: z-slab PML in the same pass (else k_pml_slabs afterwards)
+    int tmax;                 // TMA kernels: row length of the shared-memory copies of the PML R tables (max thickness)
+    int pf_depth;             // TMA kernels: Phi prefetch distance in planes (cp.async ring per thread), 0 = direct loads
     int persist;              // TMA kernels: persistent CTAs pulling (tile, x-chunk) items from an atomic counter
 };
 
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) k_update_h(const PhaseParams<R> p)
             const int a = sl.axis;
             const int pos = (a == 0) ? i : (a == 1) ? j : k;
             const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
-            R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+            R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
             // magnetic x: Hy += , dEz/dx ; Hz -= , dEy/dx   (pml_updates_magnetic_HORIPML_ext.pyx:79-87)
             // magnetic y: Hx -= , dEz/dy ; Hz += , dEx/dy   (:347-355)
             // magnetic z: Hx += , dEy/dz ; Hy -= , dEx/dz   (:615-623)
@@ -374,7 +381,7 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
             const int a = sl.axis;
             const int pos = (a == 0) ? i : (a == 1) ? j : k;
             const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
-            R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+            R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
             // electric x: Ey -= , dHz/dx ; Ez += , dHy/dx   (pml_updates_electric_HORIPML_ext.pyx:79-87)
             // electric y: Ex += , dHz/dy ; Ez -= , dHx/dy   (:347-355)
             // electric z: Ex -= , dHy/dz ; Ey += , dHx/dz   (:615-623)

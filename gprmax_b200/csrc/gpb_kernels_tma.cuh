@@ -13,22 +13,16 @@
 //     kStages planes (~30 KB each) are in flight per CTA regardless of register pressure;
 //   * the x-neighbour plane (i-1 for E, i+1 for H) rides in a register queue as before;
 //   * results go straight from registers to global memory with 128-bit stores.
-// x / y PML slabs are applied in the same pass (vectorised, warp-uniform); z slabs by k_pml_slabs.
+// All PML slabs are applied in the same pass: x / y slabs vectorised and warp-uniform, z slabs on the few lanes of a warp that
+// hold the first / last cells of a z row; Phi is prefetched per thread with cp.async (see `prefetch` in the kernel).
 #pragma once
 #include <cuda.h>
 
 #include "gpb_kernels_v4.cuh"
+#include "gpb_tma.h"
 
 namespace gpb {
 
-
-struct TmaMaps9 {
-    CUtensorMap opA;   // operand with both halos   (E phase: Hx ; H phase: Ex)  box (TZ+4) x (TY+1)
-    CUtensorMap opB;   // operand with the k halo   (E phase: Hy ; H phase: Ey)  box (TZ+4) x TY
-    CUtensorMap opC;   // operand with the j halo   (E phase: Hz ; H phase: Ez)  box TZ x (TY+1)
-    CUtensorMap own0, own1, own2;  // fields being updated, box TZ x TY
-    CUtensorMap id0, id1, id2;     // their material IDs,   box TZ x TY (elements of IDT)
-};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -66,26 +60,92 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
                  "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// per-thread asynchronous global -> shared copy of one 4-cell vector (Phi prefetch), L2 only
+template <typename R>
+__device__ __forceinline__ void cp_async_v4(void *sdst, const R *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(g) : "memory");
+    if (sizeof(R) == 8)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst) + 16), "l"(reinterpret_cast<const char *>(g) + 16) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// PML coefficient set of one depth from the shared-memory copy of a slab's R tables, tb = [RA|RB|RE|RF][order][tmax]
+// (same expressions as pml_load in gpb_kernels_v4.cuh)
+template <typename R>
+__device__ __forceinline__ PmlCo<R> pml_load_s(int form, int order, const R *tb, int tmax, int depth)
+{
+    PmlCo<R> c;
+    const R one = (R)1;
+    const R *RA = tb + depth, *RB = tb + order * tmax + depth, *RE = tb + 2 * order * tmax + depth, *RF = tb + 3 * order * tmax + depth;
+    if (form == 0) {
+        if (order == 1) {
+            c.a = RA[0] - one;  // RA01
+            c.b = RB[0];
+            c.e = RE[0];
+            c.f = RF[0];
+        } else {
+            const R RA0 = RA[0], RA1 = RA[tmax];
+            c.a = RA0 * RA1 - one;  // RA01
+            c.b = RB[0];
+            c.e = RE[0];
+            c.f = RF[0];
+            c.c = RA0;
+            c.d = RA1;
+            c.g = RB[tmax];
+            c.h = RE[tmax];
+            c.r = RF[tmax];
+        }
+    } else {
+        if (order == 1) {
+            const R IRA = one / RA[0];
+            c.a = IRA;
+            c.b = IRA - one;
+            c.c = IRA * RB[0] * RF[0];  // RC0
+            c.e = RE[0];
+        } else {
+            const R IRA = one / (RA[0] + RA[tmax]);
+            c.a = IRA;
+            c.b = IRA - one;
+            c.c = IRA * RF[0];
+            c.d = IRA * RF[tmax];
+            c.e = RE[0];
+            c.h = RE[tmax];
+            c.f = RB[0];
+            c.g = RB[tmax];
+        }
+    }
+    return c;
 }
 
 // shared-memory layout of one stage (byte offsets), every sub-buffer 128-byte aligned
 template <typename R, typename IDT, int TY, int TZ>
 struct StageLayout {
     static constexpr int a128(int x) { return (x + 127) / 128 * 128; }
-    static constexpr int PA = TZ + 4;  // row pitch (elements) of opA / opB
-    static constexpr int szA = a128((TY + 1) * PA * (int)sizeof(R));
-    static constexpr int szB = a128(TY * PA * (int)sizeof(R));
-    static constexpr int szC = a128((TY + 1) * TZ * (int)sizeof(R));
-    static constexpr int szO = a128(TY * TZ * (int)sizeof(R));
-    static constexpr int szI = a128(TY * TZ * (int)sizeof(IDT));
-    static constexpr int oA = 0, oB = oA + szA, oC = oB + szB, oO0 = oC + szC, oO1 = oO0 + szO, oO2 = oO1 + szO;
-    static constexpr int oI0 = oO2 + szO, oI1 = oI0 + szI, oI2 = oI1 + szI;
-    static constexpr int bytes = oI2 + szI;
+    static constexpr int PA = TZ + 4;               // row pitch (elements) of the operand tiles
+    static constexpr int CS = (TY + 1) * PA;        // elements per operand component
+    static constexpr int OS = TY * TZ;              // elements per own / id component
+    static constexpr int oOp = 0, szOp = a128(3 * CS * (int)sizeof(R));
+    static constexpr int oOwn = oOp + szOp, szOwn = a128(3 * OS * (int)sizeof(R));
+    static constexpr int oId = oOwn + szOwn, szId = a128(3 * OS * (int)sizeof(IDT));
+    static constexpr int bytes = oId + szId;
     // bytes the TMA unit delivers per stage (full boxes, out-of-range parts are zero-filled)
-    static constexpr int tx = ((TY + 1) * PA + TY * PA + (TY + 1) * TZ + 3 * TY * TZ) * (int)sizeof(R) + 3 * TY * TZ * (int)sizeof(IDT);
+    static constexpr int tx = 3 * CS * (int)sizeof(R) + 3 * OS * (int)sizeof(R) + 3 * OS * (int)sizeof(IDT);
+    static constexpr int tx_x = 2 * CS * (int)sizeof(R);   // x-neighbour slot: operand components B and C (staged in the own buffer)
+    static_assert(2 * CS <= 3 * OS, "x-neighbour tiles must fit the own buffer");
 };
 
 template <typename IDT>
@@ -109,39 +169,102 @@ __device__ __forceinline__ Ids4 lds_ids4<uint32_t>(const unsigned char *base, in
     return {v.x, v.y, v.z, v.w};
 }
 
+// Order in which the x chunks are handed out: both ends first, the middle last.  The chunks that cross the x slabs take
+// 2-3 times as long as the others; handed out last they formed a final, half-empty wave of slow items.
+__device__ __forceinline__ int chunk_of(int q, int nchunks)
+{
+    return (q & 1) ? nchunks - 1 - (q >> 1) : (q >> 1);
+}
+
+// slabs whose x range holds plane i (CTA-uniform)
+template <typename R>
+__device__ __forceinline__ unsigned slabs_on_plane(const PhaseParams<R> &p, int i)
+{
+    unsigned act = 0;
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s)
+        if (s < p.nslabs && i >= p.slab[s].lo[0] && i < p.slab[s].hi[0]) act |= 1u << s;
+    return act;
+}
+
+// One PML component of one slab on the thread's 4 cells, Phi included: load (prefetch slot or global), apply, store.
+// Deliberately one component at a time with few values live: the slab path shares its register allocation with the
+// straight-line update of every thread (two inlined variants that held both components' Phi spilled the hot loop:
+// 47 -> 15 Gcells/s at 300^3; real calls spilled the register queue around them).
+template <typename R, int DSTEP>
+__device__ __forceinline__ void pml_comp(int form, int order, const R *tb, int tmax, int depth0, int dsign, R inv_d, unsigned m, const Ids4 &id,
+                                         const R *src, R sign, const V4<R> &dF, V4<R> &F, R *phi, long long ostride2, const V4<R> *slot, int slot_stride2)
+{
+    V4<R> P0, P1;
+    if (slot) {
+        P0 = slot[0];
+        P1 = order == 2 ? slot[slot_stride2] : P0;
+    } else {
+        P0 = ld4(phi);
+        P1 = order == 2 ? ld4(phi + ostride2) : P0;
+    }
+    if (DSTEP == 0) {
+        const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0);
+        if (m & 1u) F.x = F.x + sign * (src[id.a] * pml_apply(form, order, co, dF.x * inv_d, P0.x, P1.x));
+        if (m & 2u) F.y = F.y + sign * (src[id.b] * pml_apply(form, order, co, dF.y * inv_d, P0.y, P1.y));
+        if (m & 4u) F.z = F.z + sign * (src[id.c] * pml_apply(form, order, co, dF.z * inv_d, P0.z, P1.z));
+        if (m & 8u) F.w = F.w + sign * (src[id.d] * pml_apply(form, order, co, dF.w * inv_d, P0.w, P1.w));
+    } else {
+        if (m & 1u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0); F.x = F.x + sign * (src[id.a] * pml_apply(form, order, co, dF.x * inv_d, P0.x, P1.x)); }
+        if (m & 2u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0 + dsign); F.y = F.y + sign * (src[id.b] * pml_apply(form, order, co, dF.y * inv_d, P0.y, P1.y)); }
+        if (m & 4u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0 + 2 * dsign); F.z = F.z + sign * (src[id.c] * pml_apply(form, order, co, dF.z * inv_d, P0.z, P1.z)); }
+        if (m & 8u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0 + 3 * dsign); F.w = F.w + sign * (src[id.d] * pml_apply(form, order, co, dF.w * inv_d, P0.w, P1.w)); }
+    }
+    st4(phi, P0);
+    if (order == 2) st4(phi + ostride2, P1);
+}
+
 // ------------------------------------------------------------------------------------------
 // PHASE 1: electric half-step (marches +x, operands H, queue = Hy,Hz of plane i-1)
 // PHASE 0: magnetic half-step (marches -x, operands E, queue = Ey,Ez of plane i+1)
 // Arithmetic identical to k_update_e4 / k_update_h4.
-// Shared memory: [kStages mbarriers][coefficient rows][kStages stages]
+// Shared memory: [kStages full + kStages empty mbarriers | item ring][coefficient rows][kStages stages]
+//
+// Work items = (tile, x-chunk) pairs.  Non-persistent launch: one CTA per item.  Persistent launch (p.persist):
+// GPB_TMA_CTAS CTAs per SM pull items from an atomic counter and keep ONE continuous TMA pipeline running across item
+// boundaries, so the ring never drains between marches.  Every item starts with a slot that carries only the two
+// x-neighbour operand tiles (register-queue initialisation); a final empty slot carries the end-of-work signal.
+// sched[0] = next item, sched[1] = finished CTAs (the last one resets both for the next launch).
+//
+// Producer (3 TMA instructions per plane: the operand, own and ID triples are 4-D boxes).  PW = 1: a dedicated warp --
+// one lane walks the CTA's slot sequence and waits only for the stages' `empty` mbarriers (TY = 14: 7 consumer warps +
+// the producer = 8 warps at 128 registers; a ninth warp would cap the kernel at 96 registers and spill, measured
+// 40.2 vs 47.0 Gcells/s).  PW = 0: thread 0 of the first consumer warp refills right after its warp released a stage,
+// before its own arithmetic.  (r1g ncu source page of the first design, where thread 0 issued 9 loads per plane
+// after its arithmetic: 24 % of all stall samples sat on the `full` wait of the other seven warps.)
 // ------------------------------------------------------------------------------------------
 #ifndef GPB_TMA_CTAS
 #define GPB_TMA_CTAS 2
 #endif
-// Work items = (tile, x-chunk) pairs.  Non-persistent launch: one CTA per item.  Persistent launch (p.persist):
-// GPB_TMA_CTAS CTAs per SM pull items from an atomic counter and keep ONE continuous TMA pipeline running across item
-// boundaries, so the ring never drains between marches (the ncu source page showed a quarter of all stall samples on
-// the `full` mbarrier wait while fresh CTAs filled their pipelines).  Every item starts with a pseudo-plane slot that
-// carries only the two x-neighbour operand tiles (register-queue initialisation); a final empty slot carries the
-// end-of-work signal.  sched[0] = next item, sched[1] = finished CTAs (the last one resets both for the next launch).
-template <typename R, typename IDT, int TY, int TZ, int kStages, int PHASE>
-__global__ void __launch_bounds__(TY * TZ / 4, (sizeof(R) == 4 ? GPB_TMA_CTAS * 256 / (TY * TZ / 4) : 1))
-k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int tiles_k, int tiles, int nchunks, int *sched)
+template <typename R, typename IDT, int TY, int TZ, int kStages, int PHASE, int PW, int PV>
+__global__ void __launch_bounds__(TY * TZ / 4 + 32 * PW, (sizeof(R) == 4 ? GPB_TMA_CTAS : 1))
+k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int tiles_k, int tiles, int nchunks, int *sched)
 {
-    constexpr int kTmaThreads = TY * TZ / 4;  // every thread owns 4 consecutive z cells of the tile
-    static_assert(kTmaThreads % 32 == 0 && kTmaThreads <= 256, "tile shape");
+    constexpr int kTmaThreads = TY * TZ / 4;  // consumer threads: every thread owns 4 consecutive z cells of the tile
+    static_assert(kTmaThreads % 32 == 0 && kTmaThreads + 32 * PW <= 256, "tile shape");
+    // PML formulation and order are compile-time (PV = 2 * form + order - 1): with both at run time the four inlined variants of
+    // every correction spilled ~500 bytes of the straight-line update of every thread (47 -> 15 Gcells/s at 300^3)
+    constexpr int PFORM = PV >> 1, PORDER = (PV & 1) + 1;
     using L = StageLayout<R, IDT, TY, TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);   // [kStages] TMA bytes landed
-    uint64_t *empty = full + kStages;                           // [kStages] all warps have read the stage
+    uint64_t *empty = full + kStages;                           // [kStages] all consumer warps have read the stage
     volatile int *ring = reinterpret_cast<volatile int *>(empty + kStages);  // [4] item ids, producer -> consumers
     Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw + 128);
     R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
     const int coef_bytes = (int)((p.nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128);
-    unsigned char *stages = smem_raw + 128 + coef_bytes;
+    R *stab = reinterpret_cast<R *>(smem_raw + 128 + coef_bytes);   // PML R tables [nslabs][RA|RB|RE|RF][order][tmax]
+    const int tab_bytes = (int)((p.nslabs * 4 * PORDER * p.tmax * sizeof(R) + 127) / 128 * 128);
+    V4<R> *spf = reinterpret_cast<V4<R> *>(smem_raw + 128 + coef_bytes + tab_bytes);   // Phi prefetch [pf_depth][2*order][threads]
+    const int pf_bytes = p.pf_depth * 2 * PORDER * kTmaThreads * (int)sizeof(V4<R>);
+    unsigned char *stages = smem_raw + 128 + coef_bytes + tab_bytes + pf_bytes;
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int r = tid / (TZ / 4), c = (tid % (TZ / 4)) * 4;
     const int W = tiles * nchunks;
 
     if (tid == 0) {
@@ -150,30 +273,38 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int 
             mbar_init(empty + s, kTmaThreads / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        tma_prefetch_desc(&maps.opA);
-        tma_prefetch_desc(&maps.opB);
-        tma_prefetch_desc(&maps.opC);
-        tma_prefetch_desc(&maps.own0);
-        tma_prefetch_desc(&maps.id0);
     }
-    for (int m = tid; m < p.nmat; m += kTmaThreads) {
+    if (tid == 32) {
+        tma_prefetch_desc(&maps.op);
+        tma_prefetch_desc(&maps.opx);
+        tma_prefetch_desc(&maps.own);
+        tma_prefetch_desc(&maps.id);
+    }
+    for (int m = tid; m < p.nmat; m += kTmaThreads + 32 * PW) {
         scoef[m] = p.coef[m];
         ssrc[m] = p.src[m];
     }
+    for (int s = 0; s < p.nslabs; ++s) {
+        const SlabDev<R> &sl = p.slab[s];
+        for (int m = tid; m < 4 * PORDER * sl.t; m += kTmaThreads + 32 * PW) {
+            const int q = m / (PORDER * sl.t), o = (m / sl.t) % PORDER, dd = m % sl.t;
+            const R *src = q == 0 ? sl.RA : (q == 1 ? sl.RB : (q == 2 ? sl.RE : sl.RF));
+            stab[((s * 4 + q) * PORDER + o) * p.tmax + dd] = src[o * sl.t + dd];
+        }
+    }
     __syncthreads();
 
-    // ---------------- producer (thread 0): one slot of the CTA's slot sequence per call
-    int p_item = -1, p_n = -1, p_q = 0, p_g = 0;   // item being loaded, its next plane (-1 = pseudo-plane), item ordinal, slot
+    // ---------------- producer: one slot of the CTA's slot sequence per call (3 TMA instructions per plane)
+    int p_item = -1, p_n = -1, p_q = 0, p_g = 0;   // item being loaded, its next plane (-1 = x-neighbour slot), item ordinal, slot
     int p_j0 = 0, p_k0 = 0, p_l0 = 0, p_l1 = 0;
-    bool p_first = true, p_done = false;
+    bool p_done = false;
     auto fetch = [&]() {
         int w;
         if (p.persist) w = atomicAdd(sched, 1);
-        else w = p_first ? (int)(blockIdx.y * gridDim.x + blockIdx.x) : W;
-        p_first = false;
+        else w = p_q == 0 ? (int)(blockIdx.y * gridDim.x + blockIdx.x) : W;
         p_item = w < W ? w : -1;
         if (p_item >= 0) {
-            const int tile = p_item % tiles, chunk = p_item / tiles;
+            const int tile = p_item % tiles, chunk = chunk_of(p_item / tiles, nchunks);
             p_k0 = (tile % tiles_k) * TZ;
             p_j0 = (tile / tiles_k) * TY;
             p_l0 = p.p0 + chunk * p.xchunk;
@@ -182,61 +313,61 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int 
         p_n = -1;
     };
     auto produce = [&]() {
-        if (p_done) return;
         const int stg = p_g % kStages;
         if (p_g >= kStages) mbar_wait(empty + stg, (uint32_t)(((p_g / kStages) - 1) & 1));
         unsigned char *st = stages + (size_t)stg * L::bytes;
         uint64_t *bar = full + stg;
+        ++p_g;
         if (p_item < 0) {   // end of work: publish the sentinel and complete the phase without bytes
             ring[p_q & 3] = -1;
             __threadfence_block();
             mbar_arrive(bar);
             p_done = true;
-            ++p_g;
             return;
         }
+        const int ck = PHASE == 1 ? p_k0 - 4 : p_k0, cj = PHASE == 1 ? p_j0 - 1 : p_j0;
         if (p_n < 0) {
-            // pseudo-plane: x-neighbour plane (i-1 for E, i+1 for H) of the item's first plane; operand tiles B and C only
+            // x-neighbour plane (i-1 for E, i+1 for H) of the item's first plane: operand components B and C.  They land in the
+            // stage's `own` buffer: a 4-D box is dense, so components B and C of the operand buffer do not start on the 128-byte
+            // boundary a TMA destination needs.
             ring[p_q & 3] = p_item;
             __threadfence_block();
-            const int pl = PHASE == 1 ? p_l0 : p_l1 + 1;
-            mbar_expect_tx(bar, (uint32_t)((TY * L::PA + (TY + 1) * TZ) * sizeof(R)));
-            if (PHASE == 1) {
-                tma_load_3d(st + L::oB, &maps.opB, bar, p_k0 - 4, p_j0, pl);
-                tma_load_3d(st + L::oC, &maps.opC, bar, p_k0, p_j0 - 1, pl);
-            } else {
-                tma_load_3d(st + L::oB, &maps.opB, bar, p_k0, p_j0, pl);
-                tma_load_3d(st + L::oC, &maps.opC, bar, p_k0, p_j0, pl);
-            }
+            mbar_expect_tx(bar, (uint32_t)L::tx_x);
+            tma_load_4d(st + L::oOwn, &maps.opx, bar, ck, cj, PHASE == 1 ? p_l0 : p_l1 + 1, 1);
         } else {
             const int pl = PHASE == 1 ? (p_l0 + p_n + 1) : (p_l1 - 1 - p_n + 1);
             mbar_expect_tx(bar, (uint32_t)L::tx);
-            if (PHASE == 1) {
-                tma_load_3d(st + L::oA, &maps.opA, bar, p_k0 - 4, p_j0 - 1, pl);
-                tma_load_3d(st + L::oB, &maps.opB, bar, p_k0 - 4, p_j0, pl);
-                tma_load_3d(st + L::oC, &maps.opC, bar, p_k0, p_j0 - 1, pl);
-            } else {
-                tma_load_3d(st + L::oA, &maps.opA, bar, p_k0, p_j0, pl);
-                tma_load_3d(st + L::oB, &maps.opB, bar, p_k0, p_j0, pl);
-                tma_load_3d(st + L::oC, &maps.opC, bar, p_k0, p_j0, pl);
-            }
-            tma_load_3d(st + L::oO0, &maps.own0, bar, p_k0, p_j0, pl);
-            tma_load_3d(st + L::oO1, &maps.own1, bar, p_k0, p_j0, pl);
-            tma_load_3d(st + L::oO2, &maps.own2, bar, p_k0, p_j0, pl);
-            tma_load_3d(st + L::oI0, &maps.id0, bar, p_k0, p_j0, pl);
-            tma_load_3d(st + L::oI1, &maps.id1, bar, p_k0, p_j0, pl);
-            tma_load_3d(st + L::oI2, &maps.id2, bar, p_k0, p_j0, pl);
+            tma_load_4d(st + L::oOp, &maps.op, bar, ck, cj, pl, 0);
+            tma_load_4d(st + L::oOwn, &maps.own, bar, p_k0, p_j0, pl, 0);
+            tma_load_4d(st + L::oId, &maps.id, bar, p_k0, p_j0, pl, 0);
         }
-        ++p_g;
         if (++p_n == p_l1 - p_l0) {
             ++p_q;
             fetch();
         }
     };
-    if (tid == 0) {
+    if (PW) {
+        // dedicated producer warp: one lane walks the slot sequence, held back only by the `empty` barriers
+        if (tid >= kTmaThreads) {
+            if (lane == 0) {
+                fetch();
+                while (!p_done) produce();
+            }
+            return;
+        }
+    } else if (tid == 0) {
+        // thread 0 of the first consumer warp: fill the ring now, then one slot per consumed slot (right after the warp
+        // has released the slot it read, before its own arithmetic)
         fetch();
-        for (int s = 0; s < kStages; ++s) produce();
+        for (int s = 0; s < kStages && !p_done; ++s) produce();
     }
+
+    // ---------------- consumers
+    const int r = tid / (TZ / 4), c = (tid % (TZ / 4)) * 4;
+    // element offsets of my 4 cells inside the operand / own tiles
+    const int eo = PHASE == 1 ? ((r + 1) * L::PA + c + 4) : (r * L::PA + c);   // centre
+    const int eoj = PHASE == 1 ? (eo - L::PA) : (eo + L::PA);                    // j-1 (E) / j+1 (H)
+    const int e = r * TZ + c;
 
     // fields this phase writes (the operand arrays are read-only in this phase)
     R *__restrict__ F0 = PHASE == 1 ? p.Ex : p.Hx;
@@ -245,32 +376,24 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int 
 
     int g = 0;   // consumer position in the slot sequence
     for (int q = 0;; ++q) {
-    // ---------------- item prologue: the pseudo-plane slot (or the end-of-work signal)
+    // ---------------- item prologue: the x-neighbour slot (or the end-of-work signal)
     mbar_wait(full + (g % kStages), (uint32_t)((g / kStages) & 1));
     const int item = ring[q & 3];
     if (item < 0) break;
-    const int tile = item % tiles, chunkid = item / tiles;
+    const int tile = item % tiles, chunkid = chunk_of(item / tiles, nchunks);
     const int k0 = (tile % tiles_k) * TZ, j0 = (tile / tiles_k) * TY;
     const int j = j0 + r, k = k0 + c;
     const int l0 = p.p0 + chunkid * p.xchunk;
     const int l1 = min(l0 + p.xchunk, p.p1);
     const int nl = l1 - l0;
-    auto plane_of = [&](int n) { return PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1); };
     V4<R> qb, qc;   // register queue: operand B / C of the x-neighbour plane at my cells
     {
-        const unsigned char *st = stages + (size_t)(g % kStages) * L::bytes;
-        const R *sB = reinterpret_cast<const R *>(st + L::oB);
-        const R *sC = reinterpret_cast<const R *>(st + L::oC);
-        if (PHASE == 1) {
-            qb = ld4(sB + r * L::PA + c + 4);
-            qc = ld4(sC + (r + 1) * TZ + c);
-        } else {
-            qb = ld4(sB + r * L::PA + c);
-            qc = ld4(sC + r * TZ + c);
-        }
+        const R *sX = reinterpret_cast<const R *>(stages + (size_t)(g % kStages) * L::bytes + L::oOwn);
+        qb = ld4(sX + eo);
+        qc = ld4(sX + L::CS + eo);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + (g % kStages));
-        if (tid == 0) produce();
+        if (!PW && tid == 0 && !p_done) produce();
         ++g;
     }
 
@@ -279,227 +402,259 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps9 maps, int 
     unsigned smask = 0;
 #pragma unroll
     for (int s = 0; s < kMaxSlabs; ++s)
-        if (s < p.nslabs && p.slab[s].axis != 2 && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
+        if (s < p.nslabs && (p.zfused || p.slab[s].axis != 2) && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
     const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u);
-    // fast path: all 4 cells inside all three update boxes and outside every y-slab footprint; then on the planes
-    // between the x slabs (p.fast_i0 <= i < p.fast_i1) the update is straight-line code
+    // fast cells: all 4 inside all three update boxes and outside every y- and z-slab footprint; on the planes between the x
+    // slabs (p.fast_i0 <= i < p.fast_i1) such a thread needs no masks and no slab logic
     unsigned yfoot = 0;
 #pragma unroll
     for (int s = 0; s < kMaxSlabs; ++s)
-        if (s < p.nslabs && p.slab[s].axis == 1) yfoot |= (smask >> (4 * s)) & 0xfu;
+        if (s < p.nslabs && p.slab[s].axis != 0) yfoot |= (smask >> (4 * s)) & 0xfu;
     const bool fast_jk = valid && bx.kmask == 0xfu && by.kmask == 0xfu && bz.kmask == 0xfu && yfoot == 0u;
     const long long eoff = valid ? ((long long)j * p.pitch + k) : 0;
 
+    // Phi prefetch: the lowest-numbered slab that touches my cells on a plane is fetched one plane ahead (pf_depth 2) or at the
+    // top of the same iteration (pf_depth 1) with per-thread cp.async into a private shared-memory slot, so the DRAM latency of
+    // Phi hides behind the TMA wait and the base update; any further slab on the same cells (edges, corners) loads directly
+    unsigned smask6 = 0;   // bit s: slab s touches at least one of my cells
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s)
+        if ((smask >> (4 * s)) & 0xfu) smask6 |= 1u << s;
+    const bool pf = smask6 != 0u && p.pf_depth > 0;
+    auto i_of = [&](int n) { return p.x_start + (PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1)) - 1; };
+    auto prefetch = [&](V4<R> *slot, unsigned pmn, int ii) {   // Phi of the lowest-numbered slab in pmn at plane ii -> my slot
+        const SlabDev<R> &sl = p.slab[__ffs(pmn) - 1];
+        const R *phi = sl.phi + ((long long)(ii - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
+        for (int q = 0; q < 2 * PORDER; ++q) cp_async_v4<R>(slot + q * kTmaThreads, phi + q * sl.ostride);
+    };
+    unsigned act = slabs_on_plane(p, i_of(0));   // slabs on the current plane (CTA-uniform), carried from iteration to iteration
+    if (pf && p.pf_depth == 2) {
+        if (act & smask6) prefetch(spf + tid, act & smask6, i_of(0));
+        cp_async_commit();
+    }
+
     for (int n = 0; n < nl; ++n, ++g) {
-        const int pl = plane_of(n);
+        const unsigned act_next = n + 1 < nl ? slabs_on_plane(p, i_of(n + 1)) : 0u;
+        if (pf) {
+            const int np = n + p.pf_depth - 1;   // plane fetched now
+            const unsigned pmn = (p.pf_depth == 2 ? act_next : act) & smask6;
+            if (pmn) prefetch(spf + (size_t)(np % p.pf_depth) * 2 * PORDER * kTmaThreads + tid, pmn, i_of(np));
+            cp_async_commit();
+        }
+        const int pl = PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1);
         const int i = p.x_start + pl - 1;
         const unsigned char *st = stages + (size_t)(g % kStages) * L::bytes;
         mbar_wait(full + (g % kStages), (uint32_t)((g / kStages) & 1));
-        const R *sA = reinterpret_cast<const R *>(st + L::oA);
-        const R *sB = reinterpret_cast<const R *>(st + L::oB);
-        const R *sC = reinterpret_cast<const R *>(st + L::oC);
-        V4<R> a_c, a_j, b_c, c_c, c_j;
+        const R *sOp = reinterpret_cast<const R *>(st + L::oOp);
+        const R *sOwn = reinterpret_cast<const R *>(st + L::oOwn);
+        // E phase: A = Hx (needs j-1, k-1), B = Hy (k-1), C = Hz (j-1) ; H phase: A = Ex (j+1, k+1), B = Ey (k+1), C = Ez (j+1)
+        const V4<R> a_c = ld4(sOp + eo), a_j = ld4(sOp + eoj);
+        const V4<R> b_c = ld4(sOp + L::CS + eo);
+        const V4<R> c_c = ld4(sOp + 2 * L::CS + eo), c_j = ld4(sOp + 2 * L::CS + eoj);
         R a_k, b_k;
         if (PHASE == 1) {
-            // opA = Hx rows j0-1.., cols k0-4.. ; opB = Hy cols k0-4.. ; opC = Hz rows j0-1..
-            a_c = ld4(sA + (r + 1) * L::PA + c + 4);
-            a_j = ld4(sA + r * L::PA + c + 4);
-            b_c = ld4(sB + r * L::PA + c + 4);
-            c_c = ld4(sC + (r + 1) * TZ + c);
-            c_j = ld4(sC + r * TZ + c);
             a_k = __shfl_up_sync(0xffffffffu, a_c.w, 1);
             b_k = __shfl_up_sync(0xffffffffu, b_c.w, 1);
             if (c == 0 || lane == 0) {
-                a_k = sA[(r + 1) * L::PA + c + 3];
-                b_k = sB[r * L::PA + c + 3];
+                a_k = sOp[eo - 1];
+                b_k = sOp[L::CS + eo - 1];
             }
         } else {
-            // opA = Ex rows j0.., cols k0.. (+1 row, +4 cols) ; opB = Ey (+4 cols) ; opC = Ez (+1 row)
-            a_c = ld4(sA + r * L::PA + c);
-            a_j = ld4(sA + (r + 1) * L::PA + c);
-            b_c = ld4(sB + r * L::PA + c);
-            c_c = ld4(sC + r * TZ + c);
-            c_j = ld4(sC + (r + 1) * TZ + c);
             a_k = __shfl_down_sync(0xffffffffu, a_c.x, 1);
             b_k = __shfl_down_sync(0xffffffffu, b_c.x, 1);
             if (c == TZ - 4 || lane == 31) {
-                a_k = sA[r * L::PA + c + 4];
-                b_k = sB[r * L::PA + c + 4];
+                a_k = sOp[eo + 4];
+                b_k = sOp[L::CS + eo + 4];
             }
         }
-        const int e = r * TZ + c;
-        V4<R> f0 = ld4(reinterpret_cast<const R *>(st + L::oO0) + e);
-        V4<R> f1 = ld4(reinterpret_cast<const R *>(st + L::oO1) + e);
-        V4<R> f2 = ld4(reinterpret_cast<const R *>(st + L::oO2) + e);
-        const Ids4 id0 = lds_ids4<IDT>(st + L::oI0, e), id1 = lds_ids4<IDT>(st + L::oI1, e), id2 = lds_ids4<IDT>(st + L::oI2, e);
-        // this warp has taken what it needs from the stage.  No CTA-wide barrier: warps drift freely (the
-        // first ncu capture showed barrier stalls on top); the refill is issued by thread 0 once all 8
-        // warps have arrived on the stage's `empty` mbarrier (after its own compute, below).
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + (g % kStages));
-
-        bool w0 = false, w1 = false, w2 = false;
-        // one-sided differences along z (also needed by the z-slab hand-off below)
-        V4<R> dA_dz, dB_dz;
-        if (PHASE == 1) {
-            dA_dz = {a_c.x - a_k, a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z};       // dHx/dz
-            dB_dz = {b_c.x - b_k, b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z};       // dHy/dz
-        } else {
-            dA_dz = {a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z, a_k - a_c.w};       // dEx/dz
-            dB_dz = {b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z, b_k - b_c.w};       // dEy/dz
-        }
-        if (fast_jk && i >= p.fast_i0 && i < p.fast_i1) {
-            Coef4<R> q0, q1, q2, q3;
-            coef4(scoef, id0, q0, q1, q2, q3);
-            if (PHASE == 1) {
-                f0.x = q0.a * f0.x + q0.by * (c_c.x - c_j.x) - q0.bz * dB_dz.x;
-                f0.y = q1.a * f0.y + q1.by * (c_c.y - c_j.y) - q1.bz * dB_dz.y;
-                f0.z = q2.a * f0.z + q2.by * (c_c.z - c_j.z) - q2.bz * dB_dz.z;
-                f0.w = q3.a * f0.w + q3.by * (c_c.w - c_j.w) - q3.bz * dB_dz.w;
-            } else {
-                f0.x = q0.a * f0.x - q0.by * (c_j.x - c_c.x) + q0.bz * dB_dz.x;
-                f0.y = q1.a * f0.y - q1.by * (c_j.y - c_c.y) + q1.bz * dB_dz.y;
-                f0.z = q2.a * f0.z - q2.by * (c_j.z - c_c.z) + q2.bz * dB_dz.z;
-                f0.w = q3.a * f0.w - q3.by * (c_j.w - c_c.w) + q3.bz * dB_dz.w;
-            }
-            coef4(scoef, id1, q0, q1, q2, q3);
-            if (PHASE == 1) {
-                f1.x = q0.a * f1.x + q0.bz * dA_dz.x - q0.bx * (c_c.x - qc.x);
-                f1.y = q1.a * f1.y + q1.bz * dA_dz.y - q1.bx * (c_c.y - qc.y);
-                f1.z = q2.a * f1.z + q2.bz * dA_dz.z - q2.bx * (c_c.z - qc.z);
-                f1.w = q3.a * f1.w + q3.bz * dA_dz.w - q3.bx * (c_c.w - qc.w);
-            } else {
-                f1.x = q0.a * f1.x - q0.bz * dA_dz.x + q0.bx * (qc.x - c_c.x);
-                f1.y = q1.a * f1.y - q1.bz * dA_dz.y + q1.bx * (qc.y - c_c.y);
-                f1.z = q2.a * f1.z - q2.bz * dA_dz.z + q2.bx * (qc.z - c_c.z);
-                f1.w = q3.a * f1.w - q3.bz * dA_dz.w + q3.bx * (qc.w - c_c.w);
-            }
-            coef4(scoef, id2, q0, q1, q2, q3);
-            if (PHASE == 1) {
-                f2.x = q0.a * f2.x + q0.bx * (b_c.x - qb.x) - q0.by * (a_c.x - a_j.x);
-                f2.y = q1.a * f2.y + q1.bx * (b_c.y - qb.y) - q1.by * (a_c.y - a_j.y);
-                f2.z = q2.a * f2.z + q2.bx * (b_c.z - qb.z) - q2.by * (a_c.z - a_j.z);
-                f2.w = q3.a * f2.w + q3.bx * (b_c.w - qb.w) - q3.by * (a_c.w - a_j.w);
-            } else {
-                f2.x = q0.a * f2.x - q0.bx * (qb.x - b_c.x) + q0.by * (a_j.x - a_c.x);
-                f2.y = q1.a * f2.y - q1.bx * (qb.y - b_c.y) + q1.by * (a_j.y - a_c.y);
-                f2.z = q2.a * f2.z - q2.bx * (qb.z - b_c.z) + q2.by * (a_j.z - a_c.z);
-                f2.w = q3.a * f2.w - q3.bx * (qb.w - b_c.w) + q3.by * (a_j.w - a_c.w);
-            }
-            w0 = w1 = w2 = true;
-        } else if (any) {
-            // E phase: backward differences (c - neighbour); H phase: forward (neighbour - c)
-            V4<R> dA_dy, dB_dx, dC_dx, dC_dy;
-            if (PHASE == 1) {
-                dA_dy = {a_c.x - a_j.x, a_c.y - a_j.y, a_c.z - a_j.z, a_c.w - a_j.w};   // dHx/dy
-                dB_dx = {b_c.x - qb.x, b_c.y - qb.y, b_c.z - qb.z, b_c.w - qb.w};         // dHy/dx
-                dC_dx = {c_c.x - qc.x, c_c.y - qc.y, c_c.z - qc.z, c_c.w - qc.w};         // dHz/dx
-                dC_dy = {c_c.x - c_j.x, c_c.y - c_j.y, c_c.z - c_j.z, c_c.w - c_j.w};   // dHz/dy
-            } else {
-                dA_dy = {a_j.x - a_c.x, a_j.y - a_c.y, a_j.z - a_c.z, a_j.w - a_c.w};   // dEx/dy
-                dB_dx = {qb.x - b_c.x, qb.y - b_c.y, qb.z - b_c.z, qb.w - b_c.w};         // dEy/dx
-                dC_dx = {qc.x - c_c.x, qc.y - c_c.y, qc.z - c_c.z, qc.w - c_c.w};         // dEz/dx
-                dC_dy = {c_j.x - c_c.x, c_j.y - c_c.y, c_j.z - c_c.z, c_j.w - c_c.w};   // dEz/dy
-            }
-            const unsigned m0 = (i >= p.box[0].lo[0] && i < p.box[0].hi[0]) ? bx.kmask : 0u;
-            const unsigned m1 = (i >= p.box[1].lo[0] && i < p.box[1].hi[0]) ? by.kmask : 0u;
-            const unsigned m2 = (i >= p.box[2].lo[0] && i < p.box[2].hi[0]) ? bz.kmask : 0u;
-            unsigned pm = 0;
-#pragma unroll
-            for (int s = 0; s < kMaxSlabs; ++s)
-                if (((smask >> (4 * s)) & 0xfu) && i >= p.slab[s].lo[0] && i < p.slab[s].hi[0]) pm |= 1u << s;
-            w0 = m0 != 0; w1 = m1 != 0; w2 = m2 != 0;
-            // E phase: Ex = CA Ex + CBy dHz/dy - CBz dHy/dz ; Ey = CA Ey + CBz dHx/dz - CBx dHz/dx ; Ez = CA Ez + CBx dHy/dx - CBy dHx/dy
-            // H phase: Hx = DA Hx - DBy dEz/dy + DBz dEy/dz ; Hy = DA Hy - DBz dEx/dz + DBx dEz/dx ; Hz = DA Hz - DBx dEy/dx + DBy dEx/dy
-            if (m0) {
-                Coef4<R> q0, q1, q2, q3;
-                coef4(scoef, id0, q0, q1, q2, q3);
-                if (PHASE == 1) {
-                    f0.x = sel(m0, 0, q0.a * f0.x + q0.by * dC_dy.x - q0.bz * dB_dz.x, f0.x);
-                    f0.y = sel(m0, 1, q1.a * f0.y + q1.by * dC_dy.y - q1.bz * dB_dz.y, f0.y);
-                    f0.z = sel(m0, 2, q2.a * f0.z + q2.by * dC_dy.z - q2.bz * dB_dz.z, f0.z);
-                    f0.w = sel(m0, 3, q3.a * f0.w + q3.by * dC_dy.w - q3.bz * dB_dz.w, f0.w);
-                } else {
-                    f0.x = sel(m0, 0, q0.a * f0.x - q0.by * dC_dy.x + q0.bz * dB_dz.x, f0.x);
-                    f0.y = sel(m0, 1, q1.a * f0.y - q1.by * dC_dy.y + q1.bz * dB_dz.y, f0.y);
-                    f0.z = sel(m0, 2, q2.a * f0.z - q2.by * dC_dy.z + q2.bz * dB_dz.z, f0.z);
-                    f0.w = sel(m0, 3, q3.a * f0.w - q3.by * dC_dy.w + q3.bz * dB_dz.w, f0.w);
-                }
-            }
-            if (m1) {
-                Coef4<R> q0, q1, q2, q3;
-                coef4(scoef, id1, q0, q1, q2, q3);
-                if (PHASE == 1) {
-                    f1.x = sel(m1, 0, q0.a * f1.x + q0.bz * dA_dz.x - q0.bx * dC_dx.x, f1.x);
-                    f1.y = sel(m1, 1, q1.a * f1.y + q1.bz * dA_dz.y - q1.bx * dC_dx.y, f1.y);
-                    f1.z = sel(m1, 2, q2.a * f1.z + q2.bz * dA_dz.z - q2.bx * dC_dx.z, f1.z);
-                    f1.w = sel(m1, 3, q3.a * f1.w + q3.bz * dA_dz.w - q3.bx * dC_dx.w, f1.w);
-                } else {
-                    f1.x = sel(m1, 0, q0.a * f1.x - q0.bz * dA_dz.x + q0.bx * dC_dx.x, f1.x);
-                    f1.y = sel(m1, 1, q1.a * f1.y - q1.bz * dA_dz.y + q1.bx * dC_dx.y, f1.y);
-                    f1.z = sel(m1, 2, q2.a * f1.z - q2.bz * dA_dz.z + q2.bx * dC_dx.z, f1.z);
-                    f1.w = sel(m1, 3, q3.a * f1.w - q3.bz * dA_dz.w + q3.bx * dC_dx.w, f1.w);
-                }
-            }
-            if (m2) {
-                Coef4<R> q0, q1, q2, q3;
-                coef4(scoef, id2, q0, q1, q2, q3);
-                if (PHASE == 1) {
-                    f2.x = sel(m2, 0, q0.a * f2.x + q0.bx * dB_dx.x - q0.by * dA_dy.x, f2.x);
-                    f2.y = sel(m2, 1, q1.a * f2.y + q1.bx * dB_dx.y - q1.by * dA_dy.y, f2.y);
-                    f2.z = sel(m2, 2, q2.a * f2.z + q2.bx * dB_dx.z - q2.by * dA_dy.z, f2.z);
-                    f2.w = sel(m2, 3, q3.a * f2.w + q3.bx * dB_dx.w - q3.by * dA_dy.w, f2.w);
-                } else {
-                    f2.x = sel(m2, 0, q0.a * f2.x - q0.bx * dB_dx.x + q0.by * dA_dy.x, f2.x);
-                    f2.y = sel(m2, 1, q1.a * f2.y - q1.bx * dB_dx.y + q1.by * dA_dy.y, f2.y);
-                    f2.z = sel(m2, 2, q2.a * f2.z - q2.bx * dB_dx.z + q2.by * dA_dy.z, f2.z);
-                    f2.w = sel(m2, 3, q3.a * f2.w - q3.bx * dB_dx.w + q3.by * dA_dy.w, f2.w);
-                }
-            }
-            if (pm) {
-                for (int s = 0; s < p.nslabs; ++s) {
-                    if (!((pm >> s) & 1u)) continue;
-                    const SlabDev<R> &sl = p.slab[s];
-                    const unsigned m = (smask >> (4 * s)) & 0xfu;
-                    const int pos = sl.axis == 0 ? i : j;
-                    const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
-                    const PmlCo<R> co = pml_load(p.form, p.order, sl, depth);
-                    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
-                    if (PHASE == 1) {
-                        if (sl.axis == 0) {  // Ey -= , dHz/dx ; Ez += , dHy/dx
-                            pml_comp4(p.form, p.order, co, sl, phi, m, id1, ssrc, (R)-1, dC_dx, f1);
-                            pml_comp4(p.form, p.order, co, sl, phi + sl.ostride, m, id2, ssrc, (R)1, dB_dx, f2);
-                            w1 = w2 = true;
-                        } else {  // Ex += , dHz/dy ; Ez -= , dHx/dy
-                            pml_comp4(p.form, p.order, co, sl, phi, m, id0, ssrc, (R)1, dC_dy, f0);
-                            pml_comp4(p.form, p.order, co, sl, phi + sl.ostride, m, id2, ssrc, (R)-1, dA_dy, f2);
-                            w0 = w2 = true;
-                        }
-                    } else {
-                        if (sl.axis == 0) {  // Hy += , dEz/dx ; Hz -= , dEy/dx
-                            pml_comp4(p.form, p.order, co, sl, phi, m, id1, ssrc, (R)1, dC_dx, f1);
-                            pml_comp4(p.form, p.order, co, sl, phi + sl.ostride, m, id2, ssrc, (R)-1, dB_dx, f2);
-                            w1 = w2 = true;
-                        } else {  // Hx -= , dEz/dy ; Hz += , dEx/dy
-                            pml_comp4(p.form, p.order, co, sl, phi, m, id0, ssrc, (R)-1, dC_dy, f0);
-                            pml_comp4(p.form, p.order, co, sl, phi + sl.ostride, m, id2, ssrc, (R)1, dA_dy, f2);
-                            w0 = w2 = true;
-                        }
-                    }
-                }
-            }
+        V4<R> f0 = ld4(sOwn + e), f1 = ld4(sOwn + L::OS + e), f2 = ld4(sOwn + 2 * L::OS + e);
+        const unsigned pm = act & smask6;   // slabs on my cells on this plane; 0 for fast threads by construction
+        // A warp without slab cells on this plane has now taken what it needs from the stage and hands it back to the producer.
+        // A warp with slab cells keeps it until its PML corrections are done: they re-read their operands and IDs from the stage
+        // instead of keeping them in registers (which spilled the straight-line update of every thread).
+        const bool wpml = __any_sync(0xffffffffu, pm != 0u);
+        if (!wpml) {
+            if (lane == 0) mbar_arrive(empty + (g % kStages));
+            if (!PW && tid == 0 && !p_done) produce();
         }
 
         if (any) {
+            const Ids4 id0 = lds_ids4<IDT>(st + L::oId, e), id1 = lds_ids4<IDT>(st + L::oId, L::OS + e), id2 = lds_ids4<IDT>(st + L::oId, 2 * L::OS + e);
+            // one straight-line update for every thread; threads with cells outside an update box (domain faces, the
+            // two x-slab plane ranges) put the old value back per cell afterwards
+            const bool fast = fast_jk && i >= p.fast_i0 && i < p.fast_i1;
+            unsigned m0 = 0xfu, m1 = 0xfu, m2 = 0xfu;
+            if (!fast) {
+                m0 = (i >= p.box[0].lo[0] && i < p.box[0].hi[0]) ? bx.kmask : 0u;
+                m1 = (i >= p.box[1].lo[0] && i < p.box[1].hi[0]) ? by.kmask : 0u;
+                m2 = (i >= p.box[2].lo[0] && i < p.box[2].hi[0]) ? bz.kmask : 0u;
+            }
+            // E phase: backward differences (c - neighbour); H phase: forward (neighbour - c)
+            // E phase: Ex = CA Ex + CBy dHz/dy - CBz dHy/dz ; Ey = CA Ey + CBz dHx/dz - CBx dHz/dx ; Ez = CA Ez + CBx dHy/dx - CBy dHx/dy
+            // H phase: Hx = DA Hx - DBy dEz/dy + DBz dEy/dz ; Hy = DA Hy - DBz dEx/dz + DBx dEz/dx ; Hz = DA Hz - DBx dEy/dx + DBy dEx/dy
+            {
+                V4<R> dC_dy, dB_dz;
+                if (PHASE == 1) {
+                    dB_dz = {b_c.x - b_k, b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z};       // dHy/dz
+                    dC_dy = {c_c.x - c_j.x, c_c.y - c_j.y, c_c.z - c_j.z, c_c.w - c_j.w};     // dHz/dy
+                } else {
+                    dB_dz = {b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z, b_k - b_c.w};       // dEy/dz
+                    dC_dy = {c_j.x - c_c.x, c_j.y - c_c.y, c_j.z - c_c.z, c_j.w - c_c.w};     // dEz/dy
+                }
+                Coef4<R> q0, q1, q2, q3;
+                coef4(scoef, id0, q0, q1, q2, q3);
+                V4<R> u;
+                if (PHASE == 1) {
+                    u.x = q0.a * f0.x + q0.by * dC_dy.x - q0.bz * dB_dz.x;
+                    u.y = q1.a * f0.y + q1.by * dC_dy.y - q1.bz * dB_dz.y;
+                    u.z = q2.a * f0.z + q2.by * dC_dy.z - q2.bz * dB_dz.z;
+                    u.w = q3.a * f0.w + q3.by * dC_dy.w - q3.bz * dB_dz.w;
+                } else {
+                    u.x = q0.a * f0.x - q0.by * dC_dy.x + q0.bz * dB_dz.x;
+                    u.y = q1.a * f0.y - q1.by * dC_dy.y + q1.bz * dB_dz.y;
+                    u.z = q2.a * f0.z - q2.by * dC_dy.z + q2.bz * dB_dz.z;
+                    u.w = q3.a * f0.w - q3.by * dC_dy.w + q3.bz * dB_dz.w;
+                }
+                if (!fast) { u.x = sel(m0, 0, u.x, f0.x); u.y = sel(m0, 1, u.y, f0.y); u.z = sel(m0, 2, u.z, f0.z); u.w = sel(m0, 3, u.w, f0.w); }
+                f0 = u;
+            }
+            {
+                V4<R> dA_dz, dC_dx;
+                if (PHASE == 1) {
+                    dA_dz = {a_c.x - a_k, a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z};       // dHx/dz
+                    dC_dx = {c_c.x - qc.x, c_c.y - qc.y, c_c.z - qc.z, c_c.w - qc.w};         // dHz/dx
+                } else {
+                    dA_dz = {a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z, a_k - a_c.w};       // dEx/dz
+                    dC_dx = {qc.x - c_c.x, qc.y - c_c.y, qc.z - c_c.z, qc.w - c_c.w};         // dEz/dx
+                }
+                Coef4<R> q0, q1, q2, q3;
+                coef4(scoef, id1, q0, q1, q2, q3);
+                V4<R> u;
+                if (PHASE == 1) {
+                    u.x = q0.a * f1.x + q0.bz * dA_dz.x - q0.bx * dC_dx.x;
+                    u.y = q1.a * f1.y + q1.bz * dA_dz.y - q1.bx * dC_dx.y;
+                    u.z = q2.a * f1.z + q2.bz * dA_dz.z - q2.bx * dC_dx.z;
+                    u.w = q3.a * f1.w + q3.bz * dA_dz.w - q3.bx * dC_dx.w;
+                } else {
+                    u.x = q0.a * f1.x - q0.bz * dA_dz.x + q0.bx * dC_dx.x;
+                    u.y = q1.a * f1.y - q1.bz * dA_dz.y + q1.bx * dC_dx.y;
+                    u.z = q2.a * f1.z - q2.bz * dA_dz.z + q2.bx * dC_dx.z;
+                    u.w = q3.a * f1.w - q3.bz * dA_dz.w + q3.bx * dC_dx.w;
+                }
+                if (!fast) { u.x = sel(m1, 0, u.x, f1.x); u.y = sel(m1, 1, u.y, f1.y); u.z = sel(m1, 2, u.z, f1.z); u.w = sel(m1, 3, u.w, f1.w); }
+                f1 = u;
+            }
+            {
+                V4<R> dB_dx, dA_dy;
+                if (PHASE == 1) {
+                    dA_dy = {a_c.x - a_j.x, a_c.y - a_j.y, a_c.z - a_j.z, a_c.w - a_j.w};     // dHx/dy
+                    dB_dx = {b_c.x - qb.x, b_c.y - qb.y, b_c.z - qb.z, b_c.w - qb.w};         // dHy/dx
+                } else {
+                    dA_dy = {a_j.x - a_c.x, a_j.y - a_c.y, a_j.z - a_c.z, a_j.w - a_c.w};     // dEx/dy
+                    dB_dx = {qb.x - b_c.x, qb.y - b_c.y, qb.z - b_c.z, qb.w - b_c.w};         // dEy/dx
+                }
+                Coef4<R> q0, q1, q2, q3;
+                coef4(scoef, id2, q0, q1, q2, q3);
+                V4<R> u;
+                if (PHASE == 1) {
+                    u.x = q0.a * f2.x + q0.bx * dB_dx.x - q0.by * dA_dy.x;
+                    u.y = q1.a * f2.y + q1.bx * dB_dx.y - q1.by * dA_dy.y;
+                    u.z = q2.a * f2.z + q2.bx * dB_dx.z - q2.by * dA_dy.z;
+                    u.w = q3.a * f2.w + q3.bx * dB_dx.w - q3.by * dA_dy.w;
+                } else {
+                    u.x = q0.a * f2.x - q0.bx * dB_dx.x + q0.by * dA_dy.x;
+                    u.y = q1.a * f2.y - q1.bx * dB_dx.y + q1.by * dA_dy.y;
+                    u.z = q2.a * f2.z - q2.bx * dB_dx.z + q2.by * dA_dy.z;
+                    u.w = q3.a * f2.w - q3.bx * dB_dx.w + q3.by * dA_dy.w;
+                }
+                if (!fast) { u.x = sel(m2, 0, u.x, f2.x); u.y = sel(m2, 1, u.y, f2.y); u.z = sel(m2, 2, u.z, f2.z); u.w = sel(m2, 3, u.w, f2.w); }
+                f2 = u;
+            }
+            bool w0 = m0 != 0u, w1 = m1 != 0u, w2 = m2 != 0u;
+            if (pm) {
+                const V4<R> *slot = nullptr;
+                if (pf) {
+                    if (p.pf_depth == 2) cp_async_wait1();
+                    else cp_async_wait0();
+                    slot = spf + (size_t)(n % p.pf_depth) * 2 * PORDER * kTmaThreads + tid;
+                }
+                for (int s = 0; s < p.nslabs; ++s) {   // G.pmls order
+                    if (!((pm >> s) & 1u)) continue;
+                    const SlabDev<R> &sl = p.slab[s];
+                    const unsigned m = (smask >> (4 * s)) & 0xfu;
+                    const R *tb = stab + (size_t)s * 4 * PORDER * p.tmax;
+                    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
+                    const V4<R> *slb = slot ? slot + kTmaThreads : nullptr;
+                    // Component / derivative / sign table of SURVEY.md section 8a (identical in all 48 reference kernels):
+                    //   E phase  x: Ey -= dHz/dx, Ez += dHy/dx   y: Ex += dHz/dy, Ez -= dHx/dy   z: Ex -= dHy/dz, Ey += dHx/dz
+                    //   H phase  x: Hy += dEz/dx, Hz -= dEy/dx   y: Hx -= dEz/dy, Hz += dEx/dy   z: Hx += dEy/dz, Hy -= dEx/dz
+                    // The derivatives are formed again from the stage (same operands, same expression as above).
+                    if (sl.axis == 0) {
+                        const int depth = sl.minus ? (sl.dref - i) : (i - sl.dref);
+                        V4<R> dF;
+                        if (PHASE == 1) dF = {c_c.x - qc.x, c_c.y - qc.y, c_c.z - qc.z, c_c.w - qc.w};
+                        else dF = {qc.x - c_c.x, qc.y - c_c.y, qc.z - c_c.z, qc.w - c_c.w};
+                        pml_comp<R, 0>(PFORM, PORDER, tb, p.tmax, depth, 0, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, L::OS + e), ssrc, PHASE == 1 ? (R)-1 : (R)1, dF, f1, phi,
+                                       2 * sl.ostride, slot, 2 * kTmaThreads);
+                        if (PHASE == 1) dF = {b_c.x - qb.x, b_c.y - qb.y, b_c.z - qb.z, b_c.w - qb.w};
+                        else dF = {qb.x - b_c.x, qb.y - b_c.y, qb.z - b_c.z, qb.w - b_c.w};
+                        pml_comp<R, 0>(PFORM, PORDER, tb, p.tmax, depth, 0, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, 2 * L::OS + e), ssrc, PHASE == 1 ? (R)1 : (R)-1, dF, f2,
+                                       phi + sl.ostride, 2 * sl.ostride, slb, 2 * kTmaThreads);
+                        w1 = w2 = true;
+                    } else if (sl.axis == 1) {
+                        const int depth = sl.minus ? (sl.dref - j) : (j - sl.dref);
+                        V4<R> dF;
+                        {
+                            const V4<R> cj = ld4(sOp + 2 * L::CS + eoj);
+                            if (PHASE == 1) dF = {c_c.x - cj.x, c_c.y - cj.y, c_c.z - cj.z, c_c.w - cj.w};
+                            else dF = {cj.x - c_c.x, cj.y - c_c.y, cj.z - c_c.z, cj.w - c_c.w};
+                        }
+                        pml_comp<R, 0>(PFORM, PORDER, tb, p.tmax, depth, 0, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, e), ssrc, PHASE == 1 ? (R)1 : (R)-1, dF, f0, phi,
+                                       2 * sl.ostride, slot, 2 * kTmaThreads);
+                        {
+                            const V4<R> ac = ld4(sOp + eo), aj = ld4(sOp + eoj);
+                            if (PHASE == 1) dF = {ac.x - aj.x, ac.y - aj.y, ac.z - aj.z, ac.w - aj.w};
+                            else dF = {aj.x - ac.x, aj.y - ac.y, aj.z - ac.z, aj.w - ac.w};
+                        }
+                        pml_comp<R, 0>(PFORM, PORDER, tb, p.tmax, depth, 0, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, 2 * L::OS + e), ssrc, PHASE == 1 ? (R)-1 : (R)1, dF, f2,
+                                       phi + sl.ostride, 2 * sl.ostride, slb, 2 * kTmaThreads);
+                        w0 = w2 = true;
+                    } else {
+                        const int depth = sl.minus ? (sl.dref - k) : (k - sl.dref), ds = sl.minus ? -1 : 1;
+                        V4<R> dF;
+                        {
+                            const R bk = sOp[L::CS + eo + (PHASE == 1 ? -1 : 4)];
+                            if (PHASE == 1) dF = {b_c.x - bk, b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z};
+                            else dF = {b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z, bk - b_c.w};
+                        }
+                        pml_comp<R, 1>(PFORM, PORDER, tb, p.tmax, depth, ds, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, e), ssrc, PHASE == 1 ? (R)-1 : (R)1, dF, f0, phi,
+                                       2 * sl.ostride, slot, 2 * kTmaThreads);
+                        {
+                            const V4<R> ac = ld4(sOp + eo);
+                            const R ak = sOp[eo + (PHASE == 1 ? -1 : 4)];
+                            if (PHASE == 1) dF = {ac.x - ak, ac.y - ac.x, ac.z - ac.y, ac.w - ac.z};
+                            else dF = {ac.y - ac.x, ac.z - ac.y, ac.w - ac.z, ak - ac.w};
+                        }
+                        pml_comp<R, 1>(PFORM, PORDER, tb, p.tmax, depth, ds, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, L::OS + e), ssrc, PHASE == 1 ? (R)1 : (R)-1, dF, f1,
+                                       phi + sl.ostride, 2 * sl.ostride, slb, 2 * kTmaThreads);
+                        w0 = w1 = true;
+                    }
+                    slot = nullptr;   // only the first slab was prefetched
+                }
+            }
             const long long off = (long long)pl * p.plane + eoff;
             if (w0) st4(F0 + off, f0);
             if (w1) st4(F1 + off, f1);
             if (w2) st4(F2 + off, f2);
         }
-        if (tid == 0) produce();   // refill the ring one slot ahead of the oldest stage (waits for all warps' `empty` arrival)
-
+        if (wpml) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + (g % kStages));
+            if (!PW && tid == 0 && !p_done) produce();
+        }
         qb = b_c;
         qc = c_c;
+        act = act_next;
     }
     }   // items
 

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(cons
                     const int pos = sl.axis == 0 ? i : j;
                     const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
                     const PmlCo<R> co = pml_load(p.form, p.order, sl, depth);
-                    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+                    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
                     const unsigned m = (smask >> (4 * s)) & 0xfu;
                     if (sl.axis == 0) {  // Hy += , dEz/dx ; Hz -= , dEy/dx
                         pml_comp4(p.form, p.order, co, sl, phi, m, idy_, srcm, (R)1, dEz_dx, hy);
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
                     const int pos = sl.axis == 0 ? i : j;
                     const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
                     const PmlCo<R> co = pml_load(p.form, p.order, sl, depth);
-                    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+                    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
                     const unsigned m = (smask >> (4 * s)) & 0xfu;
                     if (sl.axis == 0) {  // Ey -= , dHz/dx ; Ez += , dHy/dx
                         pml_comp4(p.form, p.order, co, sl, phi, m, idy_, srce, (R)-1, dHz_dx, ey);
@@ -550,7 +550,7 @@ __device__ __forceinline__ void pml_slab_cell(const PhaseParams<R> &p, int phase
     const int pos = a == 0 ? i : (a == 1 ? j : k);
     const int depth = sl.minus ? (sl.dref - pos) : (pos - sl.dref);
     const long long off = (long long)(i - p.x_start + 1) * p.plane + (long long)j * p.pitch + k;
-    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.lo[2]);
+    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
     const long long st = a == 0 ? p.plane : (a == 1 ? p.pitch : 1);
     const R *src = p.src;
     R *Fa, *Fb;

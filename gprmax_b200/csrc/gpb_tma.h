@@ -1,0 +1,39 @@
+// gpb_tma.h -- interface between the host side (gpb_core.cu) and the translation units that hold the TMA-staged
+// E/H kernels (gpb_tma_inst.cu, compiled once per (float type, PML variant) -- see gprmax_b200/build.py).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "gpb_kernels.cuh"
+
+namespace gpb {
+
+// The three fields a phase reads (operands), the three it updates (own) and their three ID arrays are each ONE
+// allocation [3][planes][rows][pitch], so a 4-D box fetches a whole triple with a single TMA instruction.
+struct TmaMaps4 {
+    CUtensorMap op;    // operands, box (TZ+4) x (TY+1) x 1 x 3 (E phase: Hx,Hy,Hz from (k0-4, j0-1); H phase: Ex,Ey,Ez from (k0, j0))
+    CUtensorMap opx;   // x-neighbour plane at the start of an item: components B and C only, same box x 2
+    CUtensorMap own;   // fields being updated, box TZ x TY x 1 x 3
+    CUtensorMap id;    // their material IDs,   box TZ x TY x 1 x 3 (elements of IDT)
+};
+
+template <typename R>
+struct TmaLaunch {
+    PhaseParams<R> p;         // phase parameters; p0/p1/xchunk/persist/fast_i*/zfused set by the caller, tmax/pf_depth by the launcher
+    const TmaMaps4 *maps;
+    int phase;                // 0 magnetic, 1 electric
+    int ty, tz, stages, pw;   // tile, ring depth, dedicated producer warp
+    int idbytes;              // 1, 2, 4
+    int pf_max;               // upper bound on the Phi prefetch distance (GPB_TMA_PF)
+    int sm_count;
+    int *sched;               // [2] work-item scheduler state
+    cudaStream_t stream;
+};
+
+// PV = 2 * formulation + order - 1.  Returns 0, or 1 with *err filled.
+template <typename R, int PV>
+int tma_launch(const TmaLaunch<R> &a, std::string *err);
+
+}  // namespace gpb

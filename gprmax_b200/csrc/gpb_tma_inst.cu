@@ -1,0 +1,92 @@
+// gpb_tma_inst.cu -- one translation unit per (GPB_TMA_R, GPB_TMA_PV): the TMA-staged E/H kernels of that float type
+// and PML variant in every tile shape and ID width, plus their launcher.  Split like this so that (a) the PML
+// formulation and order are compile-time constants inside the kernels and (b) the variants compile in parallel.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "gpb_kernels_tma.cuh"
+
+#ifndef GPB_TMA_R
+#define GPB_TMA_R float
+#endif
+#ifndef GPB_TMA_PV
+#define GPB_TMA_PV 0
+#endif
+
+namespace gpb {
+
+static int tma_fail(std::string *err, const char *what, cudaError_t e)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed: %s", what, cudaGetErrorString(e));
+    if (err) *err = buf;
+    return 1;
+}
+
+template <typename R, int PV, typename IDT, int TY, int TZ, int S, int PW>
+static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
+{
+    using L = StageLayout<R, IDT, TY, TZ>;
+    constexpr int order = (PV & 1) + 1;
+    PhaseParams<R> p = a.p;
+    const int tiles_k = (p.pitch + TZ - 1) / TZ, tiles_j = (p.ny + 1 + TY - 1) / TY;
+    // shared memory: barriers | coefficient rows | PML R tables | per-thread Phi prefetch slots | stage ring
+    p.tmax = 1;
+    for (int s = 0; s < p.nslabs; ++s) p.tmax = std::max(p.tmax, p.slab[s].t);
+    const size_t fixed = 128 + (size_t)((p.nmat * (sizeof(Coef4<R>) + sizeof(R)) + 127) / 128 * 128) +
+                         (size_t)((p.nslabs * 4 * order * p.tmax * sizeof(R) + 127) / 128 * 128) + (size_t)S * L::bytes;
+    const size_t pf_unit = (size_t)2 * order * (TY * TZ / 4) * 4 * sizeof(R);   // one plane of Phi per thread
+    const size_t smem_cap = (sizeof(R) == 4 ? (size_t)(227 * 1024) / GPB_TMA_CTAS : (size_t)227 * 1024) - 1024;
+    p.pf_depth = p.nslabs == 0 ? 0 : (fixed + 2 * pf_unit <= smem_cap ? 2 : (fixed + pf_unit <= smem_cap ? 1 : 0));
+    p.pf_depth = std::min(p.pf_depth, a.pf_max);
+    const size_t smem = fixed + p.pf_depth * pf_unit;
+    const int tiles = tiles_k * tiles_j, nchunks = (p.p1 - p.p0 + p.xchunk - 1) / p.xchunk;
+    // persistent: as many CTAs as fit on the GPU at once (2 per SM for fp32), pulling (tile, chunk) items from a.sched
+    const int resident = (sizeof(R) == 4 ? GPB_TMA_CTAS : 1) * a.sm_count;
+    const dim3 grid = p.persist ? dim3((unsigned)std::min(tiles * nchunks, resident)) : dim3((unsigned)tiles, (unsigned)nchunks);
+    cudaError_t e;
+    if (a.phase == 0) {
+        auto kern = k_update_tma<R, IDT, TY, TZ, S, 0, PW, PV>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return tma_fail(err, "cudaFuncSetAttribute", e);
+        kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, a.sched);
+    } else {
+        auto kern = k_update_tma<R, IDT, TY, TZ, S, 1, PW, PV>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return tma_fail(err, "cudaFuncSetAttribute", e);
+        kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, a.sched);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return tma_fail(err, "k_update_tma launch", e);
+    return 0;
+}
+
+template <typename R, int PV, typename IDT>
+static int tma_launch_idt(const TmaLaunch<R> &a, std::string *err)
+{
+#define GPB_TMA_CASE(TY_, TZ_, S_, PW_) \
+    if (a.ty == TY_ && a.tz == TZ_ && a.stages == S_ && a.pw == PW_) return tma_launch_cfg<R, PV, IDT, TY_, TZ_, S_, PW_>(a, err)
+    GPB_TMA_CASE(14, 64, 3, 1);
+    GPB_TMA_CASE(16, 64, 3, 0);
+    GPB_TMA_CASE(8, 128, 3, 0);
+    GPB_TMA_CASE(32, 32, 3, 0);
+#ifdef GPB_TMA_SWEEP   // ring-depth sweep variants of profiles/README.md (not built by default)
+    GPB_TMA_CASE(14, 64, 4, 1);
+    GPB_TMA_CASE(16, 64, 2, 0);
+#endif
+#undef GPB_TMA_CASE
+    char buf[256];
+    snprintf(buf, sizeof buf, "no TMA kernel instantiated for tile %d x %d with %d stages (producer warp %d)", a.ty, a.tz, a.stages, a.pw);
+    if (err) *err = buf;
+    return 1;
+}
+
+template <typename R, int PV>
+int tma_launch(const TmaLaunch<R> &a, std::string *err)
+{
+    if (a.idbytes == 1) return tma_launch_idt<R, PV, uint8_t>(a, err);
+    if (a.idbytes == 2) return tma_launch_idt<R, PV, uint16_t>(a, err);
+    return tma_launch_idt<R, PV, uint32_t>(a, err);
+}
+
+template int tma_launch<GPB_TMA_R, GPB_TMA_PV>(const TmaLaunch<GPB_TMA_R> &, std::string *);
+
+}  // namespace gpb

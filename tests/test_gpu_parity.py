@@ -141,16 +141,21 @@ TMA_FIXTURES = ['pml_HORIPML_1', 'pml_HORIPML_2', 'pml_MRIPML_1', 'pml_MRIPML_2'
 
 
 @pytest.mark.parametrize('name', TMA_FIXTURES)
-@pytest.mark.parametrize('mode', ['tma', 'tma_nopersist', 'tma_tile8x128', 'scalar'])
+@pytest.mark.parametrize('mode', ['tma', 'tma_nopersist', 'tma_pw0', 'tma_tile8x128', 'tma_zsplit', 'scalar'])
 def test_f64_every_kernel_path(name, mode, monkeypatch):
     """The small fixtures normally run on the register-vectorised kernels (the TMA kernels are only selected above
     2.5 M nodes); force each kernel family in turn so that all of them are held to the 1e-10 bar:
-    TMA-staged persistent CTAs (default), TMA with one CTA per work item, another TMA tile shape, generic scalar."""
+    TMA-staged persistent CTAs with a producer warp (default), one CTA per work item, producer = thread 0 of a 16 x 64 tile,
+    another tile shape, z-slab PML in its own kernel, generic scalar."""
     from gprmax_b200.model_io import load_model
     if mode.startswith('tma'):
         monkeypatch.setenv('GPB_FORCE_TMA', '1')
     if mode == 'tma_nopersist':
         monkeypatch.setenv('GPB_TMA_NOPERSIST', '1')
+    if mode == 'tma_pw0':
+        monkeypatch.setenv('GPB_TMA_PW', '0')
+    if mode == 'tma_zsplit':
+        monkeypatch.setenv('GPB_TMA_ZSPLIT', '1')
     if mode == 'tma_tile8x128':
         monkeypatch.setenv('GPB_TMA_TZ', '128')
     if mode == 'scalar':
