@@ -19,7 +19,7 @@ RX_ROWS = ['Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz', 'Ix', 'Iy', 'Iz']
 SYMBOLS = ['gpb_device_count', 'gpb_device_info', 'gpb_create', 'gpb_destroy', 'gpb_run', 'gpb_iteration',
            'gpb_elapsed_seconds', 'gpb_mem_used', 'gpb_kernel_launches', 'gpb_reset', 'gpb_profile', 'gpb_half_step', 'gpb_halo',
            'gpb_stream', 'gpb_synchronize', 'gpb_get_receivers', 'gpb_get_snapshot', 'gpb_get_tline',
-           'gpb_get_field', 'gpb_set_field', 'gpb_last_error', 'gpb_version']
+           'gpb_get_field', 'gpb_set_field', 'gpb_release_cached', 'gpb_last_error', 'gpb_version']
 
 
 class DeviceInfo(C.Structure):

@@ -14,8 +14,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace gpb;
@@ -38,6 +42,131 @@ static int fail(const char *fmt, ...)
         cudaError_t e_ = (call);                                                                      \
         if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// ----------------------------------------------------------------------------------------------
+// Device-memory cache.  A B-scan (-n traces) creates and destroys one solver per trace with identical array sizes, and
+// cudaMalloc / cudaFree of the multi-GB field and ID arrays cost more than 100 ms per trace (profiles/e2e_breakdown.py).
+// Freed blocks are kept per device and handed back on an exact size match; everything is released by
+// gpb_release_cached(), when an allocation fails, or when GPB_NO_POOL is set (then every block goes straight to cudaFree).
+namespace {
+struct DevicePool {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_blocks;   // (device, bytes) -> block
+    std::map<void *, std::pair<int, size_t>> live;               // block -> (device, bytes)
+    size_t cached_bytes = 0;
+    std::vector<std::pair<size_t, void *>> pinned_free;           // page-locked host buffers (ID upload bounce buffers)
+
+    bool enabled() const { return !getenv("GPB_NO_POOL"); }
+    void release_all()
+    {
+        std::lock_guard<std::mutex> g(mu);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto &kv : free_blocks) {
+            cudaSetDevice(kv.first.first);
+            cudaFree(kv.second);
+        }
+        free_blocks.clear();
+        cached_bytes = 0;
+        for (auto &kv : pinned_free) cudaFreeHost(kv.second);
+        pinned_free.clear();
+        cudaSetDevice(cur);
+    }
+    cudaError_t alloc_pinned(void **out, size_t bytes)
+    {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t n = 0; n < pinned_free.size(); ++n)
+                if (pinned_free[n].first == bytes) {
+                    *out = pinned_free[n].second;
+                    pinned_free.erase(pinned_free.begin() + n);
+                    pinned_sizes[*out] = bytes;
+                    return cudaSuccess;
+                }
+        }
+        cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> g(mu);
+            pinned_sizes[*out] = bytes;
+        }
+        return e;
+    }
+    void free_pinned(void *p)
+    {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        auto it = pinned_sizes.find(p);
+        const size_t bytes = it == pinned_sizes.end() ? 0 : it->second;
+        if (it != pinned_sizes.end()) pinned_sizes.erase(it);
+        if (enabled() && bytes) pinned_free.push_back({bytes, p});
+        else cudaFreeHost(p);
+    }
+    std::map<void *, size_t> pinned_sizes;
+    cudaError_t alloc(void **out, size_t bytes, int device)
+    {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_blocks.find({device, bytes});
+            if (it != free_blocks.end()) {
+                *out = it->second;
+                free_blocks.erase(it);
+                cached_bytes -= bytes;
+                live[*out] = {device, bytes};
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e == cudaErrorMemoryAllocation) {   // make room and try once more
+            cudaGetLastError();
+            release_all();
+            e = cudaMalloc(out, bytes);
+        }
+        if (e == cudaSuccess) {
+            std::lock_guard<std::mutex> g(mu);
+            live[*out] = {device, bytes};
+        }
+        return e;
+    }
+    void free(void *p)
+    {
+        if (!p) return;
+        std::pair<int, size_t> info;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = live.find(p);
+            if (it == live.end()) { cudaFree(p); return; }
+            info = it->second;
+            live.erase(it);
+            if (enabled()) {
+                free_blocks.insert({info, p});
+                cached_bytes += info.second;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+};
+DevicePool g_pool;
+
+constexpr size_t kBounceBytes = 32u << 20;   // pinned bounce buffer / device stage of the ID upload
+
+// host -> pinned copy split over a few threads (one thread saturates at ~10 GB/s)
+void parallel_copy(char *dst, const char *src, size_t bytes, int nthreads)
+{
+    if (nthreads <= 1 || bytes < (4u << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t part = (bytes / nthreads + 4095) & ~(size_t)4095;
+    for (int t = 0; t < nthreads; ++t) {
+        const size_t o = (size_t)t * part;
+        if (o >= bytes) break;
+        th.emplace_back([=] { memcpy(dst + o, src + o, std::min(part, bytes - o)); });
+    }
+    for (auto &t : th) t.join();
+}
+}  // namespace
 
 // ----------------------------------------------------------------------------------------------
 struct SolverBase {
@@ -122,7 +251,7 @@ struct Solver : SolverBase {
         if (graph) cudaGraphExecDestroy(graph);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        for (void *p : allocs) cudaFree(p);
+        for (void *p : allocs) g_pool.free(p);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -131,7 +260,7 @@ struct Solver : SolverBase {
     {
         void *q = nullptr;
         size_t bytes = std::max<size_t>(n, 1) * sizeof(T_);
-        CK(cudaMalloc(&q, bytes));
+        CK(g_pool.alloc(&q, bytes, device));
         allocs.push_back(q);
         mem += bytes;
         if (zero) CK(cudaMemsetAsync(q, 0, bytes, stream));
@@ -228,7 +357,7 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
         // homogeneous domain: every edge carries the same material
         if (m.uniform_id < 0 || m.uniform_id >= nmat) return fail("uniform_id %d outside the %d materials", m.uniform_id, nmat);
         void *idbase = nullptr;
-        CK(cudaMalloc(&idbase, (size_t)narr * idbytes * 6));   // one allocation, like F
+        CK(g_pool.alloc(&idbase, (size_t)narr * idbytes * 6, device));   // one allocation, like F
         allocs.push_back(idbase);
         mem += (size_t)narr * idbytes * 6;
         for (int c = 0; c < 6; ++c) {
@@ -242,42 +371,61 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
         CK(cudaStreamSynchronize(stream));
         return 0;
     }
-    // stage uint32 planes through a bounded device buffer and narrow on the device
+    // uint32 rows -> pinned bounce buffer (several host threads) -> device stage -> narrowed on the device, double-buffered:
+    // the host copy of chunk q+1 overlaps the PCIe transfer and the narrowing kernel of chunk q (a plain cudaMemcpy from
+    // the pageable NumPy array ran at 11 GB/s: 59 ms of the 300^3 model's 62 ms set-up)
     const long long rows_per_plane = ny + 1;
-    const long long plane_src = rows_per_plane * (nz + 1);
-    const int chunk_planes = (int)std::max<long long>(1, std::min<long long>(nplanes, (256ll << 20) / (plane_src * 4)));
-    uint32_t *stage = nullptr;
+    const long long total_rows = rows_per_plane * nplanes;
+    const size_t row_bytes = (size_t)(nz + 1) * 4;
+    const long long chunk_rows = std::max<long long>(1, (long long)(kBounceBytes / row_bytes));
+    uint32_t *stage[2] = {nullptr, nullptr};
     unsigned *d_max = nullptr;
-    CK(cudaMalloc(&stage, (size_t)chunk_planes * plane_src * 4));
-    CK(cudaMalloc(&d_max, sizeof(unsigned)));
+    void *bounce[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; ++b) {
+        CK(g_pool.alloc((void **)&stage[b], kBounceBytes, device));
+        CK(g_pool.alloc_pinned(&bounce[b], kBounceBytes));
+        CK(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+    }
+    CK(g_pool.alloc((void **)&d_max, sizeof(unsigned), device));
     CK(cudaMemsetAsync(d_max, 0, sizeof(unsigned), stream));
     void *idbase = nullptr;
-    CK(cudaMalloc(&idbase, (size_t)narr * idbytes * 6));   // one allocation, like F
+    CK(g_pool.alloc(&idbase, (size_t)narr * idbytes * 6, device));   // one allocation, like F
     allocs.push_back(idbase);
     mem += (size_t)narr * idbytes * 6;
     CK(cudaMemsetAsync(idbase, 0, (size_t)narr * idbytes * 6, stream));
+    const int nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    long long q = 0;
     for (int c = 0; c < 6; ++c) {
         void *dst = (char *)idbase + (size_t)c * narr * idbytes;
         ID[c] = dst;
-        for (int p0 = 0; p0 < nplanes; p0 += chunk_planes) {
-            const int np = std::min(chunk_planes, nplanes - p0);
-            const uint32_t *src = m.ID + ((size_t)c * nplanes + p0) * plane_src;
-            CK(cudaMemcpyAsync(stage, src, (size_t)np * plane_src * 4, cudaMemcpyHostToDevice, stream));
-            const long long rows = (long long)np * rows_per_plane;
+        for (long long r0 = 0; r0 < total_rows; r0 += chunk_rows, ++q) {
+            const int b = (int)(q & 1);
+            const long long rows = std::min(chunk_rows, total_rows - r0);
+            const size_t bytes = (size_t)rows * row_bytes;
+            const char *src = (const char *)(m.ID + ((size_t)c * total_rows + r0) * (nz + 1));
+            if (q >= 2) CK(cudaEventSynchronize(ev[b]));   // the transfer out of this bounce buffer two chunks ago
+            parallel_copy((char *)bounce[b], src, bytes, nthreads);
+            CK(cudaMemcpyAsync(stage[b], bounce[b], bytes, cudaMemcpyHostToDevice, stream));
+            CK(cudaEventRecord(ev[b], stream));
             const long long n = rows * (nz + 1);
             const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
-            char *d = (char *)dst + (size_t)(p0 + 1) * plane * idbytes;
-            if (idbytes == 1) k_narrow_ids<uint8_t><<<blocks, 256, 0, stream>>>(stage, (uint8_t *)d, rows, nz + 1, pitch, d_max);
-            else if (idbytes == 2) k_narrow_ids<uint16_t><<<blocks, 256, 0, stream>>>(stage, (uint16_t *)d, rows, nz + 1, pitch, d_max);
-            else k_narrow_ids<uint32_t><<<blocks, 256, 0, stream>>>(stage, (uint32_t *)d, rows, nz + 1, pitch, d_max);
+            char *d = (char *)dst + ((size_t)plane + (size_t)r0 * pitch) * idbytes;   // plane 0 of the array is the ghost plane
+            if (idbytes == 1) k_narrow_ids<uint8_t><<<blocks, 256, 0, stream>>>(stage[b], (uint8_t *)d, rows, nz + 1, pitch, d_max);
+            else if (idbytes == 2) k_narrow_ids<uint16_t><<<blocks, 256, 0, stream>>>(stage[b], (uint16_t *)d, rows, nz + 1, pitch, d_max);
+            else k_narrow_ids<uint32_t><<<blocks, 256, 0, stream>>>(stage[b], (uint32_t *)d, rows, nz + 1, pitch, d_max);
             CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(stream));  // stage buffer is reused
         }
+    }
+    CK(cudaStreamSynchronize(stream));
+    for (int b = 0; b < 2; ++b) {
+        cudaEventDestroy(ev[b]);
+        g_pool.free(stage[b]);
+        g_pool.free_pinned(bounce[b]);
     }
     unsigned mx = 0;
     CK(cudaMemcpy(&mx, d_max, sizeof mx, cudaMemcpyDeviceToHost));
-    cudaFree(stage);
-    cudaFree(d_max);
+    g_pool.free(d_max);
     if ((int)mx >= nmat) return fail("ID array references material %u but only %d materials were given", mx, nmat);
     return 0;
 }
@@ -476,6 +624,16 @@ int Solver<R>::build(const gpb_model_t &m)
     if (nmat < 1 || !m.updatecoeffsE || !m.updatecoeffsH) return fail("material tables missing");
     if (m.npml && (order < 1 || order > 2 || form < 0 || form > 1)) return fail("unsupported PML formulation/order %d/%d", form, order);
     if (maxpoles < 0 || (maxpoles > 0 && !m.updatecoeffsdispersive)) return fail("dispersive coefficient table missing");
+    // GPB_TIMING=1: host wall clock of the set-up phases on stderr (profiles/e2e_breakdown.py)
+    const bool timing = getenv("GPB_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto tick = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(stream);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gpb] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0));
@@ -489,7 +647,9 @@ int Solver<R>::build(const gpb_model_t &m)
     // all six components in one allocation: the TMA kernels address a triple (E or H) as one 4-D tensor
     if (dalloc(&F[0], (size_t)narr * 6)) return 1;
     for (int c = 1; c < 6; ++c) F[c] = F[0] + (size_t)c * narr;
+    tick("stream + field arrays");
     if (upload_ids(m)) return 1;
+    tick("material IDs");
     // coefficient rows: [CA, CBx, CBy, CBz | srce] (materials.py:200-201)
     std::vector<Coef4<R>> hE(nmat), hH(nmat);
     std::vector<R> sE(nmat), sH(nmat);
@@ -525,7 +685,9 @@ int Solver<R>::build(const gpb_model_t &m)
     ph_e.maxpoles = maxpoles; ph_e.dcoef = dcoef; ph_e.tstride = narr;
     for (int c = 0; c < 3; ++c) ph_e.T[c] = T[c];
     set_boxes();
+    tick("coefficient tables");
     if (setup_pml(m)) return 1;
+    tick("PML slabs");
     // vectorised path: non-dispersive models (dispersive ones keep the generic scalar kernels)
     // vectorised path (dispersive E updates included; GPB_SCALAR forces the generic scalar kernels)
     use_v4 = v4_ok && !getenv("GPB_SCALAR");
@@ -543,6 +705,7 @@ int Solver<R>::build(const gpb_model_t &m)
     use_tma = use_v4 && nz + 1 >= 32 && ny + 1 >= 8 && !getenv("GPB_NO_TMA") && (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R)) <= 32 * 1024 &&
               ((long long)nplanes * plane >= 2500000ll || getenv("GPB_FORCE_TMA"));
     if (use_tma && setup_tma()) return 1;
+    tick("tensor maps");
     if (use_v4) {
         for (int s = 0; s < ph_e.nslabs; ++s)
             if (ph_e.slab[s].axis == 2) zslabs_e |= 1u << s;
@@ -557,6 +720,7 @@ int Solver<R>::build(const gpb_model_t &m)
     pp.dx = (R)m.dx; pp.dy = (R)m.dy; pp.dz = (R)m.dz;
     if (setup_points(m)) return 1;
     CK(cudaStreamSynchronize(stream));
+    tick("sources / receivers");
     return 0;
 }
 
@@ -595,14 +759,12 @@ int Solver<R>::setup_tma()
     // planes per CTA: short marches (8 planes) measured best on B200 -- many CTAs keep the two resident
     // CTAs per SM out of phase so one computes while the other's pipeline fills; shorter still when the
     // grid would otherwise have fewer than ~6 waves
-    cudaDeviceProp pr;
-    CK(cudaGetDeviceProperties(&pr, device));
-    sm_count = pr.multiProcessorCount;
+    CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));   // (cudaGetDeviceProperties took 3 - 190 ms here)
     tma_persist = !getenv("GPB_TMA_NOPERSIST");
     if (dalloc(&d_sched, 2)) return 1;
     const long long tiles = (long long)((ny + 1 + TY - 1) / TY) * ((pitch + TZ - 1) / TZ);
     tma_xchunk = 8;
-    while (tma_xchunk > 2 && tiles * ((nplanes + tma_xchunk - 1) / tma_xchunk) < 12ll * pr.multiProcessorCount) tma_xchunk /= 2;
+    while (tma_xchunk > 2 && tiles * ((nplanes + tma_xchunk - 1) / tma_xchunk) < 12ll * sm_count) tma_xchunk /= 2;
     if (getenv("GPB_TMA_XCHUNK")) tma_xchunk = std::max(1, atoi(getenv("GPB_TMA_XCHUNK")));
     return 0;
 }
@@ -1029,6 +1191,12 @@ int Solver<R>::halo(int which, void **a, void **b, size_t *bytes)
 
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
+
+int gpb_release_cached(void)
+{
+    g_pool.release_all();
+    return 0;
+}
 
 const char *gpb_last_error(void) { return g_err.c_str(); }
 const char *gpb_version(void) { return "gprmax_b200 0.1 (sm_100a)"; }

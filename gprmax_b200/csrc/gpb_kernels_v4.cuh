@@ -169,7 +169,9 @@ __device__ __forceinline__ R pml_apply(int form, int order, const PmlCo<R> &c, R
     return term;
 }
 
-// One vectorised PML component: F (4 cells) -= / += src[id] * term(dF / d), Phi advanced.
+// One vectorised PML component: F (4 cells) -= / += src[id] * term(dF / d), Phi advanced.  dF / d is formed as dF * (1/d): the
+// IEEE division's slow path is taken for denormal numerators, which is what most of a PML holds (SlabDev::inv_d); the generic
+// scalar kernels (gpb_kernels.cuh) keep the reference's division.
 // sign = +1 / -1.  `m` = lanes (cells) inside the slab.
 template <typename R>
 __device__ __forceinline__ void pml_comp4(int form, int order, const PmlCo<R> &co, const SlabDev<R> &sl, R *phi, unsigned m,
@@ -178,10 +180,10 @@ __device__ __forceinline__ void pml_comp4(int form, int order, const PmlCo<R> &c
     V4<R> p0 = ld4(phi), p1 = p0;
     if (order == 2) p1 = ld4(phi + 2 * sl.ostride);
     V4<R> q0 = p0, q1 = p1;
-    const R tx = pml_apply(form, order, co, dF.x / sl.d, q0.x, q1.x);
-    const R ty = pml_apply(form, order, co, dF.y / sl.d, q0.y, q1.y);
-    const R tz = pml_apply(form, order, co, dF.z / sl.d, q0.z, q1.z);
-    const R tw = pml_apply(form, order, co, dF.w / sl.d, q0.w, q1.w);
+    const R tx = pml_apply(form, order, co, dF.x * sl.inv_d, q0.x, q1.x);
+    const R ty = pml_apply(form, order, co, dF.y * sl.inv_d, q0.y, q1.y);
+    const R tz = pml_apply(form, order, co, dF.z * sl.inv_d, q0.z, q1.z);
+    const R tw = pml_apply(form, order, co, dF.w * sl.inv_d, q0.w, q1.w);
     if (m & 1u) { F.x = F.x + sign * (src[id.a] * tx); p0.x = q0.x; p1.x = q1.x; }
     if (m & 2u) { F.y = F.y + sign * (src[id.b] * ty); p0.y = q0.y; p1.y = q1.y; }
     if (m & 4u) { F.z = F.z + sign * (src[id.c] * tz); p0.z = q0.z; p1.z = q1.z; }
@@ -562,15 +564,15 @@ __device__ __forceinline__ void pml_slab_cell(const PhaseParams<R> &p, int phase
         if (a == 0) { Fa = p.Ey; Ga = p.Hz; sa = -1; ca = 1; Fb = p.Ez; Gb = p.Hy; sb = 1; cb = 2; }
         else if (a == 1) { Fa = p.Ex; Ga = p.Hz; sa = 1; ca = 0; Fb = p.Ez; Gb = p.Hx; sb = -1; cb = 2; }
         else { Fa = p.Ex; Ga = p.Hy; sa = -1; ca = 0; Fb = p.Ey; Gb = p.Hx; sb = 1; cb = 1; }
-        dA = (Ga[off] - Ga[off - st]) / sl.d;
-        dB = (Gb[off] - Gb[off - st]) / sl.d;
+        dA = (Ga[off] - Ga[off - st]) * sl.inv_d;
+        dB = (Gb[off] - Gb[off - st]) * sl.inv_d;
     } else {
         // magnetic: forward differences of E along the slab axis
         if (a == 0) { Fa = p.Hy; Ga = p.Ez; sa = 1; ca = 1; Fb = p.Hz; Gb = p.Ey; sb = -1; cb = 2; }
         else if (a == 1) { Fa = p.Hx; Ga = p.Ez; sa = -1; ca = 0; Fb = p.Hz; Gb = p.Ex; sb = 1; cb = 2; }
         else { Fa = p.Hx; Ga = p.Ey; sa = 1; ca = 0; Fb = p.Hy; Gb = p.Ex; sb = -1; cb = 1; }
-        dA = (Ga[off + st] - Ga[off]) / sl.d;
-        dB = (Gb[off + st] - Gb[off]) / sl.d;
+        dA = (Ga[off + st] - Ga[off]) * sl.inv_d;
+        dB = (Gb[off + st] - Gb[off]) * sl.inv_d;
     }
     const unsigned ma = ld_id<IDT>(p.ID[ca], off), mb = ld_id<IDT>(p.ID[cb], off);
     Fa[off] = Fa[off] + sa * (src[ma] * pml_term(p.form, p.order, sl, depth, dA, phi, sl.ostride));

@@ -184,6 +184,11 @@ int gpb_get_tline(gpb_handle h, int index, void *vtotal, void *itotal, size_t by
 int gpb_get_field(gpb_handle h, int component, void *out, size_t out_bytes);
 int gpb_set_field(gpb_handle h, int component, const void *in, size_t in_bytes);
 
+/* Device memory freed by gpb_destroy is kept per device and reused by the next gpb_create with arrays of the same size (a
+ * B-scan creates one solver per trace; the reference pays a fresh CUDA context and allocations per model run,
+ * model_build_run.py:492-497, 713-714).  gpb_release_cached returns it to the driver; GPB_NO_POOL=1 disables the cache. */
+int gpb_release_cached(void);
+
 const char *gpb_last_error(void);
 const char *gpb_version(void);
 
