@@ -766,6 +766,8 @@ int Solver<R>::setup_tma()
     tma_xchunk = 8;
     while (tma_xchunk > 2 && tiles * ((nplanes + tma_xchunk - 1) / tma_xchunk) < 12ll * sm_count) tma_xchunk /= 2;
     if (getenv("GPB_TMA_XCHUNK")) tma_xchunk = std::max(1, atoi(getenv("GPB_TMA_XCHUNK")));
+    // work items travel as tile | chunk << 20 through the kernels' item ring
+    if (tiles >= (1ll << 20) || (nplanes + tma_xchunk - 1) / tma_xchunk >= (1 << 11)) use_tma = false;
     return 0;
 }
 

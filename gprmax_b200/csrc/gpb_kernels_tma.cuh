@@ -40,18 +40,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Wait for the phase with the given parity.  try_wait carries a suspend-time hint: the waiting thread is parked by the hardware
+// until the phase completes (or the hint expires) instead of spinning -- without it the spin loops of the producer warp and of
+// consumers waiting for data were 16 % of all issued instructions of an issue-bound kernel (profiles/README.md, r1k).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
@@ -169,8 +172,46 @@ __device__ __forceinline__ Ids4 lds_ids4<uint32_t>(const unsigned char *base, in
     return {v.x, v.y, v.z, v.w};
 }
 
-// Order in which the x chunks are handed out: both ends first, the middle last.  The chunks that cross the x slabs take
-// 2-3 times as long as the others; handed out last they formed a final, half-empty wave of slow items.
+// The material IDs of a thread's 4 cells as loaded (packed): the common case "all four equal" is one multiply and one compare on
+// the packed word, and only mixed quads are unpacked.
+template <typename IDT>
+struct IdQ;
+template <>
+struct IdQ<uint8_t> {
+    unsigned v;
+    __device__ __forceinline__ static IdQ load(const unsigned char *base, int elem) { return {*reinterpret_cast<const unsigned *>(base + elem)}; }
+    __device__ __forceinline__ bool uniform() const { return v == (v & 0xffu) * 0x01010101u; }
+    __device__ __forceinline__ unsigned at(int q) const { return (v >> (8 * q)) & 0xffu; }
+};
+template <>
+struct IdQ<uint16_t> {
+    uint2 v;
+    __device__ __forceinline__ static IdQ load(const unsigned char *base, int elem) { return {*reinterpret_cast<const uint2 *>(base + 2 * elem)}; }
+    __device__ __forceinline__ bool uniform() const { return v.x == v.y && (v.x & 0xffffu) == (v.x >> 16); }
+    __device__ __forceinline__ unsigned at(int q) const { return ((q < 2 ? v.x : v.y) >> (16 * (q & 1))) & 0xffffu; }
+};
+template <>
+struct IdQ<uint32_t> {
+    uint4 v;
+    __device__ __forceinline__ static IdQ load(const unsigned char *base, int elem) { return {*reinterpret_cast<const uint4 *>(base + 4 * elem)}; }
+    __device__ __forceinline__ bool uniform() const { return v.x == v.y && v.x == v.z && v.x == v.w; }
+    __device__ __forceinline__ unsigned at(int q) const { return q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w)); }
+};
+template <typename R, typename IDT>
+__device__ __forceinline__ void coef4q(const Coef4<R> *coef, const IdQ<IDT> &id, Coef4<R> &c0, Coef4<R> &c1, Coef4<R> &c2, Coef4<R> &c3)
+{
+    c0 = coef[id.at(0)];
+    if (id.uniform()) {
+        c1 = c2 = c3 = c0;
+    } else {
+        c1 = coef[id.at(1)];
+        c2 = coef[id.at(2)];
+        c3 = coef[id.at(3)];
+    }
+}
+
+// Default order in which the x chunks are handed out (no sorted item list): both ends first, the middle last.  The chunks that
+// cross the x slabs take 2-3 times as long as the others; handed out last they formed a final, half-empty wave of slow items.
 __device__ __forceinline__ int chunk_of(int q, int nchunks)
 {
     return (q & 1) ? nchunks - 1 - (q >> 1) : (q >> 1);
@@ -302,9 +343,12 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         int w;
         if (p.persist) w = atomicAdd(sched, 1);
         else w = p_q == 0 ? (int)(blockIdx.y * gridDim.x + blockIdx.x) : W;
-        p_item = w < W ? w : -1;
+        // x chunks from both ends inwards (chunk_of), tiles in row-major order: neighbouring tiles run at the same time and share
+        // their halo rows / columns in L2.  (Handing the items out by estimated cost, most expensive first, to shorten the tail --
+        // 7 % of the SM cycles are idle at the end -- broke that locality: 57.5 -> 53.8 Gcells/s at 300^3, 75.2 -> 66.8 at 500^3.)
+        p_item = w < W ? ((w % tiles) | (chunk_of(w / tiles, nchunks) << 20)) : -1;
         if (p_item >= 0) {
-            const int tile = p_item % tiles, chunk = chunk_of(p_item / tiles, nchunks);
+            const int tile = p_item & 0xfffff, chunk = p_item >> 20;
             p_k0 = (tile % tiles_k) * TZ;
             p_j0 = (tile / tiles_k) * TY;
             p_l0 = p.p0 + chunk * p.xchunk;
@@ -380,7 +424,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     mbar_wait(full + (g % kStages), (uint32_t)((g / kStages) & 1));
     const int item = ring[q & 3];
     if (item < 0) break;
-    const int tile = item % tiles, chunkid = chunk_of(item / tiles, nchunks);
+    const int tile = item & 0xfffff, chunkid = item >> 20;
     const int k0 = (tile % tiles_k) * TZ, j0 = (tile / tiles_k) * TY;
     const int j = j0 + r, k = k0 + c;
     const int l0 = p.p0 + chunkid * p.xchunk;
@@ -427,17 +471,29 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         const R *phi = sl.phi + ((long long)(ii - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
         for (int q = 0; q < 2 * PORDER; ++q) cp_async_v4<R>(slot + q * kTmaThreads, phi + q * sl.ostride);
     };
-    unsigned act = slabs_on_plane(p, i_of(0));   // slabs on the current plane (CTA-uniform), carried from iteration to iteration
+    // slabs on a plane (CTA-uniform): the same set on every plane of the item unless the item straddles the edge of an x slab
+    unsigned act_all = 0, act_some = 0;
+    {
+        const int ilo = min(i_of(0), i_of(nl - 1)), ihi = max(i_of(0), i_of(nl - 1));
+#pragma unroll
+        for (int s = 0; s < kMaxSlabs; ++s)
+            if (s < p.nslabs) {
+                if (ilo >= p.slab[s].lo[0] && ihi < p.slab[s].hi[0]) act_all |= 1u << s;
+                if (ihi >= p.slab[s].lo[0] && ilo < p.slab[s].hi[0]) act_some |= 1u << s;
+            }
+    }
+    const bool act_same = act_all == act_some;
+    auto act_of = [&](int n) { return act_same ? act_all : slabs_on_plane(p, i_of(n)); };
     if (pf && p.pf_depth == 2) {
-        if (act & smask6) prefetch(spf + tid, act & smask6, i_of(0));
+        if (act_of(0) & smask6) prefetch(spf + tid, act_of(0) & smask6, i_of(0));
         cp_async_commit();
     }
 
     for (int n = 0; n < nl; ++n, ++g) {
-        const unsigned act_next = n + 1 < nl ? slabs_on_plane(p, i_of(n + 1)) : 0u;
+        const unsigned act = act_of(n);
         if (pf) {
             const int np = n + p.pf_depth - 1;   // plane fetched now
-            const unsigned pmn = (p.pf_depth == 2 ? act_next : act) & smask6;
+            const unsigned pmn = (p.pf_depth == 2 ? (n + 1 < nl ? act_of(n + 1) : 0u) : act) & smask6;
             if (pmn) prefetch(spf + (size_t)(np % p.pf_depth) * 2 * PORDER * kTmaThreads + tid, pmn, i_of(np));
             cp_async_commit();
         }
@@ -479,7 +535,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         }
 
         if (any) {
-            const Ids4 id0 = lds_ids4<IDT>(st + L::oId, e), id1 = lds_ids4<IDT>(st + L::oId, L::OS + e), id2 = lds_ids4<IDT>(st + L::oId, 2 * L::OS + e);
+            const IdQ<IDT> id0 = IdQ<IDT>::load(st + L::oId, e), id1 = IdQ<IDT>::load(st + L::oId, L::OS + e), id2 = IdQ<IDT>::load(st + L::oId, 2 * L::OS + e);
             // one straight-line update for every thread; threads with cells outside an update box (domain faces, the
             // two x-slab plane ranges) put the old value back per cell afterwards
             const bool fast = fast_jk && i >= p.fast_i0 && i < p.fast_i1;
@@ -502,7 +558,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                     dC_dy = {c_j.x - c_c.x, c_j.y - c_c.y, c_j.z - c_c.z, c_j.w - c_c.w};     // dEz/dy
                 }
                 Coef4<R> q0, q1, q2, q3;
-                coef4(scoef, id0, q0, q1, q2, q3);
+                coef4q(scoef, id0, q0, q1, q2, q3);
                 V4<R> u;
                 if (PHASE == 1) {
                     u.x = q0.a * f0.x + q0.by * dC_dy.x - q0.bz * dB_dz.x;
@@ -528,7 +584,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                     dC_dx = {qc.x - c_c.x, qc.y - c_c.y, qc.z - c_c.z, qc.w - c_c.w};         // dEz/dx
                 }
                 Coef4<R> q0, q1, q2, q3;
-                coef4(scoef, id1, q0, q1, q2, q3);
+                coef4q(scoef, id1, q0, q1, q2, q3);
                 V4<R> u;
                 if (PHASE == 1) {
                     u.x = q0.a * f1.x + q0.bz * dA_dz.x - q0.bx * dC_dx.x;
@@ -554,7 +610,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                     dB_dx = {qb.x - b_c.x, qb.y - b_c.y, qb.z - b_c.z, qb.w - b_c.w};         // dEy/dx
                 }
                 Coef4<R> q0, q1, q2, q3;
-                coef4(scoef, id2, q0, q1, q2, q3);
+                coef4q(scoef, id2, q0, q1, q2, q3);
                 V4<R> u;
                 if (PHASE == 1) {
                     u.x = q0.a * f2.x + q0.bx * dB_dx.x - q0.by * dA_dy.x;
@@ -654,7 +710,6 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         }
         qb = b_c;
         qc = c_c;
-        act = act_next;
     }
     }   // items
 
