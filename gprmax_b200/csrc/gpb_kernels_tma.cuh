@@ -216,6 +216,23 @@ __device__ __forceinline__ int chunk_of(int q, int nchunks)
 {
     return (q & 1) ? nchunks - 1 - (q >> 1) : (q >> 1);
 }
+// Plane range [l0, l1) of hand-out slot v.  The last `nsplit` chunks of the hand-out order (about one wave of items) are
+// handed out as two halves each, so that the SMs run dry within half an item of each other at the end of the kernel.
+__device__ __forceinline__ void chunk_range(int v, int nchunks, int nsplit, int xc, int p0, int p1, int &l0, int &l1)
+{
+    const int nbig = nchunks - nsplit;
+    int c, lo = 0, len = xc;
+    if (v < nbig) {
+        c = chunk_of(v, nchunks);
+    } else {
+        const int u = v - nbig;
+        c = chunk_of(nbig + (u >> 1), nchunks);
+        lo = (u & 1) * (xc >> 1);
+        len = (u & 1) ? xc - (xc >> 1) : (xc >> 1);
+    }
+    l0 = min(p0 + c * xc + lo, p1);
+    l1 = min(l0 + len, p1);
+}
 
 // slabs whose x range holds plane i (CTA-uniform)
 template <typename R>
@@ -284,7 +301,7 @@ __device__ __forceinline__ void pml_comp(int form, int order, const R *tb, int t
 #endif
 template <typename R, typename IDT, int TY, int TZ, int kStages, int PHASE, int PW, int PV>
 __global__ void __launch_bounds__(TY * TZ / 4 + 32 * PW, (sizeof(R) == 4 ? GPB_TMA_CTAS : 1))
-k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int tiles_k, int tiles, int nchunks, int *sched)
+k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int tiles_k, int tiles, int nchunks, int nsplit, int *sched)
 {
     constexpr int kTmaThreads = TY * TZ / 4;  // consumer threads: every thread owns 4 consecutive z cells of the tile
     static_assert(kTmaThreads % 32 == 0 && kTmaThreads + 32 * PW <= 256, "tile shape");
@@ -306,7 +323,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     unsigned char *stages = smem_raw + 128 + coef_bytes + tab_bytes + pf_bytes;
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int W = tiles * nchunks;
+    const int W = tiles * (nchunks + nsplit);
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -346,13 +363,12 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         // x chunks from both ends inwards (chunk_of), tiles in row-major order: neighbouring tiles run at the same time and share
         // their halo rows / columns in L2.  (Handing the items out by estimated cost, most expensive first, to shorten the tail --
         // 7 % of the SM cycles are idle at the end -- broke that locality: 57.5 -> 53.8 Gcells/s at 300^3, 75.2 -> 66.8 at 500^3.)
-        p_item = w < W ? ((w % tiles) | (chunk_of(w / tiles, nchunks) << 20)) : -1;
+        p_item = w < W ? ((w % tiles) | ((w / tiles) << 20)) : -1;
         if (p_item >= 0) {
             const int tile = p_item & 0xfffff, chunk = p_item >> 20;
             p_k0 = (tile % tiles_k) * TZ;
             p_j0 = (tile / tiles_k) * TY;
-            p_l0 = p.p0 + chunk * p.xchunk;
-            p_l1 = min(p_l0 + p.xchunk, p.p1);
+            chunk_range(chunk, nchunks, nsplit, p.xchunk, p.p0, p.p1, p_l0, p_l1);
         }
         p_n = -1;
     };
@@ -427,8 +443,8 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     const int tile = item & 0xfffff, chunkid = item >> 20;
     const int k0 = (tile % tiles_k) * TZ, j0 = (tile / tiles_k) * TY;
     const int j = j0 + r, k = k0 + c;
-    const int l0 = p.p0 + chunkid * p.xchunk;
-    const int l1 = min(l0 + p.xchunk, p.p1);
+    int l0, l1;
+    chunk_range(chunkid, nchunks, nsplit, p.xchunk, p.p0, p.p1, l0, l1);
     const int nl = l1 - l0;
     V4<R> qb, qc;   // register queue: operand B / C of the x-neighbour plane at my cells
     {

@@ -44,16 +44,18 @@ static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
     const int tiles = tiles_k * tiles_j, nchunks = (p.p1 - p.p0 + p.xchunk - 1) / p.xchunk;
     // persistent: as many CTAs as fit on the GPU at once (2 per SM for fp32), pulling (tile, chunk) items from a.sched
     const int resident = (sizeof(R) == 4 ? GPB_TMA_CTAS : 1) * a.sm_count;
-    const dim3 grid = p.persist ? dim3((unsigned)std::min(tiles * nchunks, resident)) : dim3((unsigned)tiles, (unsigned)nchunks);
+    // persistent launches hand the last ~wave of chunks out in halves (chunk_range)
+    const int nsplit = (p.persist && p.xchunk >= 4 && !getenv("GPB_TMA_NOSPLIT")) ? std::min(nchunks, (resident + tiles - 1) / tiles + 1) : 0;
+    const dim3 grid = p.persist ? dim3((unsigned)std::min(tiles * (nchunks + nsplit), resident)) : dim3((unsigned)tiles, (unsigned)nchunks);
     cudaError_t e;
     if (a.phase == 0) {
         auto kern = k_update_tma<R, IDT, TY, TZ, S, 0, PW, PV>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return tma_fail(err, "cudaFuncSetAttribute", e);
-        kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, a.sched);
+        kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, nsplit, a.sched);
     } else {
         auto kern = k_update_tma<R, IDT, TY, TZ, S, 1, PW, PV>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return tma_fail(err, "cudaFuncSetAttribute", e);
-        kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, a.sched);
+        kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, nsplit, a.sched);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return tma_fail(err, "k_update_tma launch", e);
     return 0;
