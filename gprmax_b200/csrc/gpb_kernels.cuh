@@ -98,59 +98,124 @@ struct PhaseParams {
 };
 
 // ------------------------------------------------------------------------------------------
-// PML recursive-integration term for one component.  Arithmetic follows
-// pml_updates_electric_HORIPML_ext.pyx:69-87 (order 1), :132-157 (order 2) and
-// pml_updates_electric_MRIPML_ext.pyx:68-89, :133-162 (identical in the magnetic files).
-// Returns the bracket that multiplies srce/srcm and advances Phi in place.
+// Explicitly rounded building blocks.  Every kernel family (scalar, register-vectorised, TMA-staged) forms the field
+// update and the PML terms from these, so the placement of the fused multiply-adds is fixed by the source and not by
+// how the compiler happens to contract a*b + c*d in each kernel: a sharded run may put a shard on another kernel
+// family than the single-GPU run it must reproduce bit for bit (an inlined a*f + b*d - c*e came out with two
+// different contractions in k_update_tma and k_update_e4: 1-ulp differences next to the source after 3 iterations).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
+// a*f + b1*d1 + b2*d2 (pass -b for a subtracted term): fma(b2, d2, fma(b1, d1, a*f))
+template <typename R>
+__device__ __forceinline__ R upd3(R a, R f, R b1, R d1, R b2, R d2)
+{
+    return fma_(b2, d2, fma_(b1, d1, mul_(a, f)));
+}
+
+// ------------------------------------------------------------------------------------------
+// PML recursive integration.  Arithmetic follows pml_updates_electric_HORIPML_ext.pyx:69-87 (order 1), :132-157
+// (order 2) and pml_updates_electric_MRIPML_ext.pyx:68-89, :133-162 (identical in the magnetic files).
+// PmlCo = the coefficient set of one depth; pml_apply returns the bracket that multiplies srce/srcm and advances Phi.
 // ------------------------------------------------------------------------------------------
 template <typename R>
-__device__ __forceinline__ R pml_term(int form, int order, const SlabDev<R> &s, int depth, R dF, R *phi0p, long long ostride)
+struct PmlCo {
+    R a, b, c, d, e, f, g, h, r;
+};
+// from the R-table values of one depth (index 0 / 1 = first / second CFS)
+template <typename R>
+__device__ __forceinline__ PmlCo<R> pml_co(int form, int order, R RA0, R RA1, R RB0, R RB1, R RE0, R RE1, R RF0, R RF1)
 {
+    PmlCo<R> c;
     const R one = (R)1;
-    R term;
     if (form == 0) {
         if (order == 1) {
-            R RA01 = __ldg(s.RA + depth) - one;
-            R RB0 = __ldg(s.RB + depth), RE0 = __ldg(s.RE + depth), RF0 = __ldg(s.RF + depth);
-            R phi0 = *phi0p;
-            term = RA01 * dF + RB0 * phi0;
-            *phi0p = RE0 * phi0 - RF0 * dF;
+            c.a = RA0 - one;  // RA01
+            c.b = RB0;
+            c.e = RE0;
+            c.f = RF0;
         } else {
-            R RA0 = __ldg(s.RA + depth), RA1 = __ldg(s.RA + s.t + depth);
-            R RB0 = __ldg(s.RB + depth), RB1 = __ldg(s.RB + s.t + depth);
-            R RE0 = __ldg(s.RE + depth), RE1 = __ldg(s.RE + s.t + depth);
-            R RF0 = __ldg(s.RF + depth), RF1 = __ldg(s.RF + s.t + depth);
-            R RA01 = RA0 * RA1 - one;
-            R *phi1p = phi0p + 2 * ostride;
-            R phi0 = *phi0p, phi1 = *phi1p;
-            term = RA01 * dF + RA1 * RB0 * phi0 + RB1 * phi1;
-            *phi1p = RE1 * phi1 - RF1 * (RA0 * dF + RB0 * phi0);
-            *phi0p = RE0 * phi0 - RF0 * dF;
+            c.a = fma_(RA0, RA1, -one);  // RA01
+            c.b = RB0;
+            c.e = RE0;
+            c.f = RF0;
+            c.c = RA0;
+            c.d = RA1;
+            c.g = RB1;
+            c.h = RE1;
+            c.r = RF1;
         }
     } else {
         if (order == 1) {
-            R RB0 = __ldg(s.RB + depth), RE0 = __ldg(s.RE + depth), RF0 = __ldg(s.RF + depth);
-            R IRA = one / __ldg(s.RA + depth);
-            R IRA1 = IRA - one;
-            R RC0 = IRA * RB0 * RF0;
-            R phi0 = *phi0p;
-            term = IRA1 * dF - IRA * phi0;
-            *phi0p = RE0 * phi0 + RC0 * dF - RC0 * phi0;
+            const R IRA = one / RA0;
+            c.a = IRA;
+            c.b = IRA - one;
+            c.c = mul_(mul_(IRA, RB0), RF0);  // RC0
+            c.e = RE0;
         } else {
-            R RB0 = __ldg(s.RB + depth), RB1 = __ldg(s.RB + s.t + depth);
-            R RE0 = __ldg(s.RE + depth), RE1 = __ldg(s.RE + s.t + depth);
-            R RF0 = __ldg(s.RF + depth), RF1 = __ldg(s.RF + s.t + depth);
-            R IRA = one / (__ldg(s.RA + depth) + __ldg(s.RA + s.t + depth));
-            R IRA1 = IRA - one;
-            R RC0 = IRA * RF0, RC1 = IRA * RF1;
-            R *phi1p = phi0p + 2 * ostride;
-            R phi0 = *phi0p, phi1 = *phi1p;
-            R psi = RB0 * phi0 + RB1 * phi1;
-            term = IRA1 * dF - IRA * psi;
-            *phi1p = RE1 * phi1 + RC1 * (dF - psi);
-            *phi0p = RE0 * phi0 + RC0 * (dF - psi);
+            const R IRA = one / (RA0 + RA1);
+            c.a = IRA;
+            c.b = IRA - one;
+            c.c = mul_(IRA, RF0);
+            c.d = mul_(IRA, RF1);
+            c.e = RE0;
+            c.h = RE1;
+            c.f = RB0;
+            c.g = RB1;
         }
     }
+    return c;
+}
+template <typename R>
+__device__ __forceinline__ PmlCo<R> pml_load(int form, int order, const SlabDev<R> &s, int depth)
+{
+    const R RA0 = __ldg(s.RA + depth), RB0 = __ldg(s.RB + depth), RE0 = __ldg(s.RE + depth), RF0 = __ldg(s.RF + depth);
+    R RA1 = RA0, RB1 = RB0, RE1 = RE0, RF1 = RF0;
+    if (order == 2) {
+        RA1 = __ldg(s.RA + s.t + depth); RB1 = __ldg(s.RB + s.t + depth); RE1 = __ldg(s.RE + s.t + depth); RF1 = __ldg(s.RF + s.t + depth);
+    }
+    return pml_co(form, order, RA0, RA1, RB0, RB1, RE0, RE1, RF0, RF1);
+}
+// phi0 / phi1 are updated in registers
+template <typename R>
+__device__ __forceinline__ R pml_apply(int form, int order, const PmlCo<R> &c, R dF, R &phi0, R &phi1)
+{
+    R term;
+    if (form == 0) {
+        if (order == 1) {
+            term = fma_(c.a, dF, mul_(c.b, phi0));                       // RA01 dF + RB0 Phi0
+            phi0 = fma_(c.e, phi0, -mul_(c.f, dF));                      // RE0 Phi0 - RF0 dF
+        } else {
+            term = fma_(c.g, phi1, fma_(c.a, dF, mul_(mul_(c.d, c.b), phi0)));   // RA01 dF + RA1 RB0 Phi0 + RB1 Phi1
+            phi1 = fma_(c.h, phi1, -mul_(c.r, fma_(c.c, dF, mul_(c.b, phi0))));  // RE1 Phi1 - RF1 (RA0 dF + RB0 Phi0)
+            phi0 = fma_(c.e, phi0, -mul_(c.f, dF));
+        }
+    } else {
+        if (order == 1) {
+            term = fma_(c.b, dF, -mul_(c.a, phi0));                      // (IRA - 1) dF - IRA Phi0
+            phi0 = fma_(-c.c, phi0, fma_(c.c, dF, mul_(c.e, phi0)));     // RE0 Phi0 + RC0 dF - RC0 Phi0
+        } else {
+            const R psi = fma_(c.f, phi0, mul_(c.g, phi1));              // RB0 Phi0 + RB1 Phi1
+            term = fma_(c.b, dF, -mul_(c.a, psi));
+            const R dd = dF - psi;
+            phi1 = fma_(c.h, phi1, mul_(c.d, dd));
+            phi0 = fma_(c.e, phi0, mul_(c.c, dd));
+        }
+    }
+    return term;
+}
+// one cell, Phi in memory (scalar kernels, k_pml_slabs)
+template <typename R>
+__device__ __forceinline__ R pml_term(int form, int order, const SlabDev<R> &s, int depth, R dF, R *phi0p, long long ostride)
+{
+    const PmlCo<R> co = pml_load(form, order, s, depth);
+    R *phi1p = phi0p + 2 * ostride;
+    R phi0 = *phi0p, phi1 = order == 2 ? *phi1p : phi0;
+    const R term = pml_apply(form, order, co, dF, phi0, phi1);
+    *phi0p = phi0;
+    if (order == 2) *phi1p = phi1;
     return term;
 }
 
@@ -223,19 +288,19 @@ __global__ void __launch_bounds__(kThreads) k_update_h(const PhaseParams<R> p)
         if (in_box<R>(p.box[0].lo, p.box[0].hi, i, j, k)) {
             mx = ld_id<IDT>(p.ID[0], off);
             const Coef4<R> c = coef[mx];
-            hx = c.a * hx - c.by * dEz_dy + c.bz * dEy_dz;
+            hx = upd3(c.a, hx, -c.by, dEz_dy, c.bz, dEy_dz);
             wx = true;
         }
         if (in_box<R>(p.box[1].lo, p.box[1].hi, i, j, k)) {
             my = ld_id<IDT>(p.ID[1], off);
             const Coef4<R> c = coef[my];
-            hy = c.a * hy - c.bz * dEx_dz + c.bx * dEz_dx;
+            hy = upd3(c.a, hy, -c.bz, dEx_dz, c.bx, dEz_dx);
             wy = true;
         }
         if (in_box<R>(p.box[2].lo, p.box[2].hi, i, j, k)) {
             mz = ld_id<IDT>(p.ID[2], off);
             const Coef4<R> c = coef[mz];
-            hz = c.a * hz - c.bx * dEy_dx + c.by * dEx_dy;
+            hz = upd3(c.a, hz, -c.bx, dEy_dx, c.by, dEx_dy);
             wz = true;
         }
         for (int s = 0; s < p.nslabs; ++s) {
@@ -251,20 +316,20 @@ __global__ void __launch_bounds__(kThreads) k_update_h(const PhaseParams<R> p)
             if (a == 0) {
                 if (!wy) my = ld_id<IDT>(p.ID[1], off);
                 if (!wz) mz = ld_id<IDT>(p.ID[2], off);
-                hy = hy + srcm[my] * pml_term(p.form, p.order, sl, depth, dEz_dx / sl.d, phi, sl.ostride);
-                hz = hz - srcm[mz] * pml_term(p.form, p.order, sl, depth, dEy_dx / sl.d, phi + sl.ostride, sl.ostride);
+                hy = fma_((R)1, mul_(srcm[my], pml_term(p.form, p.order, sl, depth, dEz_dx / sl.d, phi, sl.ostride)), hy);
+                hz = fma_((R)-1, mul_(srcm[mz], pml_term(p.form, p.order, sl, depth, dEy_dx / sl.d, phi + sl.ostride, sl.ostride)), hz);
                 wy = wz = true;
             } else if (a == 1) {
                 if (!wx) mx = ld_id<IDT>(p.ID[0], off);
                 if (!wz) mz = ld_id<IDT>(p.ID[2], off);
-                hx = hx - srcm[mx] * pml_term(p.form, p.order, sl, depth, dEz_dy / sl.d, phi, sl.ostride);
-                hz = hz + srcm[mz] * pml_term(p.form, p.order, sl, depth, dEx_dy / sl.d, phi + sl.ostride, sl.ostride);
+                hx = fma_((R)-1, mul_(srcm[mx], pml_term(p.form, p.order, sl, depth, dEz_dy / sl.d, phi, sl.ostride)), hx);
+                hz = fma_((R)1, mul_(srcm[mz], pml_term(p.form, p.order, sl, depth, dEx_dy / sl.d, phi + sl.ostride, sl.ostride)), hz);
                 wx = wz = true;
             } else {
                 if (!wx) mx = ld_id<IDT>(p.ID[0], off);
                 if (!wy) my = ld_id<IDT>(p.ID[1], off);
-                hx = hx + srcm[mx] * pml_term(p.form, p.order, sl, depth, dEy_dz / sl.d, phi, sl.ostride);
-                hy = hy - srcm[my] * pml_term(p.form, p.order, sl, depth, dEx_dz / sl.d, phi + sl.ostride, sl.ostride);
+                hx = fma_((R)1, mul_(srcm[mx], pml_term(p.form, p.order, sl, depth, dEy_dz / sl.d, phi, sl.ostride)), hx);
+                hy = fma_((R)-1, mul_(srcm[my], pml_term(p.form, p.order, sl, depth, dEx_dz / sl.d, phi + sl.ostride, sl.ostride)), hy);
                 wx = wy = true;
             }
         }
@@ -347,9 +412,9 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
             const Coef4<R> c = coef[mx];
             if (DISP) {
                 const R phi = dispersive_AB(p, 0, mx, off, ex);
-                ex = c.a * ex + c.by * dHz_dy - c.bz * dHy_dz - srce[mx] * phi;
+                ex = upd3(c.a, ex, c.by, dHz_dy, -c.bz, dHy_dz) - srce[mx] * phi;
             } else {
-                ex = c.a * ex + c.by * dHz_dy - c.bz * dHy_dz;
+                ex = upd3(c.a, ex, c.by, dHz_dy, -c.bz, dHy_dz);
             }
             wx = true;
         }
@@ -358,9 +423,9 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
             const Coef4<R> c = coef[my];
             if (DISP) {
                 const R phi = dispersive_AB(p, 1, my, off, ey);
-                ey = c.a * ey + c.bz * dHx_dz - c.bx * dHz_dx - srce[my] * phi;
+                ey = upd3(c.a, ey, c.bz, dHx_dz, -c.bx, dHz_dx) - srce[my] * phi;
             } else {
-                ey = c.a * ey + c.bz * dHx_dz - c.bx * dHz_dx;
+                ey = upd3(c.a, ey, c.bz, dHx_dz, -c.bx, dHz_dx);
             }
             wy = true;
         }
@@ -369,9 +434,9 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
             const Coef4<R> c = coef[mz];
             if (DISP) {
                 const R phi = dispersive_AB(p, 2, mz, off, ez);
-                ez = c.a * ez + c.bx * dHy_dx - c.by * dHx_dy - srce[mz] * phi;
+                ez = upd3(c.a, ez, c.bx, dHy_dx, -c.by, dHx_dy) - srce[mz] * phi;
             } else {
-                ez = c.a * ez + c.bx * dHy_dx - c.by * dHx_dy;
+                ez = upd3(c.a, ez, c.bx, dHy_dx, -c.by, dHx_dy);
             }
             wz = true;
         }
@@ -388,20 +453,20 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
             if (a == 0) {
                 if (!wy) my = ld_id<IDT>(p.ID[1], off);
                 if (!wz) mz = ld_id<IDT>(p.ID[2], off);
-                ey = ey - srce[my] * pml_term(p.form, p.order, sl, depth, dHz_dx / sl.d, phi, sl.ostride);
-                ez = ez + srce[mz] * pml_term(p.form, p.order, sl, depth, dHy_dx / sl.d, phi + sl.ostride, sl.ostride);
+                ey = fma_((R)-1, mul_(srce[my], pml_term(p.form, p.order, sl, depth, dHz_dx / sl.d, phi, sl.ostride)), ey);
+                ez = fma_((R)1, mul_(srce[mz], pml_term(p.form, p.order, sl, depth, dHy_dx / sl.d, phi + sl.ostride, sl.ostride)), ez);
                 wy = wz = true;
             } else if (a == 1) {
                 if (!wx) mx = ld_id<IDT>(p.ID[0], off);
                 if (!wz) mz = ld_id<IDT>(p.ID[2], off);
-                ex = ex + srce[mx] * pml_term(p.form, p.order, sl, depth, dHz_dy / sl.d, phi, sl.ostride);
-                ez = ez - srce[mz] * pml_term(p.form, p.order, sl, depth, dHx_dy / sl.d, phi + sl.ostride, sl.ostride);
+                ex = fma_((R)1, mul_(srce[mx], pml_term(p.form, p.order, sl, depth, dHz_dy / sl.d, phi, sl.ostride)), ex);
+                ez = fma_((R)-1, mul_(srce[mz], pml_term(p.form, p.order, sl, depth, dHx_dy / sl.d, phi + sl.ostride, sl.ostride)), ez);
                 wx = wz = true;
             } else {
                 if (!wx) mx = ld_id<IDT>(p.ID[0], off);
                 if (!wy) my = ld_id<IDT>(p.ID[1], off);
-                ex = ex - srce[mx] * pml_term(p.form, p.order, sl, depth, dHy_dz / sl.d, phi, sl.ostride);
-                ey = ey + srce[my] * pml_term(p.form, p.order, sl, depth, dHx_dz / sl.d, phi + sl.ostride, sl.ostride);
+                ex = fma_((R)-1, mul_(srce[mx], pml_term(p.form, p.order, sl, depth, dHy_dz / sl.d, phi, sl.ostride)), ex);
+                ey = fma_((R)1, mul_(srce[my], pml_term(p.form, p.order, sl, depth, dHx_dz / sl.d, phi + sl.ostride, sl.ostride)), ey);
                 wx = wy = true;
             }
         }

@@ -87,51 +87,12 @@ __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_g
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // PML coefficient set of one depth from the shared-memory copy of a slab's R tables, tb = [RA|RB|RE|RF][order][tmax]
-// (same expressions as pml_load in gpb_kernels_v4.cuh)
 template <typename R>
 __device__ __forceinline__ PmlCo<R> pml_load_s(int form, int order, const R *tb, int tmax, int depth)
 {
-    PmlCo<R> c;
-    const R one = (R)1;
     const R *RA = tb + depth, *RB = tb + order * tmax + depth, *RE = tb + 2 * order * tmax + depth, *RF = tb + 3 * order * tmax + depth;
-    if (form == 0) {
-        if (order == 1) {
-            c.a = RA[0] - one;  // RA01
-            c.b = RB[0];
-            c.e = RE[0];
-            c.f = RF[0];
-        } else {
-            const R RA0 = RA[0], RA1 = RA[tmax];
-            c.a = RA0 * RA1 - one;  // RA01
-            c.b = RB[0];
-            c.e = RE[0];
-            c.f = RF[0];
-            c.c = RA0;
-            c.d = RA1;
-            c.g = RB[tmax];
-            c.h = RE[tmax];
-            c.r = RF[tmax];
-        }
-    } else {
-        if (order == 1) {
-            const R IRA = one / RA[0];
-            c.a = IRA;
-            c.b = IRA - one;
-            c.c = IRA * RB[0] * RF[0];  // RC0
-            c.e = RE[0];
-        } else {
-            const R IRA = one / (RA[0] + RA[tmax]);
-            c.a = IRA;
-            c.b = IRA - one;
-            c.c = IRA * RF[0];
-            c.d = IRA * RF[tmax];
-            c.e = RE[0];
-            c.h = RE[tmax];
-            c.f = RB[0];
-            c.g = RB[tmax];
-        }
-    }
-    return c;
+    const int o1 = order == 2 ? tmax : 0;
+    return pml_co(form, order, RA[0], RA[o1], RB[0], RB[o1], RE[0], RE[o1], RF[0], RF[o1]);
 }
 
 // shared-memory layout of one stage (byte offsets), every sub-buffer 128-byte aligned
@@ -263,15 +224,15 @@ __device__ __forceinline__ void pml_comp(int form, int order, const R *tb, int t
     }
     if (DSTEP == 0) {
         const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0);
-        if (m & 1u) F.x = F.x + sign * (src[id.a] * pml_apply(form, order, co, dF.x * inv_d, P0.x, P1.x));
-        if (m & 2u) F.y = F.y + sign * (src[id.b] * pml_apply(form, order, co, dF.y * inv_d, P0.y, P1.y));
-        if (m & 4u) F.z = F.z + sign * (src[id.c] * pml_apply(form, order, co, dF.z * inv_d, P0.z, P1.z));
-        if (m & 8u) F.w = F.w + sign * (src[id.d] * pml_apply(form, order, co, dF.w * inv_d, P0.w, P1.w));
+        if (m & 1u) F.x = fma_(sign, mul_(src[id.a], pml_apply(form, order, co, mul_(dF.x, inv_d), P0.x, P1.x)), F.x);
+        if (m & 2u) F.y = fma_(sign, mul_(src[id.b], pml_apply(form, order, co, mul_(dF.y, inv_d), P0.y, P1.y)), F.y);
+        if (m & 4u) F.z = fma_(sign, mul_(src[id.c], pml_apply(form, order, co, mul_(dF.z, inv_d), P0.z, P1.z)), F.z);
+        if (m & 8u) F.w = fma_(sign, mul_(src[id.d], pml_apply(form, order, co, mul_(dF.w, inv_d), P0.w, P1.w)), F.w);
     } else {
-        if (m & 1u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0); F.x = F.x + sign * (src[id.a] * pml_apply(form, order, co, dF.x * inv_d, P0.x, P1.x)); }
-        if (m & 2u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0 + dsign); F.y = F.y + sign * (src[id.b] * pml_apply(form, order, co, dF.y * inv_d, P0.y, P1.y)); }
-        if (m & 4u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0 + 2 * dsign); F.z = F.z + sign * (src[id.c] * pml_apply(form, order, co, dF.z * inv_d, P0.z, P1.z)); }
-        if (m & 8u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0 + 3 * dsign); F.w = F.w + sign * (src[id.d] * pml_apply(form, order, co, dF.w * inv_d, P0.w, P1.w)); }
+        if (m & 1u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0); F.x = fma_(sign, mul_(src[id.a], pml_apply(form, order, co, mul_(dF.x, inv_d), P0.x, P1.x)), F.x); }
+        if (m & 2u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0 + dsign); F.y = fma_(sign, mul_(src[id.b], pml_apply(form, order, co, mul_(dF.y, inv_d), P0.y, P1.y)), F.y); }
+        if (m & 4u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0 + 2 * dsign); F.z = fma_(sign, mul_(src[id.c], pml_apply(form, order, co, mul_(dF.z, inv_d), P0.z, P1.z)), F.z); }
+        if (m & 8u) { const PmlCo<R> co = pml_load_s(form, order, tb, tmax, depth0 + 3 * dsign); F.w = fma_(sign, mul_(src[id.d], pml_apply(form, order, co, mul_(dF.w, inv_d), P0.w, P1.w)), F.w); }
     }
     st4(phi, P0);
     if (order == 2) st4(phi + ostride2, P1);
@@ -544,14 +505,16 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         // A warp without slab cells on this plane has now taken what it needs from the stage and hands it back to the producer.
         // A warp with slab cells keeps it until its PML corrections are done: they re-read their operands and IDs from the stage
         // instead of keeping them in registers (which spilled the straight-line update of every thread).
+        // (the IDs are read here, before the release: the stage is refilled as soon as the last warp has arrived)
+        const IdQ<IDT> id0 = IdQ<IDT>::load(st + L::oId, e), id1 = IdQ<IDT>::load(st + L::oId, L::OS + e), id2 = IdQ<IDT>::load(st + L::oId, 2 * L::OS + e);
         const bool wpml = __any_sync(0xffffffffu, pm != 0u);
         if (!wpml) {
+            __syncwarp();
             if (lane == 0) mbar_arrive(empty + (g % kStages));
             if (!PW && tid == 0 && !p_done) produce();
         }
 
         if (any) {
-            const IdQ<IDT> id0 = IdQ<IDT>::load(st + L::oId, e), id1 = IdQ<IDT>::load(st + L::oId, L::OS + e), id2 = IdQ<IDT>::load(st + L::oId, 2 * L::OS + e);
             // one straight-line update for every thread; threads with cells outside an update box (domain faces, the
             // two x-slab plane ranges) put the old value back per cell afterwards
             const bool fast = fast_jk && i >= p.fast_i0 && i < p.fast_i1;
@@ -577,15 +540,15 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                 coef4q(scoef, id0, q0, q1, q2, q3);
                 V4<R> u;
                 if (PHASE == 1) {
-                    u.x = q0.a * f0.x + q0.by * dC_dy.x - q0.bz * dB_dz.x;
-                    u.y = q1.a * f0.y + q1.by * dC_dy.y - q1.bz * dB_dz.y;
-                    u.z = q2.a * f0.z + q2.by * dC_dy.z - q2.bz * dB_dz.z;
-                    u.w = q3.a * f0.w + q3.by * dC_dy.w - q3.bz * dB_dz.w;
+                    u.x = upd3(q0.a, f0.x, q0.by, dC_dy.x, -q0.bz, dB_dz.x);
+                    u.y = upd3(q1.a, f0.y, q1.by, dC_dy.y, -q1.bz, dB_dz.y);
+                    u.z = upd3(q2.a, f0.z, q2.by, dC_dy.z, -q2.bz, dB_dz.z);
+                    u.w = upd3(q3.a, f0.w, q3.by, dC_dy.w, -q3.bz, dB_dz.w);
                 } else {
-                    u.x = q0.a * f0.x - q0.by * dC_dy.x + q0.bz * dB_dz.x;
-                    u.y = q1.a * f0.y - q1.by * dC_dy.y + q1.bz * dB_dz.y;
-                    u.z = q2.a * f0.z - q2.by * dC_dy.z + q2.bz * dB_dz.z;
-                    u.w = q3.a * f0.w - q3.by * dC_dy.w + q3.bz * dB_dz.w;
+                    u.x = upd3(q0.a, f0.x, -q0.by, dC_dy.x, q0.bz, dB_dz.x);
+                    u.y = upd3(q1.a, f0.y, -q1.by, dC_dy.y, q1.bz, dB_dz.y);
+                    u.z = upd3(q2.a, f0.z, -q2.by, dC_dy.z, q2.bz, dB_dz.z);
+                    u.w = upd3(q3.a, f0.w, -q3.by, dC_dy.w, q3.bz, dB_dz.w);
                 }
                 if (!fast) { u.x = sel(m0, 0, u.x, f0.x); u.y = sel(m0, 1, u.y, f0.y); u.z = sel(m0, 2, u.z, f0.z); u.w = sel(m0, 3, u.w, f0.w); }
                 f0 = u;
@@ -603,15 +566,15 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                 coef4q(scoef, id1, q0, q1, q2, q3);
                 V4<R> u;
                 if (PHASE == 1) {
-                    u.x = q0.a * f1.x + q0.bz * dA_dz.x - q0.bx * dC_dx.x;
-                    u.y = q1.a * f1.y + q1.bz * dA_dz.y - q1.bx * dC_dx.y;
-                    u.z = q2.a * f1.z + q2.bz * dA_dz.z - q2.bx * dC_dx.z;
-                    u.w = q3.a * f1.w + q3.bz * dA_dz.w - q3.bx * dC_dx.w;
+                    u.x = upd3(q0.a, f1.x, q0.bz, dA_dz.x, -q0.bx, dC_dx.x);
+                    u.y = upd3(q1.a, f1.y, q1.bz, dA_dz.y, -q1.bx, dC_dx.y);
+                    u.z = upd3(q2.a, f1.z, q2.bz, dA_dz.z, -q2.bx, dC_dx.z);
+                    u.w = upd3(q3.a, f1.w, q3.bz, dA_dz.w, -q3.bx, dC_dx.w);
                 } else {
-                    u.x = q0.a * f1.x - q0.bz * dA_dz.x + q0.bx * dC_dx.x;
-                    u.y = q1.a * f1.y - q1.bz * dA_dz.y + q1.bx * dC_dx.y;
-                    u.z = q2.a * f1.z - q2.bz * dA_dz.z + q2.bx * dC_dx.z;
-                    u.w = q3.a * f1.w - q3.bz * dA_dz.w + q3.bx * dC_dx.w;
+                    u.x = upd3(q0.a, f1.x, -q0.bz, dA_dz.x, q0.bx, dC_dx.x);
+                    u.y = upd3(q1.a, f1.y, -q1.bz, dA_dz.y, q1.bx, dC_dx.y);
+                    u.z = upd3(q2.a, f1.z, -q2.bz, dA_dz.z, q2.bx, dC_dx.z);
+                    u.w = upd3(q3.a, f1.w, -q3.bz, dA_dz.w, q3.bx, dC_dx.w);
                 }
                 if (!fast) { u.x = sel(m1, 0, u.x, f1.x); u.y = sel(m1, 1, u.y, f1.y); u.z = sel(m1, 2, u.z, f1.z); u.w = sel(m1, 3, u.w, f1.w); }
                 f1 = u;
@@ -629,15 +592,15 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                 coef4q(scoef, id2, q0, q1, q2, q3);
                 V4<R> u;
                 if (PHASE == 1) {
-                    u.x = q0.a * f2.x + q0.bx * dB_dx.x - q0.by * dA_dy.x;
-                    u.y = q1.a * f2.y + q1.bx * dB_dx.y - q1.by * dA_dy.y;
-                    u.z = q2.a * f2.z + q2.bx * dB_dx.z - q2.by * dA_dy.z;
-                    u.w = q3.a * f2.w + q3.bx * dB_dx.w - q3.by * dA_dy.w;
+                    u.x = upd3(q0.a, f2.x, q0.bx, dB_dx.x, -q0.by, dA_dy.x);
+                    u.y = upd3(q1.a, f2.y, q1.bx, dB_dx.y, -q1.by, dA_dy.y);
+                    u.z = upd3(q2.a, f2.z, q2.bx, dB_dx.z, -q2.by, dA_dy.z);
+                    u.w = upd3(q3.a, f2.w, q3.bx, dB_dx.w, -q3.by, dA_dy.w);
                 } else {
-                    u.x = q0.a * f2.x - q0.bx * dB_dx.x + q0.by * dA_dy.x;
-                    u.y = q1.a * f2.y - q1.bx * dB_dx.y + q1.by * dA_dy.y;
-                    u.z = q2.a * f2.z - q2.bx * dB_dx.z + q2.by * dA_dy.z;
-                    u.w = q3.a * f2.w - q3.bx * dB_dx.w + q3.by * dA_dy.w;
+                    u.x = upd3(q0.a, f2.x, -q0.bx, dB_dx.x, q0.by, dA_dy.x);
+                    u.y = upd3(q1.a, f2.y, -q1.bx, dB_dx.y, q1.by, dA_dy.y);
+                    u.z = upd3(q2.a, f2.z, -q2.bx, dB_dx.z, q2.by, dA_dy.z);
+                    u.w = upd3(q3.a, f2.w, -q3.bx, dB_dx.w, q3.by, dA_dy.w);
                 }
                 if (!fast) { u.x = sel(m2, 0, u.x, f2.x); u.y = sel(m2, 1, u.y, f2.y); u.z = sel(m2, 2, u.z, f2.z); u.w = sel(m2, 3, u.w, f2.w); }
                 f2 = u;

@@ -92,83 +92,6 @@ __device__ __forceinline__ R sel(unsigned mask, int q, R a, R b)
     return (mask >> q) & 1u ? a : b;
 }
 
-// coefficient set of one PML depth, read once per thread (cf. pml_term in gpb_kernels.cuh)
-template <typename R>
-struct PmlCo {
-    R a, b, c, d, e, f, g, h, r;
-};
-template <typename R>
-__device__ __forceinline__ PmlCo<R> pml_load(int form, int order, const SlabDev<R> &s, int depth)
-{
-    PmlCo<R> c;
-    const R one = (R)1;
-    if (form == 0) {
-        if (order == 1) {
-            c.a = __ldg(s.RA + depth) - one;  // RA01
-            c.b = __ldg(s.RB + depth);
-            c.e = __ldg(s.RE + depth);
-            c.f = __ldg(s.RF + depth);
-        } else {
-            const R RA0 = __ldg(s.RA + depth), RA1 = __ldg(s.RA + s.t + depth);
-            c.a = RA0 * RA1 - one;  // RA01
-            c.b = __ldg(s.RB + depth);
-            c.e = __ldg(s.RE + depth);
-            c.f = __ldg(s.RF + depth);
-            c.c = RA0;
-            c.d = RA1;
-            c.g = __ldg(s.RB + s.t + depth);
-            c.h = __ldg(s.RE + s.t + depth);
-            c.r = __ldg(s.RF + s.t + depth);
-        }
-    } else {
-        if (order == 1) {
-            const R IRA = one / __ldg(s.RA + depth);
-            c.a = IRA;
-            c.b = IRA - one;
-            c.c = IRA * __ldg(s.RB + depth) * __ldg(s.RF + depth);  // RC0
-            c.e = __ldg(s.RE + depth);
-        } else {
-            const R IRA = one / (__ldg(s.RA + depth) + __ldg(s.RA + s.t + depth));
-            c.a = IRA;
-            c.b = IRA - one;
-            c.c = IRA * __ldg(s.RF + depth);
-            c.d = IRA * __ldg(s.RF + s.t + depth);
-            c.e = __ldg(s.RE + depth);
-            c.h = __ldg(s.RE + s.t + depth);
-            c.f = __ldg(s.RB + depth);
-            c.g = __ldg(s.RB + s.t + depth);
-        }
-    }
-    return c;
-}
-// same expressions as pml_term(); phi0/phi1 are updated in registers
-template <typename R>
-__device__ __forceinline__ R pml_apply(int form, int order, const PmlCo<R> &c, R dF, R &phi0, R &phi1)
-{
-    R term;
-    if (form == 0) {
-        if (order == 1) {
-            term = c.a * dF + c.b * phi0;
-            phi0 = c.e * phi0 - c.f * dF;
-        } else {
-            term = c.a * dF + c.d * c.b * phi0 + c.g * phi1;
-            phi1 = c.h * phi1 - c.r * (c.c * dF + c.b * phi0);
-            phi0 = c.e * phi0 - c.f * dF;
-        }
-    } else {
-        if (order == 1) {
-            term = c.b * dF - c.a * phi0;
-            phi0 = c.e * phi0 + c.c * dF - c.c * phi0;
-        } else {
-            const R psi = c.f * phi0 + c.g * phi1;
-            term = c.b * dF - c.a * psi;
-            phi1 = c.h * phi1 + c.d * (dF - psi);
-            phi0 = c.e * phi0 + c.c * (dF - psi);
-        }
-    }
-    return term;
-}
-
 // One vectorised PML component: F (4 cells) -= / += src[id] * term(dF / d), Phi advanced.  dF / d is formed as dF * (1/d): the
 // IEEE division's slow path is taken for denormal numerators, which is what most of a PML holds (SlabDev::inv_d); the generic
 // scalar kernels (gpb_kernels.cuh) keep the reference's division.
@@ -180,14 +103,14 @@ __device__ __forceinline__ void pml_comp4(int form, int order, const PmlCo<R> &c
     V4<R> p0 = ld4(phi), p1 = p0;
     if (order == 2) p1 = ld4(phi + 2 * sl.ostride);
     V4<R> q0 = p0, q1 = p1;
-    const R tx = pml_apply(form, order, co, dF.x * sl.inv_d, q0.x, q1.x);
-    const R ty = pml_apply(form, order, co, dF.y * sl.inv_d, q0.y, q1.y);
-    const R tz = pml_apply(form, order, co, dF.z * sl.inv_d, q0.z, q1.z);
-    const R tw = pml_apply(form, order, co, dF.w * sl.inv_d, q0.w, q1.w);
-    if (m & 1u) { F.x = F.x + sign * (src[id.a] * tx); p0.x = q0.x; p1.x = q1.x; }
-    if (m & 2u) { F.y = F.y + sign * (src[id.b] * ty); p0.y = q0.y; p1.y = q1.y; }
-    if (m & 4u) { F.z = F.z + sign * (src[id.c] * tz); p0.z = q0.z; p1.z = q1.z; }
-    if (m & 8u) { F.w = F.w + sign * (src[id.d] * tw); p0.w = q0.w; p1.w = q1.w; }
+    const R tx = pml_apply(form, order, co, mul_(dF.x, sl.inv_d), q0.x, q1.x);
+    const R ty = pml_apply(form, order, co, mul_(dF.y, sl.inv_d), q0.y, q1.y);
+    const R tz = pml_apply(form, order, co, mul_(dF.z, sl.inv_d), q0.z, q1.z);
+    const R tw = pml_apply(form, order, co, mul_(dF.w, sl.inv_d), q0.w, q1.w);
+    if (m & 1u) { F.x = fma_(sign, mul_(src[id.a], tx), F.x); p0.x = q0.x; p1.x = q1.x; }
+    if (m & 2u) { F.y = fma_(sign, mul_(src[id.b], ty), F.y); p0.y = q0.y; p1.y = q1.y; }
+    if (m & 4u) { F.z = fma_(sign, mul_(src[id.c], tz), F.z); p0.z = q0.z; p1.z = q1.z; }
+    if (m & 8u) { F.w = fma_(sign, mul_(src[id.d], tw), F.w); p0.w = q0.w; p1.w = q1.w; }
     st4(phi, p0);
     if (order == 2) st4(phi + 2 * sl.ostride, p1);
 }
@@ -295,26 +218,26 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(cons
             if (mx) {
                 Coef4<R> c0, c1, c2, c3;
                 coef4(coef, idx_, c0, c1, c2, c3);
-                hx.x = sel(mx, 0, c0.a * hx.x - c0.by * dEz_dy.x + c0.bz * dEy_dz.x, hx.x);
-                hx.y = sel(mx, 1, c1.a * hx.y - c1.by * dEz_dy.y + c1.bz * dEy_dz.y, hx.y);
-                hx.z = sel(mx, 2, c2.a * hx.z - c2.by * dEz_dy.z + c2.bz * dEy_dz.z, hx.z);
-                hx.w = sel(mx, 3, c3.a * hx.w - c3.by * dEz_dy.w + c3.bz * dEy_dz.w, hx.w);
+                hx.x = sel(mx, 0, upd3(c0.a, hx.x, -c0.by, dEz_dy.x, c0.bz, dEy_dz.x), hx.x);
+                hx.y = sel(mx, 1, upd3(c1.a, hx.y, -c1.by, dEz_dy.y, c1.bz, dEy_dz.y), hx.y);
+                hx.z = sel(mx, 2, upd3(c2.a, hx.z, -c2.by, dEz_dy.z, c2.bz, dEy_dz.z), hx.z);
+                hx.w = sel(mx, 3, upd3(c3.a, hx.w, -c3.by, dEz_dy.w, c3.bz, dEy_dz.w), hx.w);
             }
             if (my) {
                 Coef4<R> c0, c1, c2, c3;
                 coef4(coef, idy_, c0, c1, c2, c3);
-                hy.x = sel(my, 0, c0.a * hy.x - c0.bz * dEx_dz.x + c0.bx * dEz_dx.x, hy.x);
-                hy.y = sel(my, 1, c1.a * hy.y - c1.bz * dEx_dz.y + c1.bx * dEz_dx.y, hy.y);
-                hy.z = sel(my, 2, c2.a * hy.z - c2.bz * dEx_dz.z + c2.bx * dEz_dx.z, hy.z);
-                hy.w = sel(my, 3, c3.a * hy.w - c3.bz * dEx_dz.w + c3.bx * dEz_dx.w, hy.w);
+                hy.x = sel(my, 0, upd3(c0.a, hy.x, -c0.bz, dEx_dz.x, c0.bx, dEz_dx.x), hy.x);
+                hy.y = sel(my, 1, upd3(c1.a, hy.y, -c1.bz, dEx_dz.y, c1.bx, dEz_dx.y), hy.y);
+                hy.z = sel(my, 2, upd3(c2.a, hy.z, -c2.bz, dEx_dz.z, c2.bx, dEz_dx.z), hy.z);
+                hy.w = sel(my, 3, upd3(c3.a, hy.w, -c3.bz, dEx_dz.w, c3.bx, dEz_dx.w), hy.w);
             }
             if (mz) {
                 Coef4<R> c0, c1, c2, c3;
                 coef4(coef, idz_, c0, c1, c2, c3);
-                hz.x = sel(mz, 0, c0.a * hz.x - c0.bx * dEy_dx.x + c0.by * dEx_dy.x, hz.x);
-                hz.y = sel(mz, 1, c1.a * hz.y - c1.bx * dEy_dx.y + c1.by * dEx_dy.y, hz.y);
-                hz.z = sel(mz, 2, c2.a * hz.z - c2.bx * dEy_dx.z + c2.by * dEx_dy.z, hz.z);
-                hz.w = sel(mz, 3, c3.a * hz.w - c3.bx * dEy_dx.w + c3.by * dEx_dy.w, hz.w);
+                hz.x = sel(mz, 0, upd3(c0.a, hz.x, -c0.bx, dEy_dx.x, c0.by, dEx_dy.x), hz.x);
+                hz.y = sel(mz, 1, upd3(c1.a, hz.y, -c1.bx, dEy_dx.y, c1.by, dEx_dy.y), hz.y);
+                hz.z = sel(mz, 2, upd3(c2.a, hz.z, -c2.bx, dEy_dx.z, c2.by, dEx_dy.z), hz.z);
+                hz.w = sel(mz, 3, upd3(c3.a, hz.w, -c3.bx, dEy_dx.w, c3.by, dEx_dy.w), hz.w);
             }
             if (pm) {
                 for (int s = 0; s < p.nslabs; ++s) {
@@ -464,15 +387,15 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
                 if (DISP) {
                     V4<R> ph;
                     disp4(p, 0, idx_, off, mx, ex, ph);
-                    ex.x = sel(mx, 0, c0.a * ex.x + c0.by * dHz_dy.x - c0.bz * dHy_dz.x - srce[idx_.a] * ph.x, ex.x);
-                    ex.y = sel(mx, 1, c1.a * ex.y + c1.by * dHz_dy.y - c1.bz * dHy_dz.y - srce[idx_.b] * ph.y, ex.y);
-                    ex.z = sel(mx, 2, c2.a * ex.z + c2.by * dHz_dy.z - c2.bz * dHy_dz.z - srce[idx_.c] * ph.z, ex.z);
-                    ex.w = sel(mx, 3, c3.a * ex.w + c3.by * dHz_dy.w - c3.bz * dHy_dz.w - srce[idx_.d] * ph.w, ex.w);
+                    ex.x = sel(mx, 0, upd3(c0.a, ex.x, c0.by, dHz_dy.x, -c0.bz, dHy_dz.x) - srce[idx_.a] * ph.x, ex.x);
+                    ex.y = sel(mx, 1, upd3(c1.a, ex.y, c1.by, dHz_dy.y, -c1.bz, dHy_dz.y) - srce[idx_.b] * ph.y, ex.y);
+                    ex.z = sel(mx, 2, upd3(c2.a, ex.z, c2.by, dHz_dy.z, -c2.bz, dHy_dz.z) - srce[idx_.c] * ph.z, ex.z);
+                    ex.w = sel(mx, 3, upd3(c3.a, ex.w, c3.by, dHz_dy.w, -c3.bz, dHy_dz.w) - srce[idx_.d] * ph.w, ex.w);
                 } else {
-                ex.x = sel(mx, 0, c0.a * ex.x + c0.by * dHz_dy.x - c0.bz * dHy_dz.x, ex.x);
-                ex.y = sel(mx, 1, c1.a * ex.y + c1.by * dHz_dy.y - c1.bz * dHy_dz.y, ex.y);
-                ex.z = sel(mx, 2, c2.a * ex.z + c2.by * dHz_dy.z - c2.bz * dHy_dz.z, ex.z);
-                ex.w = sel(mx, 3, c3.a * ex.w + c3.by * dHz_dy.w - c3.bz * dHy_dz.w, ex.w);
+                ex.x = sel(mx, 0, upd3(c0.a, ex.x, c0.by, dHz_dy.x, -c0.bz, dHy_dz.x), ex.x);
+                ex.y = sel(mx, 1, upd3(c1.a, ex.y, c1.by, dHz_dy.y, -c1.bz, dHy_dz.y), ex.y);
+                ex.z = sel(mx, 2, upd3(c2.a, ex.z, c2.by, dHz_dy.z, -c2.bz, dHy_dz.z), ex.z);
+                ex.w = sel(mx, 3, upd3(c3.a, ex.w, c3.by, dHz_dy.w, -c3.bz, dHy_dz.w), ex.w);
                 }
             }
             if (my) {
@@ -481,15 +404,15 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
                 if (DISP) {
                     V4<R> ph;
                     disp4(p, 1, idy_, off, my, ey, ph);
-                    ey.x = sel(my, 0, c0.a * ey.x + c0.bz * dHx_dz.x - c0.bx * dHz_dx.x - srce[idy_.a] * ph.x, ey.x);
-                    ey.y = sel(my, 1, c1.a * ey.y + c1.bz * dHx_dz.y - c1.bx * dHz_dx.y - srce[idy_.b] * ph.y, ey.y);
-                    ey.z = sel(my, 2, c2.a * ey.z + c2.bz * dHx_dz.z - c2.bx * dHz_dx.z - srce[idy_.c] * ph.z, ey.z);
-                    ey.w = sel(my, 3, c3.a * ey.w + c3.bz * dHx_dz.w - c3.bx * dHz_dx.w - srce[idy_.d] * ph.w, ey.w);
+                    ey.x = sel(my, 0, upd3(c0.a, ey.x, c0.bz, dHx_dz.x, -c0.bx, dHz_dx.x) - srce[idy_.a] * ph.x, ey.x);
+                    ey.y = sel(my, 1, upd3(c1.a, ey.y, c1.bz, dHx_dz.y, -c1.bx, dHz_dx.y) - srce[idy_.b] * ph.y, ey.y);
+                    ey.z = sel(my, 2, upd3(c2.a, ey.z, c2.bz, dHx_dz.z, -c2.bx, dHz_dx.z) - srce[idy_.c] * ph.z, ey.z);
+                    ey.w = sel(my, 3, upd3(c3.a, ey.w, c3.bz, dHx_dz.w, -c3.bx, dHz_dx.w) - srce[idy_.d] * ph.w, ey.w);
                 } else {
-                ey.x = sel(my, 0, c0.a * ey.x + c0.bz * dHx_dz.x - c0.bx * dHz_dx.x, ey.x);
-                ey.y = sel(my, 1, c1.a * ey.y + c1.bz * dHx_dz.y - c1.bx * dHz_dx.y, ey.y);
-                ey.z = sel(my, 2, c2.a * ey.z + c2.bz * dHx_dz.z - c2.bx * dHz_dx.z, ey.z);
-                ey.w = sel(my, 3, c3.a * ey.w + c3.bz * dHx_dz.w - c3.bx * dHz_dx.w, ey.w);
+                ey.x = sel(my, 0, upd3(c0.a, ey.x, c0.bz, dHx_dz.x, -c0.bx, dHz_dx.x), ey.x);
+                ey.y = sel(my, 1, upd3(c1.a, ey.y, c1.bz, dHx_dz.y, -c1.bx, dHz_dx.y), ey.y);
+                ey.z = sel(my, 2, upd3(c2.a, ey.z, c2.bz, dHx_dz.z, -c2.bx, dHz_dx.z), ey.z);
+                ey.w = sel(my, 3, upd3(c3.a, ey.w, c3.bz, dHx_dz.w, -c3.bx, dHz_dx.w), ey.w);
                 }
             }
             if (mz) {
@@ -498,15 +421,15 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
                 if (DISP) {
                     V4<R> ph;
                     disp4(p, 2, idz_, off, mz, ez, ph);
-                    ez.x = sel(mz, 0, c0.a * ez.x + c0.bx * dHy_dx.x - c0.by * dHx_dy.x - srce[idz_.a] * ph.x, ez.x);
-                    ez.y = sel(mz, 1, c1.a * ez.y + c1.bx * dHy_dx.y - c1.by * dHx_dy.y - srce[idz_.b] * ph.y, ez.y);
-                    ez.z = sel(mz, 2, c2.a * ez.z + c2.bx * dHy_dx.z - c2.by * dHx_dy.z - srce[idz_.c] * ph.z, ez.z);
-                    ez.w = sel(mz, 3, c3.a * ez.w + c3.bx * dHy_dx.w - c3.by * dHx_dy.w - srce[idz_.d] * ph.w, ez.w);
+                    ez.x = sel(mz, 0, upd3(c0.a, ez.x, c0.bx, dHy_dx.x, -c0.by, dHx_dy.x) - srce[idz_.a] * ph.x, ez.x);
+                    ez.y = sel(mz, 1, upd3(c1.a, ez.y, c1.bx, dHy_dx.y, -c1.by, dHx_dy.y) - srce[idz_.b] * ph.y, ez.y);
+                    ez.z = sel(mz, 2, upd3(c2.a, ez.z, c2.bx, dHy_dx.z, -c2.by, dHx_dy.z) - srce[idz_.c] * ph.z, ez.z);
+                    ez.w = sel(mz, 3, upd3(c3.a, ez.w, c3.bx, dHy_dx.w, -c3.by, dHx_dy.w) - srce[idz_.d] * ph.w, ez.w);
                 } else {
-                ez.x = sel(mz, 0, c0.a * ez.x + c0.bx * dHy_dx.x - c0.by * dHx_dy.x, ez.x);
-                ez.y = sel(mz, 1, c1.a * ez.y + c1.bx * dHy_dx.y - c1.by * dHx_dy.y, ez.y);
-                ez.z = sel(mz, 2, c2.a * ez.z + c2.bx * dHy_dx.z - c2.by * dHx_dy.z, ez.z);
-                ez.w = sel(mz, 3, c3.a * ez.w + c3.bx * dHy_dx.w - c3.by * dHx_dy.w, ez.w);
+                ez.x = sel(mz, 0, upd3(c0.a, ez.x, c0.bx, dHy_dx.x, -c0.by, dHx_dy.x), ez.x);
+                ez.y = sel(mz, 1, upd3(c1.a, ez.y, c1.bx, dHy_dx.y, -c1.by, dHx_dy.y), ez.y);
+                ez.z = sel(mz, 2, upd3(c2.a, ez.z, c2.bx, dHy_dx.z, -c2.by, dHx_dy.z), ez.z);
+                ez.w = sel(mz, 3, upd3(c3.a, ez.w, c3.bx, dHy_dx.w, -c3.by, dHx_dy.w), ez.w);
                 }
             }
             if (pm) {
@@ -575,8 +498,8 @@ __device__ __forceinline__ void pml_slab_cell(const PhaseParams<R> &p, int phase
         dB = (Gb[off + st] - Gb[off]) * sl.inv_d;
     }
     const unsigned ma = ld_id<IDT>(p.ID[ca], off), mb = ld_id<IDT>(p.ID[cb], off);
-    Fa[off] = Fa[off] + sa * (src[ma] * pml_term(p.form, p.order, sl, depth, dA, phi, sl.ostride));
-    Fb[off] = Fb[off] + sb * (src[mb] * pml_term(p.form, p.order, sl, depth, dB, phi + sl.ostride, sl.ostride));
+    Fa[off] = fma_(sa, mul_(src[ma], pml_term(p.form, p.order, sl, depth, dA, phi, sl.ostride)), Fa[off]);
+    Fb[off] = fma_(sb, mul_(src[mb], pml_term(p.form, p.order, sl, depth, dB, phi + sl.ostride, sl.ostride)), Fb[off]);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -164,3 +164,42 @@ def test_f64_every_kernel_path(name, mode, monkeypatch):
     out = _solve(G)
     worst, rep = compare_traces(out, golden, np.float64, tol=tolerance(G, np.float64))
     assert worst <= 1.0, rep
+
+
+def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
+    """A grid large enough for the persistent TMA kernels (many work items per CTA) with a random mix of materials on
+    every edge: the TMA-staged kernels (persistent / one CTA per item / thread-0 producer / z slabs in their own kernel)
+    and the register-vectorised kernels must produce the same bits, twice in a row.  Catches stage-release races (a
+    consumer reading material IDs after handing the stage back read the next tile's IDs -- harmless on homogeneous
+    benchmarks, timing-dependent here) and any difference in FMA placement between kernel families, which a sharded run
+    next to its single-GPU reference would expose."""
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    sys.path.insert(0, sys_path)
+    from gprmax_b200 import Solver
+    from gprmax_b200.synthetic import homogeneous_model, material_rows
+    nx, ny, nz, its = 160, 144, 128, 30
+    G = homogeneous_model((nx, ny, nz), iterations=its, er=6.0, se=0.01, src=(nx // 2 * 1e-3, ny // 2 * 1e-3, nz // 2 * 1e-3), src_pol='z',
+                          rxs=[((nx // 2 + 3) * 1e-3, (ny // 2 + 2) * 1e-3, nz // 2 * 1e-3)])
+    real = G.updatecoeffsE.dtype
+    rows = [material_rows(er, se, 1.0, 0.0, G.dx, G.dy, G.dz, G.dt, real) for er, se in ((3.0, 0.001), (9.0, 0.02), (4.5, 0.0), (12.0, 0.05))]
+    G.updatecoeffsE = np.concatenate([G.updatecoeffsE, np.stack([r[0] for r in rows])])
+    G.updatecoeffsH = np.concatenate([G.updatecoeffsH, np.stack([r[1] for r in rows])])
+    rng = np.random.default_rng(7)
+    G.ID = rng.integers(2, G.updatecoeffsE.shape[0], size=G.ID.shape, dtype=np.uint32)
+
+    def run(env):
+        for k in ('GPB_NO_TMA', 'GPB_TMA_NOPERSIST', 'GPB_TMA_PW', 'GPB_TMA_ZSPLIT'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Solver(G, device_id=0) as sv:
+            sv.run()
+            return [sv.get_field(c) for c in range(6)] + [sv.receivers()]
+
+    ref = run({'GPB_NO_TMA': '1'})
+    assert np.abs(ref[-1]).max() > 0
+    for env in ({}, {}, {'GPB_TMA_NOPERSIST': '1'}, {'GPB_TMA_PW': '0'}, {'GPB_TMA_ZSPLIT': '1'}):
+        out = run(env)
+        for c, (a, b) in enumerate(zip(out, ref)):
+            assert np.array_equal(a, b), (env, c, int((a != b).sum()))
