@@ -181,19 +181,20 @@ def run_single_gpu(args):
         alg_bytes = cells * b_alg / 2.0  # one half-step
         achieved = alg_bytes / t_launch / 1e9
         share = prof[dom] / max(sum(prof.values()), 1e-30)
-        # DRAM bytes per launch from the committed ncu --set full capture of the same workload (profiles/README.md):
-        # k_update_tma 818+319 MB and its k_pml_slabs 141+16 MB at 300^3; only quoted for that exact workload
-        traffic = 1.294e9 if N == 300 else None
-        roof = {'bound': 'hbm', 'kernel': 'half-step launch pair: k_update_tma<PHASE={}> + k_pml_slabs ({})'.format(1 if dom == 'update_e' else 0, dom),
+        # DRAM bytes per launch from the committed ncu --set full capture of the same workload (profiles/README.md, r1k):
+        # k_update_tma 846 MB read + 342 MB written at 300^3 (all PML slabs fused); only quoted for that exact workload
+        traffic = 1.188e9 if N == 300 else None
+        roof = {'bound': 'hbm', 'kernel': 'k_update_tma<PHASE={}> ({}: base update + all six PML slabs in one launch)'.format(1 if dom == 'update_e' else 0, dom),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'traffic_source': 'profiles/r1e_main_raw.csv + r1e_pml_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum)',
+                'traffic': traffic, 'traffic_source': 'profiles/r1k_main_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum)',
                 'peak_source': peak_src, 'alg_bytes_per_launch': alg_bytes, 'launch_ms': t_launch * 1e3,
                 'share_of_step': share, 'whole_step_frac': value * 1e6 * b_alg / 1e9 / peak,
                 'kernel_ms_per_iteration': {k: v / nprof_timed for k, v in prof.items()}}
 
     # ---- end-to-end leg: the public drop-in call from host arrays
-    # (1 untimed call, then `steps` timed calls; the median is reported because the host side -- pageable 654 MB
-    # upload, cudaMalloc/cudaFree -- shows occasional multi-100-ms outliers on shared hosts; all samples are kept)
+    # (1 untimed call, then `steps` timed calls, median reported, all samples kept.  Every call creates a solver from the
+    # host arrays -- 654 MB of uint32 IDs go through pinned bounce buffers -- runs all iterations and copies the traces
+    # back; device memory freed by the previous call is reused by the library's cache, as in a B-scan)
     e2e_t = []
     for s in range(1 + max(args.steps, 3)):
         t0 = time.perf_counter()
