@@ -790,6 +790,7 @@ int Solver<R>::launch_tma(int phase, int p0, int p1)
         }
     if (getenv("GPB_TMA_NOFAST")) p.fast_i1 = p.fast_i0;
     p.zfused = getenv("GPB_TMA_ZSPLIT") ? 0 : 1;
+    p.znocoop = getenv("GPB_TMA_ZNOCOOP") ? 1 : 0;
     a.maps = phase == 0 ? &maps_h : &maps_e;
     a.phase = phase;
     a.ty = tma_ty; a.tz = tma_tz; a.stages = tma_stages; a.pw = tma_pw;

@@ -92,6 +92,7 @@ struct PhaseParams {
     int xreverse;             // TMA kernels: E phase visits the x chunks in descending order (L2 reuse across phases)
     int fast_i0, fast_i1;     // TMA kernels: planes between the x slabs and inside all three update boxes
     int zfused;               // TMA kernels: z-slab PML in the same pass (else k_pml_slabs afterwards)
+    int znocoop;              // TMA kernels: z-slab corrections per thread (4 cells) instead of one cell per lane
     int tmax;                 // TMA kernels: row length of the shared-memory copies of the PML R tables (max thickness)
     int pf_depth;             // TMA kernels: Phi prefetch distance in planes (cp.async ring per thread), 0 = direct loads
     int persist;              // TMA kernels: persistent CTAs pulling (tile, x-chunk) items from an atomic counter

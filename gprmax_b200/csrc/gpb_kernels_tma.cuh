@@ -441,6 +441,33 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
 #pragma unroll
     for (int s = 0; s < kMaxSlabs; ++s)
         if ((smask >> (4 * s)) & 0xfu) smask6 |= 1u << s;
+    // Cooperative z-slab corrections.  A z slab covers ~10 cells at one end of every z row: handled per thread, 3 of the 16
+    // threads of a row would run the whole correction for their 4 cells while the other 13 idle (r1k: the z corrections were the
+    // largest PML cost, executed by 40 % of all warps on 6 of 32 lanes).  Instead lane c of a row takes ONE cell (column zkq0 + c
+    // of its own row) and both components, and hands the correction to the owner of the cell by warp shuffle.  Needs a single z
+    // slab in the tile with at most TZ/4 columns here; otherwise that slab stays on the per-thread path.
+    constexpr int LPR = TZ / 4;   // lanes per tile row
+    int zs = -1;
+    if (p.zfused && !p.znocoop) {
+#pragma unroll
+        for (int s = 0; s < kMaxSlabs; ++s)
+            if (s < p.nslabs && p.slab[s].axis == 2 && min(k0 + TZ, p.slab[s].hi[2]) > max(k0, p.slab[s].lo[2])) zs = zs == -1 ? s : -2;
+    }
+    int zkq0 = 0;
+    if (zs >= 0) {
+        zkq0 = max(p.slab[zs].ko, k0);
+        if (LPR > 32 || min(p.slab[zs].hi[2], k0 + TZ) - zkq0 > LPR) zs = -1;
+    }
+    const bool zcoop = zs >= 0;
+    const int zc = zcoop ? zs : 0;                      // index used for parameter reads (any valid slab when unused)
+    const int zk = zkq0 + (tid % LPR);                  // my cooperative cell: own row j, column zk
+    const bool zok = zcoop && j <= p.ny && j >= p.slab[zc].lo[1] && j < p.slab[zc].hi[1] && zk >= p.slab[zc].lo[2] && zk < p.slab[zc].hi[2];
+    const int zdepth = p.slab[zc].minus ? (p.slab[zc].dref - zk) : (zk - p.slab[zc].dref);
+    const long long zphi_off = zok ? ((long long)(j - p.slab[zc].lo[1]) * p.slab[zc].n2 + (zk - p.slab[zc].ko)) : 0;
+    const unsigned zm = zcoop ? ((smask >> (4 * zc)) & 0xfu) : 0u;   // cells of my own quad inside that slab
+    if (zcoop) {   // the per-thread machinery (prefetch, slab loop) no longer sees the slab
+        smask6 &= ~(1u << zc);
+    }
     const bool pf = smask6 != 0u && p.pf_depth > 0;
     auto i_of = [&](int n) { return p.x_start + (PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1)) - 1; };
     auto prefetch = [&](V4<R> *slot, unsigned pmn, int ii) {   // Phi of the lowest-numbered slab in pmn at plane ii -> my slot
@@ -476,6 +503,14 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         }
         const int pl = PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1);
         const int i = p.x_start + pl - 1;
+        // cooperative z slab: my cell's Phi (both components) straight into registers, before the wait for the plane
+        const bool zact = zcoop && i >= p.slab[zc].lo[0] && i < p.slab[zc].hi[0];   // CTA-uniform
+        R *zphi = p.slab[zc].phi + (long long)(i - p.slab[zc].lo[0]) * p.slab[zc].n1 * p.slab[zc].n2 + zphi_off;
+        R zP[2 * PORDER];
+        if (zact && zok) {
+#pragma unroll
+            for (int q = 0; q < 2 * PORDER; ++q) zP[q] = zphi[q * p.slab[zc].ostride];
+        }
         const unsigned char *st = stages + (size_t)(g % kStages) * L::bytes;
         mbar_wait(full + (g % kStages), (uint32_t)((g / kStages) & 1));
         const R *sOp = reinterpret_cast<const R *>(st + L::oOp);
@@ -507,13 +542,14 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         // instead of keeping them in registers (which spilled the straight-line update of every thread).
         // (the IDs are read here, before the release: the stage is refilled as soon as the last warp has arrived)
         const IdQ<IDT> id0 = IdQ<IDT>::load(st + L::oId, e), id1 = IdQ<IDT>::load(st + L::oId, L::OS + e), id2 = IdQ<IDT>::load(st + L::oId, 2 * L::OS + e);
-        const bool wpml = __any_sync(0xffffffffu, pm != 0u);
+        const bool wpml = __any_sync(0xffffffffu, pm != 0u) || zact;
         if (!wpml) {
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + (g % kStages));
             if (!PW && tid == 0 && !p_done) produce();
         }
 
+        bool w0 = false, w1 = false, w2 = false;
         if (any) {
             // one straight-line update for every thread; threads with cells outside an update box (domain faces, the
             // two x-slab plane ranges) put the old value back per cell afterwards
@@ -605,15 +641,51 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                 if (!fast) { u.x = sel(m2, 0, u.x, f2.x); u.y = sel(m2, 1, u.y, f2.y); u.z = sel(m2, 2, u.z, f2.z); u.w = sel(m2, 3, u.w, f2.w); }
                 f2 = u;
             }
-            bool w0 = m0 != 0u, w1 = m1 != 0u, w2 = m2 != 0u;
-            if (pm) {
+            w0 = m0 != 0u; w1 = m1 != 0u; w2 = m2 != 0u;
+        }
+        if (wpml) {   // warp-uniform
+            {
                 const V4<R> *slot = nullptr;
-                if (pf) {
+                if (pf && pm) {
                     if (p.pf_depth == 2) cp_async_wait1();
                     else cp_async_wait0();
                     slot = spf + (size_t)(n % p.pf_depth) * 2 * PORDER * kTmaThreads + tid;
                 }
-                for (int s = 0; s < p.nslabs; ++s) {   // G.pmls order
+                for (int s = 0; s < p.nslabs; ++s) {   // G.pmls order; s is CTA-uniform
+                    if (zact && s == zs) {
+                        // ---- cooperative z slab: one cell per lane, both components
+                        const SlabDev<R> &sl = p.slab[s];
+                        R corr_a = 0, corr_b = 0;
+                        if (zok) {
+                            const PmlCo<R> co = pml_load_s(PFORM, PORDER, stab + (size_t)s * 4 * PORDER * p.tmax, p.tmax, zdepth);
+                            const int zkk = zk - k0;
+                            const int o = PHASE == 1 ? ((r + 1) * L::PA + zkk + 4) : (r * L::PA + zkk);
+                            R dB, dA;   // d(operand B)/dz for the first component, d(operand A)/dz for the second, as in the quad path
+                            if (PHASE == 1) { dB = sOp[L::CS + o] - sOp[L::CS + o - 1]; dA = sOp[o] - sOp[o - 1]; }
+                            else { dB = sOp[L::CS + o + 1] - sOp[L::CS + o]; dA = sOp[o + 1] - sOp[o]; }
+                            const IDT *sid = reinterpret_cast<const IDT *>(st + L::oId);
+                            const unsigned ida = sid[r * TZ + zkk], idb = sid[L::OS + r * TZ + zkk];
+                            R Pa0 = zP[0], Pb0 = zP[1], Pa1 = PORDER == 2 ? zP[2 * (PORDER - 1)] : Pa0, Pb1 = PORDER == 2 ? zP[2 * (PORDER - 1) + 1] : Pb0;
+                            corr_a = mul_(ssrc[ida], pml_apply(PFORM, PORDER, co, mul_(dB, sl.inv_d), Pa0, Pa1));
+                            corr_b = mul_(ssrc[idb], pml_apply(PFORM, PORDER, co, mul_(dA, sl.inv_d), Pb0, Pb1));
+                            zphi[0] = Pa0;
+                            zphi[sl.ostride] = Pb0;
+                            if (PORDER == 2) { zphi[2 * sl.ostride] = Pa1; zphi[3 * sl.ostride] = Pb1; }
+                        }
+                        // to the owners: cell e of my quad was computed by lane (row base) + (k - zkq0) + e
+                        const int src0 = (lane & ~(LPR - 1)) + (k - zkq0);
+                        const R sa = PHASE == 1 ? (R)-1 : (R)1;   // E: Ex -= , Ey += ; H: Hx += , Hy -=
+                        const R ca0 = __shfl_sync(0xffffffffu, corr_a, src0 & 31), ca1 = __shfl_sync(0xffffffffu, corr_a, (src0 + 1) & 31);
+                        const R ca2 = __shfl_sync(0xffffffffu, corr_a, (src0 + 2) & 31), ca3 = __shfl_sync(0xffffffffu, corr_a, (src0 + 3) & 31);
+                        const R cb0 = __shfl_sync(0xffffffffu, corr_b, src0 & 31), cb1 = __shfl_sync(0xffffffffu, corr_b, (src0 + 1) & 31);
+                        const R cb2 = __shfl_sync(0xffffffffu, corr_b, (src0 + 2) & 31), cb3 = __shfl_sync(0xffffffffu, corr_b, (src0 + 3) & 31);
+                        if (zm & 1u) { f0.x = fma_(sa, ca0, f0.x); f1.x = fma_(-sa, cb0, f1.x); }
+                        if (zm & 2u) { f0.y = fma_(sa, ca1, f0.y); f1.y = fma_(-sa, cb1, f1.y); }
+                        if (zm & 4u) { f0.z = fma_(sa, ca2, f0.z); f1.z = fma_(-sa, cb2, f1.z); }
+                        if (zm & 8u) { f0.w = fma_(sa, ca3, f0.w); f1.w = fma_(-sa, cb3, f1.w); }
+                        if (zm) w0 = w1 = true;
+                        continue;
+                    }
                     if (!((pm >> s) & 1u)) continue;
                     const SlabDev<R> &sl = p.slab[s];
                     const unsigned m = (smask >> (4 * s)) & 0xfu;
@@ -677,6 +749,8 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                     slot = nullptr;   // only the first slab was prefetched
                 }
             }
+        }
+        if (any) {
             const long long off = (long long)pl * p.plane + eoff;
             if (w0) st4(F0 + off, f0);
             if (w1) st4(F1 + off, f1);

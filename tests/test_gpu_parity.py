@@ -141,12 +141,12 @@ TMA_FIXTURES = ['pml_HORIPML_1', 'pml_HORIPML_2', 'pml_MRIPML_1', 'pml_MRIPML_2'
 
 
 @pytest.mark.parametrize('name', TMA_FIXTURES)
-@pytest.mark.parametrize('mode', ['tma', 'tma_nopersist', 'tma_pw0', 'tma_tile8x128', 'tma_zsplit', 'scalar'])
+@pytest.mark.parametrize('mode', ['tma', 'tma_nopersist', 'tma_pw0', 'tma_tile8x128', 'tma_zsplit', 'tma_znocoop', 'scalar'])
 def test_f64_every_kernel_path(name, mode, monkeypatch):
     """The small fixtures normally run on the register-vectorised kernels (the TMA kernels are only selected above
     2.5 M nodes); force each kernel family in turn so that all of them are held to the 1e-10 bar:
     TMA-staged persistent CTAs with a producer warp (default), one CTA per work item, producer = thread 0 of a 16 x 64 tile,
-    another tile shape, z-slab PML in its own kernel, generic scalar."""
+    another tile shape, z-slab PML in its own kernel, z-slab PML per thread instead of one cell per lane, generic scalar."""
     from gprmax_b200.model_io import load_model
     if mode.startswith('tma'):
         monkeypatch.setenv('GPB_FORCE_TMA', '1')
@@ -156,6 +156,8 @@ def test_f64_every_kernel_path(name, mode, monkeypatch):
         monkeypatch.setenv('GPB_TMA_PW', '0')
     if mode == 'tma_zsplit':
         monkeypatch.setenv('GPB_TMA_ZSPLIT', '1')
+    if mode == 'tma_znocoop':
+        monkeypatch.setenv('GPB_TMA_ZNOCOOP', '1')
     if mode == 'tma_tile8x128':
         monkeypatch.setenv('GPB_TMA_TZ', '128')
     if mode == 'scalar':
@@ -189,7 +191,7 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
     G.ID = rng.integers(2, G.updatecoeffsE.shape[0], size=G.ID.shape, dtype=np.uint32)
 
     def run(env):
-        for k in ('GPB_NO_TMA', 'GPB_TMA_NOPERSIST', 'GPB_TMA_PW', 'GPB_TMA_ZSPLIT'):
+        for k in ('GPB_NO_TMA', 'GPB_TMA_NOPERSIST', 'GPB_TMA_PW', 'GPB_TMA_ZSPLIT', 'GPB_TMA_ZNOCOOP'):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -199,7 +201,7 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
 
     ref = run({'GPB_NO_TMA': '1'})
     assert np.abs(ref[-1]).max() > 0
-    for env in ({}, {}, {'GPB_TMA_NOPERSIST': '1'}, {'GPB_TMA_PW': '0'}, {'GPB_TMA_ZSPLIT': '1'}):
+    for env in ({}, {}, {'GPB_TMA_NOPERSIST': '1'}, {'GPB_TMA_PW': '0'}, {'GPB_TMA_ZSPLIT': '1'}, {'GPB_TMA_ZNOCOOP': '1'}):
         out = run(env)
         for c, (a, b) in enumerate(zip(out, ref)):
             assert np.array_equal(a, b), (env, c, int((a != b).sum()))
