@@ -218,11 +218,13 @@ def bench_sharded(args):
     import torch.distributed as dist
     from .synthetic import homogeneous_model
 
-    if not dist.is_initialized():
-        dist.init_process_group('nccl')
-    rank, world = dist.get_rank(), dist.get_world_size()
-    local = int(os.environ.get('LOCAL_RANK', rank))
+    # stdout carries exactly one JSON line: NCCL's own log lines ("NCCL version ...", NCCL_DEBUG=INFO output) go to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    local = int(os.environ.get('LOCAL_RANK', os.environ.get('RANK', '0')))
     torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank, world = dist.get_rank(), dist.get_world_size()
     per_gpu = int(os.environ.get('GPB_SHARD_PLANES', '256'))
     ny, nz = int(os.environ.get('GPB_SHARD_NY', '2048')), int(os.environ.get('GPB_SHARD_NZ', '1024'))
     nx = per_gpu * world
