@@ -505,9 +505,10 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         const int i = p.x_start + pl - 1;
         // cooperative z slab: my cell's Phi (both components) straight into registers, before the wait for the plane
         const bool zact = zcoop && i >= p.slab[zc].lo[0] && i < p.slab[zc].hi[0];   // CTA-uniform
-        R *zphi = p.slab[zc].phi + (long long)(i - p.slab[zc].lo[0]) * p.slab[zc].n1 * p.slab[zc].n2 + zphi_off;
+        R *zphi = nullptr;
         R zP[2 * PORDER];
         if (zact && zok) {
+            zphi = p.slab[zc].phi + (long long)(i - p.slab[zc].lo[0]) * p.slab[zc].n1 * p.slab[zc].n2 + zphi_off;
 #pragma unroll
             for (int q = 0; q < 2 * PORDER; ++q) zP[q] = zphi[q * p.slab[zc].ostride];
         }
