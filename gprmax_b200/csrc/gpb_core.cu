@@ -779,7 +779,6 @@ int Solver<R>::launch_tma(int phase, int p0, int p1)
     PhaseParams<R> &p = a.p;
     p = phase == 0 ? ph_h : ph_e;
     p.p0 = p0; p.p1 = p1; p.xchunk = tma_xchunk; p.persist = tma_persist ? 1 : 0;
-    p.xreverse = 0;
     // planes on which a thread whose 4 cells are interior in (j,k) needs no mask / slab logic at all
     p.fast_i0 = std::max(p.box[0].lo[0], std::max(p.box[1].lo[0], p.box[2].lo[0]));
     p.fast_i1 = std::min(p.box[0].hi[0], std::min(p.box[1].hi[0], p.box[2].hi[0]));

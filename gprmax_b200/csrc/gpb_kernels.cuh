@@ -89,7 +89,6 @@ struct PhaseParams {
     // sub-range of owned planes processed by this launch (for halo overlap): [p0, p1)
     int p0, p1;
     int xchunk;               // planes marched by one CTA of the TMA kernels
-    int xreverse;             // TMA kernels: E phase visits the x chunks in descending order (L2 reuse across phases)
     int fast_i0, fast_i1;     // TMA kernels: planes between the x slabs and inside all three update boxes
     int zfused;               // TMA kernels: z-slab PML in the same pass (else k_pml_slabs afterwards)
     int znocoop;              // TMA kernels: z-slab corrections per thread (4 cells) instead of one cell per lane
