@@ -205,3 +205,20 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
         out = run(env)
         for c, (a, b) in enumerate(zip(out, ref)):
             assert np.array_equal(a, b), (env, c, int((a != b).sum()))
+
+
+def test_device_memory_cache_reuse_and_release():
+    """gpb_destroy keeps the device blocks for the next gpb_create of the same size (a B-scan creates one solver per trace):
+    a second solver built from stale cached blocks must give the same bits as the first, and gpb_release_cached must work."""
+    from gprmax_b200 import Solver, _lib
+    from gprmax_b200.model_io import load_model
+    G, _ = load_model(golden_path('pml_HORIPML_2', 'f32'))
+    outs = []
+    for rep in range(3):
+        with Solver(G, device_id=0) as sv:
+            sv.run()
+            outs.append(sv.receivers())
+        if rep == 1:
+            assert _lib.lib().gpb_release_cached() == 0
+    assert np.abs(outs[0]).max() > 0
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
