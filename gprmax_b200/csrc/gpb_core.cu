@@ -756,15 +756,15 @@ int Solver<R>::setup_tma()
             make_map(&mp.id, ids, idt, idbytes, pitch, rows, planes, narr, TZ, TY, 3))
             return 1;
     }
-    // planes per CTA: short marches (8 planes) measured best on B200 -- many CTAs keep the two resident
-    // CTAs per SM out of phase so one computes while the other's pipeline fills; shorter still when the
-    // grid would otherwise have fewer than ~6 waves
     CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));   // (cudaGetDeviceProperties took 3 - 190 ms here)
     tma_persist = !getenv("GPB_TMA_NOPERSIST");
     if (dalloc(&d_sched, 2)) return 1;
     const long long tiles = (long long)((ny + 1 + TY - 1) / TY) * ((pitch + TZ - 1) / TZ);
+    // planes per work item: 8 (every item pays one extra slot for its x-neighbour plane and a per-item set-up of the masks);
+    // 4 only when there would otherwise be fewer than two items per resident CTA to balance (measured at 150^3 with the
+    // persistent kernels: 2 planes 23.4, 4 planes 25.5, 8 planes 25.3 Gcells/s; 170^3: 33.1 / 33.9 for 4 / 8)
     tma_xchunk = 8;
-    while (tma_xchunk > 2 && tiles * ((nplanes + tma_xchunk - 1) / tma_xchunk) < 12ll * sm_count) tma_xchunk /= 2;
+    if (tiles * ((nplanes + 7) / 8) < 2ll * 2 * sm_count) tma_xchunk = 4;
     if (getenv("GPB_TMA_XCHUNK")) tma_xchunk = std::max(1, atoi(getenv("GPB_TMA_XCHUNK")));
     // work items travel as tile | chunk << 20 through the kernels' item ring
     if (tiles >= (1ll << 20) || (nplanes + tma_xchunk - 1) / tma_xchunk >= (1 << 11)) use_tma = false;
