@@ -251,6 +251,7 @@ struct Solver : SolverBase {
         if (graph) cudaGraphExecDestroy(graph);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamSynchronize(stream);   // cached blocks are handed to the next solver, which runs on another stream
         for (void *p : allocs) g_pool.free(p);
         if (stream) cudaStreamDestroy(stream);
     }
