@@ -287,7 +287,7 @@ struct Solver : SolverBase {
     template <typename IDT>
     int launch_e(int p0, int p1);
     int launch_phase(int phase, int p0, int p1);
-    int launch_sources(int phase);
+    int launch_sources(int phase, int p0, int p1, bool tl_on);
     int launch_begin();
     int launch_snapshots();
     int enqueue_step(bool with_snap);
@@ -924,12 +924,15 @@ int Solver<R>::launch_phase(int phase, int p0, int p1)
 }
 
 template <typename R>
-int Solver<R>::launch_sources(int phase)
+int Solver<R>::launch_sources(int phase, int p0, int p1, bool tl_on)
 {
+    // point sources on the owned planes [p0, p1) (local indices) and, if tl_on, the transmission lines
     if (phase == 0 ? !has_hsrc : !has_esrc) return 0;
-    if (idbytes == 1) k_sources<R, uint8_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls);
-    else if (idbytes == 2) k_sources<R, uint16_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls);
-    else k_sources<R, uint32_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls);
+    const int i_lo = x_start + p0, i_hi = x_start + p1;
+    if (i_hi <= i_lo && !(tl_on && ntl)) return 0;
+    if (idbytes == 1) k_sources<R, uint8_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls, i_lo, i_hi, tl_on ? 1 : 0);
+    else if (idbytes == 2) k_sources<R, uint16_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls, i_lo, i_hi, tl_on ? 1 : 0);
+    else k_sources<R, uint32_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls, i_lo, i_hi, tl_on ? 1 : 0);
     CK(cudaGetLastError());
     ++launches;
     return 0;
@@ -965,9 +968,9 @@ int Solver<R>::enqueue_step(bool with_snap)
     if (launch_begin()) return 1;
     if (with_snap && launch_snapshots()) return 1;
     if (launch_phase(0, 0, nplanes)) return 1;
-    if (launch_sources(0)) return 1;
+    if (launch_sources(0, 0, nplanes, true)) return 1;
     if (launch_phase(1, 0, nplanes)) return 1;
-    if (launch_sources(1)) return 1;
+    if (launch_sources(1, 0, nplanes, true)) return 1;
     return 0;
 }
 
@@ -1048,11 +1051,11 @@ int Solver<R>::profile(int n, double *ms4)
         CK(cudaEventRecord(ev[1], stream));
         if (launch_phase(0, 0, nplanes)) return 1;
         CK(cudaEventRecord(ev[2], stream));
-        if (launch_sources(0)) return 1;
+        if (launch_sources(0, 0, nplanes, true)) return 1;
         CK(cudaEventRecord(ev[3], stream));
         if (launch_phase(1, 0, nplanes)) return 1;
         CK(cudaEventRecord(ev[4], stream));
-        if (launch_sources(1)) return 1;
+        if (launch_sources(1, 0, nplanes, true)) return 1;
         CK(cudaEventRecord(ev[5], stream));
         CK(cudaEventSynchronize(ev[5]));
         float t01, t12, t23, t34, t45;
@@ -1079,13 +1082,15 @@ int Solver<R>::half_step(int phase, int part)
             if (launch_begin() || launch_snapshots()) return 1;
             // boundary plane first (its Hy,Hz feed the right neighbour) so the host can start the halo
             // transfer while the interior runs
-            if (launch_phase(0, nplanes - 1, nplanes)) return 1;
+            // (with the point sources that sit on it: the plane is sent as soon as this part is done)
+            if (launch_phase(0, nplanes - 1, nplanes) || launch_sources(0, nplanes - 1, nplanes, false)) return 1;
         }
-        if (second && (launch_phase(0, 0, nplanes - 1) || launch_sources(0))) return 1;
+        if (second && (launch_phase(0, 0, nplanes - 1) || launch_sources(0, 0, nplanes - 1, true))) return 1;
     } else {
-        if (first && launch_phase(1, 0, 1)) return 1;  // first owned plane: its Ey,Ez feed the left neighbour
+        // first owned plane: its Ey,Ez feed the left neighbour
+        if (first && (launch_phase(1, 0, 1) || launch_sources(1, 0, 1, false))) return 1;
         if (second) {
-            if (launch_phase(1, 1, nplanes) || launch_sources(1)) return 1;
+            if (launch_phase(1, 1, nplanes) || launch_sources(1, 1, nplanes, true)) return 1;
             ++iteration;
         }
     }

@@ -581,10 +581,13 @@ __global__ void k_step_begin(PointParams<R> p, int *iter_cur, int *iter_next, in
 // phase 0 (after H update + H-PML): transmission lines (current), magnetic dipoles   model_build_run.py:440-442
 // phase 1 (after E update + E-PML): voltage sources, transmission lines (voltage), Hertzian dipoles  :458-461
 template <typename R, typename IDT>
-__global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R> *srcs, int ntl, const TLDev<R> *tls)
+__global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R> *srcs, int ntl, const TLDev<R> *tls, int i_lo, int i_hi, int tl_on)
 {
+    // [i_lo, i_hi): global planes whose point sources this launch applies (a sharded half-step applies the sources of its
+    // boundary plane before that plane is sent to the neighbour); tl_on: advance the transmission lines in this launch
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     const int it = *p.iter;
+    if (!tl_on) ntl = 0;
     if (phase == 0) {
         for (int t = 0; t < ntl; ++t) {
             const TLDev<R> &tl = tls[t];
@@ -599,7 +602,7 @@ __global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R>
         }
         for (int s = 0; s < nsrc; ++s) {
             const SrcDev<R> &sc = srcs[s];
-            if (sc.kind != 1 || it < sc.it_first || it > sc.it_last || !pt_owned(p, sc.i)) continue;
+            if (sc.kind != 1 || it < sc.it_first || it > sc.it_last || !pt_owned(p, sc.i) || sc.i < i_lo || sc.i >= i_hi) continue;
             const long long o = pt_off(p, sc.i, sc.j, sc.k);
             const unsigned m = ld_id<IDT>(p.ID[3 + sc.pol], o);
             // sources.py:220-232
@@ -608,7 +611,7 @@ __global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R>
     } else {
         for (int s = 0; s < nsrc; ++s) {
             const SrcDev<R> &sc = srcs[s];
-            if (sc.kind != 2 || it < sc.it_first || it > sc.it_last || !pt_owned(p, sc.i)) continue;
+            if (sc.kind != 2 || it < sc.it_first || it > sc.it_last || !pt_owned(p, sc.i) || sc.i < i_lo || sc.i >= i_hi) continue;
             const long long o = pt_off(p, sc.i, sc.j, sc.k);
             if (sc.hard) {
                 p.F[sc.pol][o] = -sc.wave[it] / sc.f2;  // sources.py:103, 110, 117
@@ -635,7 +638,7 @@ __global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R>
         }
         for (int s = 0; s < nsrc; ++s) {
             const SrcDev<R> &sc = srcs[s];
-            if (sc.kind != 0 || it < sc.it_first || it > sc.it_last || !pt_owned(p, sc.i)) continue;
+            if (sc.kind != 0 || it < sc.it_first || it > sc.it_last || !pt_owned(p, sc.i) || sc.i < i_lo || sc.i >= i_hi) continue;
             const long long o = pt_off(p, sc.i, sc.j, sc.k);
             const unsigned m = ld_id<IDT>(p.ID[sc.pol], o);
             // sources.py:181-193

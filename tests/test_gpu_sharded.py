@@ -91,3 +91,24 @@ def test_nccl_shards_bit_exact_tma_path(tmp_path):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert np.array_equal(np.load(out), ref_rx)
+
+
+def test_nccl_source_on_cut_plane(tmp_path):
+    """A Hertzian dipole on the first owned plane of a rank: with the boundary-first overlap that plane is sent to the left
+    neighbour before the interior is updated, so the source term has to be applied to it first (gpb_half_step part 0)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from sharded_worker import build
+    from gprmax_b200.gpu import device_count
+    n = device_count()
+    if n < 2:
+        pytest.skip('needs at least 2 GPUs')
+    world = 4 if n >= 4 else 2
+    spec = 'synthetic_cut:64,48,40,90'
+    ref_rx, _ = _single(build(spec))
+    assert np.abs(ref_rx).max() > 0
+    out = str(tmp_path / 'rx.npy')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr', '127.0.0.1',
+           '--master-port', '29535', os.path.join(ROOT, 'tests', 'sharded_worker.py'), spec, out, '1']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert np.array_equal(np.load(out), ref_rx)
