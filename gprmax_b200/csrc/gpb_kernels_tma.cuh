@@ -652,7 +652,10 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                     else cp_async_wait0();
                     slot = spf + (size_t)(n % p.pf_depth) * 2 * PORDER * kTmaThreads + tid;
                 }
-                for (int s = 0; s < p.nslabs; ++s) {   // G.pmls order; s is CTA-uniform
+                // slabs any lane of this warp has to apply on this plane, in G.pmls order (warp-uniform: the cooperative z step
+                // needs every lane)
+                for (unsigned todo = __reduce_or_sync(0xffffffffu, pm) | (zact ? 1u << zs : 0u); todo; todo &= todo - 1) {
+                    const int s = __ffs(todo) - 1;
                     if (zact && s == zs) {
                         // ---- cooperative z slab: one cell per lane, both components
                         const SlabDev<R> &sl = p.slab[s];
