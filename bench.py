@@ -181,12 +181,12 @@ def run_single_gpu(args):
         alg_bytes = cells * b_alg / 2.0  # one half-step
         achieved = alg_bytes / t_launch / 1e9
         share = prof[dom] / max(sum(prof.values()), 1e-30)
-        # DRAM bytes per launch from the committed ncu --set full capture of the same workload (profiles/README.md, r1n):
-        # k_update_tma 842.5 MB read + 339 MB written at 300^3 (all PML slabs fused); only quoted for that exact workload
-        traffic = 1.1816e9 if N == 300 else None
+        # DRAM bytes per launch from the committed ncu --set full capture of the same workload (profiles/README.md, r1p):
+        # k_update_tma 843.4 MB read + 338.3 MB written at 300^3 (all PML slabs fused); only quoted for that exact workload
+        traffic = 1.1817e9 if N == 300 else None
         roof = {'bound': 'hbm', 'kernel': 'k_update_tma<PHASE={}> ({}: base update + all six PML slabs in one launch)'.format(1 if dom == 'update_e' else 0, dom),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'traffic_source': 'profiles/r1n_main_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum)',
+                'traffic': traffic, 'traffic_source': 'profiles/r1p_main_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum)',
                 'peak_source': peak_src, 'alg_bytes_per_launch': alg_bytes, 'launch_ms': t_launch * 1e3,
                 'share_of_step': share, 'whole_step_frac': value * 1e6 * b_alg / 1e9 / peak,
                 'kernel_ms_per_iteration': {k: v / nprof_timed for k, v in prof.items()}}
