@@ -423,7 +423,10 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     unsigned smask = 0;
 #pragma unroll
     for (int s = 0; s < kMaxSlabs; ++s)
-        if (s < p.nslabs && (p.zfused || p.slab[s].axis != 2) && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
+        // (slabs that do not meet this tile in (j, k) at all are skipped with a CTA-uniform test)
+        if (s < p.nslabs && (p.zfused || p.slab[s].axis != 2) && valid && p.slab[s].lo[1] < j0 + TY && p.slab[s].hi[1] > j0 && p.slab[s].lo[2] < k0 + TZ &&
+            p.slab[s].hi[2] > k0)
+            smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
     const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u);
     // fast cells: all 4 inside all three update boxes and outside every y- and z-slab footprint; on the planes between the x
     // slabs (p.fast_i0 <= i < p.fast_i1) such a thread needs no masks and no slab logic

@@ -78,11 +78,9 @@ __device__ __forceinline__ JK4 jk4_of(const int *lo, const int *hi, int j, int k
 {
     JK4 r;
     r.j_in = j >= lo[1] && j < hi[1];
-    r.kmask = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (k + q >= lo[2] && k + q < hi[2]) r.kmask |= 1u << q;
-    if (!r.j_in) r.kmask = 0;
+    // cells k + q, q = 0..3, inside [lo2, hi2): bits [max(lo2 - k, 0), min(hi2 - k, 4))
+    const int q0 = max(lo[2] - k, 0), q1 = min(hi[2] - k, 4);
+    r.kmask = (r.j_in && q1 > q0) ? (((1u << q1) - 1u) & ~((1u << q0) - 1u)) : 0u;
     return r;
 }
 
