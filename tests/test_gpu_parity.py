@@ -141,7 +141,7 @@ TMA_FIXTURES = ['pml_HORIPML_1', 'pml_HORIPML_2', 'pml_MRIPML_1', 'pml_MRIPML_2'
 
 
 @pytest.mark.parametrize('name', TMA_FIXTURES)
-@pytest.mark.parametrize('mode', ['tma', 'tma_nopersist', 'tma_pw0', 'tma_tile8x128', 'tma_zsplit', 'tma_znocoop', 'scalar'])
+@pytest.mark.parametrize('mode', ['tma', 'tma_nopersist', 'tma_pw0', 'tma_tile8x128', 'tma_zsplit', 'tma_znocoop', 'tma_ids16', 'tma_ids32', 'v4_ids16', 'scalar'])
 def test_f64_every_kernel_path(name, mode, monkeypatch):
     """The small fixtures normally run on the register-vectorised kernels (the TMA kernels are only selected above
     2.5 M nodes); force each kernel family in turn so that all of them are held to the 1e-10 bar:
@@ -158,6 +158,10 @@ def test_f64_every_kernel_path(name, mode, monkeypatch):
         monkeypatch.setenv('GPB_TMA_ZSPLIT', '1')
     if mode == 'tma_znocoop':
         monkeypatch.setenv('GPB_TMA_ZNOCOOP', '1')
+    if mode.endswith('ids16'):   # 16- / 32-bit device IDs (models with more than 256 / 65536 materials)
+        monkeypatch.setenv('GPB_ID_BYTES', '2')
+    if mode.endswith('ids32'):
+        monkeypatch.setenv('GPB_ID_BYTES', '4')
     if mode == 'tma_tile8x128':
         monkeypatch.setenv('GPB_TMA_TZ', '128')
     if mode == 'scalar':
