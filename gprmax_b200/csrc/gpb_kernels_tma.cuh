@@ -5,16 +5,19 @@
 // latency-bound at ~3.4 TB/s (profiles/r1b_*).  Here the operand planes are staged in shared memory
 // by the Tensor Memory Accelerator instead:
 //   * a CTA owns a TY x TZ tile of (j,k) and marches along x (E phase: +x, H phase: -x);
-//   * for every plane one elected thread issues 9 `cp.async.bulk.tensor.3d` loads (6 field tiles, the
-//     three operand tiles carrying their one-row / one-column halo, and 3 material-ID tiles) into one
-//     stage of a kStages-deep ring; completion is tracked with an mbarrier (expect_tx / complete_tx);
-//     out-of-range halo coordinates are zero-filled by the TMA unit, so there is no edge code;
+//   * for every plane a producer issues 3 `cp.async.bulk.tensor.4d` loads -- the operand triple with its one-row /
+//     one-column halo, the triple being updated and the material-ID triple (each triple is one allocation, so the
+//     component is the 4th tensor dimension) -- into one stage of a kStages-deep ring; completion is tracked with an
+//     mbarrier (expect_tx / complete_tx); out-of-range halo coordinates are zero-filled by the TMA unit: no edge code;
 //   * consumers read 128-bit rows from shared memory, so the j+-1 / k+-1 re-reads never touch L2, and
-//     kStages planes (~30 KB each) are in flight per CTA regardless of register pressure;
+//     kStages planes (~26 KB each) are in flight per CTA regardless of register pressure;
 //   * the x-neighbour plane (i-1 for E, i+1 for H) rides in a register queue as before;
-//   * results go straight from registers to global memory with 128-bit stores.
-// All PML slabs are applied in the same pass: x / y slabs vectorised and warp-uniform, z slabs on the few lanes of a warp that
-// hold the first / last cells of a z row; Phi is prefetched per thread with cp.async (see `prefetch` in the kernel).
+//   * results go straight from registers to global memory with 128-bit stores;
+//   * a consumer warp hands a stage back (one `empty` arrival per warp) only after EVERYTHING it reads from the stage --
+//     operands, own fields, material IDs, and for slab warps the re-reads of the PML corrections -- has been read: the
+//     producer refills the stage at once, and with persistent CTAs the refill may belong to another tile.
+// All PML slabs are applied in the same pass: x / y slabs vectorised and warp-uniform with Phi prefetched per thread by
+// cp.async (`prefetch` in the kernel), z slabs one cell per lane with the corrections handed to the owning thread by shuffle.
 #pragma once
 #include <cuda.h>
 
