@@ -109,10 +109,19 @@ def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    from gprmax_b200.synthetic import bench_model
+    from gprmax_b200.synthetic import bench_model, homogeneous_model
     N = args.size
     sample_iters = args.iters or 12
-    G = bench_model(N, iterations=sample_iters)
+    if args.gpus > 1:
+        # the N-GPU arm runs the sharded lossy-dielectric domain (256 x 2048 x 1024 cells per GPU): the CPU solver gets a
+        # bounded N^3 sample of the same recipe (material, PML, z dipole at the centre)
+        c = N // 2 * 1e-3
+        G = homogeneous_model((N, N, N), iterations=sample_iters, er=6.0, se=0.01, src=(c, c, c), src_pol='z', rxs=[(c + 0.02, c + 0.01, c)])
+        workload = ('bounded sample of the sharded synthetic lossy-dielectric domain (er=6, sigma=0.01, z Hertzian dipole, 10-cell HORIPML): '
+                    '{0}x{0}x{0} cells').format(N)
+    else:
+        G = bench_model(N, iterations=sample_iters)
+        workload = 'tests/benchmarking/bench_{0}x{0}x{0}.in free-space cube, Hertzian dipole, 10-cell HORIPML'.format(N)
     vals, secs = [], []
     for s in range(args.warmup + args.steps):
         v, kind, cores, t = cpu_reference_run(G, sample_iters)
@@ -124,10 +133,9 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': 'FDTD throughput', 'value': value, 'unit': 'Mcells/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(secs) * 1e3), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'tests/benchmarking/bench_{0}x{0}x{0}.in free-space cube, Hertzian dipole, 10-cell HORIPML'.format(N),
-                   'cells': N**3, 'iterations_per_step': sample_iters},
+        'config': {'workload': workload, 'cells': N**3, 'iterations_per_step': sample_iters},
         'cpu_baseline': {'value': value, 'unit': 'Mcells/s', 'cores': cores, 'kind': kind,
-                         'sample': 'first {} of 1559 iterations of bench_{}^3, {} OpenMP threads'.format(sample_iters, N, cores)},
+                         'sample': 'first {} iterations of a {}^3 model, {} OpenMP threads'.format(sample_iters, N, cores)},
         'e2e': {'value': value, 'unit': 'Mcells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
