@@ -87,7 +87,14 @@ class ClockSampler(object):
 
 
 def host_threads():
-    return int(os.environ.get('OMP_NUM_THREADS') or os.cpu_count() or 1)
+    """Threads for the CPU legs: the cores this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers; that
+    is a launcher default, not a property of the host, so it is ignored (GPB_CPU_THREADS overrides)."""
+    if os.environ.get('GPB_CPU_THREADS'):
+        return int(os.environ['GPB_CPU_THREADS'])
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def cpu_reference_run(G, iterations):
@@ -95,36 +102,76 @@ def cpu_reference_run(G, iterations):
     from oracle.solver import have_ref, solve_cpu
     kind = 'reference' if have_ref() else 'port'
     cores = host_threads()
-    # the reference pins its OpenMP threads this way (input_cmds_singleuse.py:78-80)
+    out = solve_cpu(G, kernels='ref' if kind == 'reference' else 'oracle', nthreads=cores, iterations=iterations)
+    mcells = G.nx * G.ny * G.nz * iterations / (out['tsolve'] * 1e6)
+    return mcells, kind, cores, out['tsolve'], out
+
+
+def pin_openmp():
+    """OpenMP environment of the CPU legs, set before the OpenMP runtime loads: all host threads (see host_threads), pinned
+    the way the reference pins them (input_cmds_singleuse.py:78-80)."""
+    os.environ['OMP_NUM_THREADS'] = str(host_threads())
     os.environ.setdefault('OMP_PLACES', 'cores')
     os.environ.setdefault('OMP_PROC_BIND', 'TRUE')
     os.environ.setdefault('OMP_DYNAMIC', 'FALSE')
-    out = solve_cpu(G, kernels='ref' if kind == 'reference' else 'oracle', nthreads=cores, iterations=iterations)
-    mcells = G.nx * G.ny * G.nz * iterations / (out['tsolve'] * 1e6)
-    return mcells, kind, cores, out['tsolve']
+
+
+SLAB = (256, 2048, 1024)   # cells per GPU of the sharded weak-scaling workload (N = 8: BASELINE.json configs[4])
+SLAB_SAMPLE = (64, 1024, 512)   # bounded CPU sample of the same recipe
+
+
+def slab_model(n, iterations, x_range=None, build_id=False):
+    """The sharded workload's recipe on an n = (nx, ny, nz) box: one lossy dielectric (er 6, sigma 0.01 S/m) filling the domain,
+    z-directed Hertzian dipole at the centre, 10-cell HORIPML."""
+    from benchkit.synthetic import homogeneous_model
+    nx, ny, nz = n
+    cx, cy, cz = nx // 2, ny // 2, nz // 2
+    return homogeneous_model(n, iterations=iterations, er=6.0, se=0.01, src=(cx * 1e-3, cy * 1e-3, cz * 1e-3), src_pol='z',
+                             rxs=[(cx * 1e-3, (cy + 20) * 1e-3, cz * 1e-3), ((cx + 7) * 1e-3, (cy + 10) * 1e-3, cz * 1e-3)],
+                             x_range=x_range, build_id=build_id)
+
+
+def bench_grid(N, iterations=None):
+    """tests/benchmarking/bench_NxNxN.in as the drop-in receives it.  Built by the unmodified reference front end when
+    baseline/_ref is present (parse + geometry / material / PML build, stopped at the solve_gpu seam), otherwise by the
+    closed-form builder benchkit/synthetic.py (pinned bit-exactly against the reference's build in tests/test_synthetic.py)."""
+    from benchkit import refmodel
+    if iterations is None and os.environ.get('GPB_BENCH_MODEL', 'reference') == 'reference' and refmodel.reference_available():
+        try:
+            G = refmodel.build_with_reference(refmodel.reference_input('tests/benchmarking/bench_{0}x{0}x{0}.in'.format(N)))
+            return G, 'reference front end (baseline/_ref, gprMax v3.1.7 unmodified) stopped at the solve_gpu seam'
+        except Exception as e:   # e.g. the input file of that size does not exist
+            sys.stderr.write('reference front end unavailable for this model ({}); using benchkit.synthetic\n'.format(e))
+    from benchkit.synthetic import bench_model
+    return bench_model(N, iterations=iterations), 'benchkit.synthetic (closed-form tables, bit-identical to the reference build)'
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path, all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path (its Cython/OpenMP kernels compiled unmodified
+    into oracle/_ref, driven in the reference's order of operations), all host threads, on a bounded sample of the workload
+    the GPU arm runs at this N."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
-    from gprmax_b200.synthetic import bench_model, homogeneous_model
-    N = args.size
+    pin_openmp()
+    from benchkit.synthetic import bench_model
     sample_iters = args.iters or 12
     if args.gpus > 1:
-        # the N-GPU arm runs the sharded lossy-dielectric domain (256 x 2048 x 1024 cells per GPU): the CPU solver gets a
-        # bounded N^3 sample of the same recipe (material, PML, z dipole at the centre)
-        c = N // 2 * 1e-3
-        G = homogeneous_model((N, N, N), iterations=sample_iters, er=6.0, se=0.01, src=(c, c, c), src_pol='z', rxs=[(c + 0.02, c + 0.01, c)])
-        workload = ('bounded sample of the sharded synthetic lossy-dielectric domain (er=6, sigma=0.01, z Hertzian dipole, 10-cell HORIPML): '
-                    '{0}x{0}x{0} cells').format(N)
+        n = SLAB_SAMPLE
+        G = slab_model(n, sample_iters, build_id=True)
+        cells = n[0] * n[1] * n[2]
+        workload = ('bounded sample of the sharded workload ({0} x {1} x {2} cells per GPU x {3} GPUs, lossy dielectric er=6 sigma=0.01, z Hertzian '
+                    'dipole, 10-cell HORIPML): the same recipe on a {4} x {5} x {6} box').format(SLAB[0], SLAB[1], SLAB[2], args.gpus, *n)
+        sample = 'first {} iterations of the {} x {} x {} sample'.format(sample_iters, *n)
     else:
+        N = args.size
         G = bench_model(N, iterations=sample_iters)
-        workload = 'tests/benchmarking/bench_{0}x{0}x{0}.in free-space cube, Hertzian dipole, 10-cell HORIPML'.format(N)
+        cells = N**3
+        workload = 'tests/benchmarking/bench_{0}x{0}x{0}.in: {0}^3 free space, Hertzian dipole, 1 rx, 10-cell HORIPML x6, float32'.format(N)
+        sample = 'first {} of 1559 iterations of the same {}^3 model'.format(sample_iters, N)
     vals, secs = [], []
     for s in range(args.warmup + args.steps):
-        v, kind, cores, t = cpu_reference_run(G, sample_iters)
+        v, kind, cores, t, _ = cpu_reference_run(G, sample_iters)
         if s >= args.warmup:
             vals.append(v)
             secs.append(t)
@@ -133,9 +180,9 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': 'FDTD throughput', 'value': value, 'unit': 'Mcells/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(secs) * 1e3), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload, 'cells': N**3, 'iterations_per_step': sample_iters},
+        'config': {'workload': workload, 'cells': cells, 'iterations_per_step': sample_iters},
         'cpu_baseline': {'value': value, 'unit': 'Mcells/s', 'cores': cores, 'kind': kind,
-                         'sample': 'first {} iterations of a {}^3 model, {} OpenMP threads'.format(sample_iters, N, cores)},
+                         'sample': '{}, {} OpenMP threads (OMP_NUM_THREADS of the launcher ignored: {} usable cores)'.format(sample, cores, cores)},
         'e2e': {'value': value, 'unit': 'Mcells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -143,25 +190,77 @@ def run_reference_arm(args):
     return 0
 
 
+def kernel_source_hash():
+    """sha256 (first 16 hex digits) over the CUDA sources: ties a committed ncu traffic figure to the kernels it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'gprmax_b200', 'csrc')
+    for name in sorted(os.listdir(d)):
+        with open(os.path.join(d, name), 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(N):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, if that capture was taken from
+    the kernels being run (profiles/traffic.json is written by profiles/ncu_traffic.py together with the capture)."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(p):
+        return None, 'no capture committed'
+    with open(p) as f:
+        t = json.load(f)
+    key = 'bench_{}'.format(N)
+    if key not in t:
+        return None, 'no capture of this workload'
+    if t[key].get('kernel_source_hash') != kernel_source_hash():
+        return None, 'capture {} is from other kernel sources (hash {} != {})'.format(t[key].get('file'), t[key].get('kernel_source_hash'), kernel_source_hash())
+    return float(t[key]['dram_bytes_per_launch']), t[key].get('file')
+
+
+def trace_parity(rx, G, ref_outputs, iters, what):
+    """max |gpu - ref| / peak(ref) over the first `iters` samples of every receiver component (rows of fields_outputs.py:81-105)."""
+    from gprmax_b200 import _lib
+    worst, comp = 0.0, None
+    for n, r in enumerate(G.rxs):
+        for name in r.outputs:
+            key = 'rx{}_{}'.format(n, name)
+            if key not in ref_outputs:
+                continue
+            ref = np.asarray(ref_outputs[key], dtype=np.float64)[:iters]
+            mine = rx[_lib.RX_ROWS.index(name), :iters, n].astype(np.float64)
+            peaks = [float(np.abs(np.asarray(ref_outputs[k], dtype=np.float64)[:iters]).max()) for k in ref_outputs
+                     if k.startswith('rx{}_'.format(n)) and k.split('_')[1][0] == name[0]]
+            scale = max(float(np.abs(ref).max()), 0.1 * max(peaks))   # tests/parity.py: numerically-zero components
+            if scale == 0:
+                continue
+            rel = float(np.abs(mine - ref).max()) / scale
+            if rel >= worst:
+                worst, comp = rel, key
+    return {'max_rel': worst, 'component': comp, 'iters': int(iters), 'against': what}
+
+
 def run_single_gpu(args):
-    import ctypes
     from gprmax_b200 import GPU, Solver, solve_gpu
-    from gprmax_b200.synthetic import bench_model
 
     N = args.size
-    G = bench_model(N, iterations=args.iters)
+    G, model_source = bench_grid(N, iterations=args.iters)
     G.gpu = GPU(0)
     G.gpu.get_gpu_info()
     cells = G.nx * G.ny * G.nz
     its = G.iterations
     S = sum(p.thickness * {'x': G.ny * G.nz, 'y': G.nx * G.nz, 'z': G.nx * G.ny}[p.direction[0]] for p in G.pmls)
-    b_alg = B_ALG_FP32 + 32.0 * len(G.cfs) * S / cells  # + PML Phi read+write
+    b_pml = 32.0 * len(G.cfs) * S / cells
+    b_alg = B_ALG_FP32 + b_pml  # + PML Phi read+write (SURVEY.md 8d)
     peak, peak_src = measured_peaks()
 
     # ---- device-resident leg: handle created once, K timed full runs
     sv = Solver(G, device_id=0)
+    kpath = sv.kernel_path
+    idbytes = 1 if G.updatecoeffsE.shape[0] <= 256 else (2 if G.updatecoeffsE.shape[0] <= 65536 else 4)
+    b_moved = 72.0 + 6.0 * idbytes + b_pml   # what the kernels have to move with the narrowed device IDs
     times = []
     launches = 0
+    rx_gpu = None
     with ClockSampler(0) as clocks:
         for s in range(args.warmup + args.steps):
             sv.reset()
@@ -170,6 +269,7 @@ def run_single_gpu(args):
             if s >= args.warmup:
                 times.append(sv.elapsed)
                 launches += sv.kernel_launches - l0
+        rx_gpu = sv.receivers()   # the trace of the last timed run (parity below)
         # per-kernel device times (plain launches, CUDA events on the launching stream)
         sv.reset()
         nprof = min(its, 200)
@@ -177,6 +277,7 @@ def run_single_gpu(args):
         prof = sv.profile(nprof - min(20, nprof)) if nprof > 20 else sv.profile(0)
         nprof_timed = max(nprof - 20, 0)
     clk = clocks.summary()
+    mem = sv.mem_used
     sv.close()
     t_step = float(np.mean(times))
     value = cells * its / (t_step * 1e6)
@@ -189,15 +290,19 @@ def run_single_gpu(args):
         alg_bytes = cells * b_alg / 2.0  # one half-step
         achieved = alg_bytes / t_launch / 1e9
         share = prof[dom] / max(sum(prof.values()), 1e-30)
-        # DRAM bytes per launch from the committed ncu --set full capture of the same workload (profiles/README.md, r1p):
-        # k_update_tma 843.4 MB read + 338.3 MB written at 300^3 (all PML slabs fused); only quoted for that exact workload
-        traffic = 1.1817e9 if N == 300 else None
-        roof = {'bound': 'hbm', 'kernel': 'k_update_tma<PHASE={}> ({}: base update + all six PML slabs in one launch)'.format(1 if dom == 'update_e' else 0, dom),
+        traffic, traffic_src = committed_traffic(N)
+        kname = [k for k in kpath.split() if k.startswith('E:' if dom == 'update_e' else 'H:')][0][2:]
+        roof = {'bound': 'hbm', 'kernel': '{} ({}: base update + PML slabs of one half-step)'.format(kname, dom),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'traffic_source': 'profiles/r1p_main_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum)',
+                'definition': 'ALGORITHMIC bytes of SURVEY.md 8(d) (uint32 IDs: {:.1f} B per cell per step) / launch time; the device narrows IDs to '
+                              '{} byte(s), so the bytes that must actually move are {:.1f} B per cell per step -> achieved_moved / frac_moved'.format(b_alg, idbytes, b_moved),
+                'achieved_moved': cells * b_moved / 2.0 / t_launch / 1e9, 'frac_moved': cells * b_moved / 2.0 / t_launch / 1e9 / peak,
+                'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': peak_src, 'alg_bytes_per_launch': alg_bytes, 'launch_ms': t_launch * 1e3,
                 'share_of_step': share, 'whole_step_frac': value * 1e6 * b_alg / 1e9 / peak,
-                'kernel_ms_per_iteration': {k: v / nprof_timed for k, v in prof.items()}}
+                'kernel_ms_per_iteration': {k: v / nprof_timed for k, v in prof.items()},
+                'note': 'kernel_ms_per_iteration is measured with plain launches and an event pair around every kernel; the graph-replayed '
+                        'iteration of the timed runs (ms_per_step / iterations) is a few % shorter than their sum'}
 
     # ---- end-to-end leg: the public drop-in call from host arrays
     # (1 untimed call, then `steps` timed calls, median reported, all samples kept.  Every call creates a solver from the
@@ -206,7 +311,7 @@ def run_single_gpu(args):
     e2e_t = []
     for s in range(1 + max(args.steps, 3)):
         t0 = time.perf_counter()
-        tsolve, mem = solve_gpu(1, 1, G)
+        tsolve, _ = solve_gpu(1, 1, G)
         dt = time.perf_counter() - t0
         if s >= 1:
             e2e_t.append(dt)
@@ -215,29 +320,79 @@ def run_single_gpu(args):
     h2d = G.ID.nbytes + G.updatecoeffsE.nbytes + G.updatecoeffsH.nbytes + sum(8 * p.ERA.nbytes for p in G.pmls) \
         + sum(s.waveformvalues_wholestep.nbytes for s in G.hertziandipoles) + 12 * len(G.rxs)
     d2h = 9 * its * len(G.rxs) * real
+    rx_e2e = {'rx{}_{}'.format(n, k): np.asarray(v) for n, r in enumerate(G.rxs) for k, v in r.outputs.items()}
 
-    # ---- CPU baseline beside it (bounded sample of the same workload)
-    cpu = None
+    # ---- CPU baseline beside it (bounded sample of the same workload) + parity of the GPU trace against it
+    cpu, parity = None, {}
     if not args.no_cpu:
-        sample = args.cpu_iters
-        Gc = bench_model(N, iterations=sample)
-        v, kind, cores, t = cpu_reference_run(Gc, sample)
+        sample = min(args.cpu_iters, its)
+        v, kind, cores, t, ref_out = cpu_reference_run(G, sample)
         cpu = {'value': v, 'unit': 'Mcells/s', 'cores': cores, 'kind': kind,
                'sample': 'first {} of {} iterations of the same {}^3 model, {} OpenMP threads, {:.1f} s'.format(sample, its, N, cores, t)}
+        parity['prefix'] = trace_parity(rx_gpu, G, ref_out, sample, 'the reference CPU kernels ({}) run here on the same grid, first {} iterations'.format(kind, sample))
+    # the complete trace against the committed golden of the unmodified reference (tests/golden/make_golden.py: bench_300_trace)
+    gold = os.path.join(ROOT, 'tests', 'golden', 'bench_{}_trace_f32.npz'.format(N))
+    if os.path.exists(gold) and args.iters is None:
+        z = np.load(gold)
+        g32 = {k[len('golden_'):]: z[k] for k in z.files}
+        parity['full'] = trace_parity(rx_gpu, G, g32, its, 'tests/golden/bench_{}_trace_f32.npz: all {} iterations, unmodified reference CPU solver'.format(N, its))
+        t64 = gold.replace('_f32.npz', '_f64.npz')
+        if os.path.exists(t64):
+            z64 = np.load(t64)
+            g64 = {k[len('golden_'):]: z64[k] for k in z64.files}
+            e_cuda = trace_parity(rx_gpu, G, g64, its, 'float64 reference')['max_rel']
+            e_ref = max(float(np.abs(g32[k].astype(np.float64) - g64[k]).max()) / max(float(np.abs(g64[k]).max()), 1e-300) for k in g32 if np.abs(g64[k]).max() > 0)
+            parity['full'].update(vs_f64_truth=e_cuda, ref32_vs_f64_truth=e_ref)
+        # the end-to-end call must give the same bits as the device-resident run
+        parity['e2e_equals_resident'] = bool(all(np.array_equal(rx_e2e[k], rx_gpu[_row(k), :, int(k[2:k.index('_')])]) for k in rx_e2e))
+    tol = 1e-4
+    checks = [parity[k]['max_rel'] for k in ('prefix', 'full') if k in parity]
+    ok_a = all(c <= tol for c in checks)
+    ok_b = 'full' in parity and 'vs_f64_truth' in parity['full'] and parity['full']['vs_f64_truth'] <= 3 * parity['full']['ref32_vs_f64_truth'] + 1e-5 \
+        and parity.get('prefix', {'max_rel': 0})['max_rel'] <= tol
+    parity['criterion'] = 'a: max|gpu32 - ref32| <= 1e-4 of trace peak' if ok_a else ('b: |gpu32 - ref64| <= 3 |ref32 - ref64| + 1e-5 (tests/parity.py)' if ok_b else 'FAIL')
+    parity['tolerance'] = tol
+    parity['ok'] = bool(ok_a or ok_b) if checks else None
+
+    # ---- weak-scaling baseline: the per-GPU slab of the sharded runs on this one GPU (so that v_N / (N v_1) is like for like)
+    wsb = None
+    if not args.no_slab and args.iters is None:
+        try:
+            Gs = slab_model(SLAB, 20 * 6)
+            with Solver(Gs, device_id=0) as ss:
+                ts = []
+                for s in range(6):
+                    e0 = ss.elapsed
+                    ss.run(20)
+                    if s >= 3:
+                        ts.append(ss.elapsed - e0)
+                wsb = {'value': SLAB[0] * SLAB[1] * SLAB[2] * 20 / (float(np.mean(ts)) * 1e6), 'unit': 'Mcells/s',
+                       'workload': '{} x {} x {} cells on one GPU: the per-GPU slab of the N > 1 runs, same recipe, 3 x 20 timed iterations'.format(*SLAB),
+                       'kernels': ss.kernel_path}
+        except Exception as e:
+            wsb = {'value': None, 'error': str(e)}
 
     line = {
         'metric': 'FDTD throughput', 'value': value, 'unit': 'Mcells/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'tests/benchmarking/bench_{0}x{0}x{0}.in: {0}^3 free space, Hertzian dipole, 1 rx, 10-cell HORIPML x6, float32'.format(N),
                    'cells': cells, 'iterations_per_step': its, 'l2': 'working set {:.0f} MB >> 126 MB L2 (no flush needed)'.format(mem / 1e6),
-                   'gpu': G.gpu.name, 'alg_bytes_per_cell_step': b_alg},
-        'roofline': roof, 'cpu_baseline': cpu,
+                   'gpu': G.gpu.name, 'alg_bytes_per_cell_step': b_alg, 'model_built_by': model_source, 'kernels': kpath},
+        'roofline': roof, 'cpu_baseline': cpu, 'parity': parity, 'weak_scaling_baseline': wsb,
         'e2e': {'value': e2e_value, 'unit': 'Mcells/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'call': 'gprmax_b200.solve_gpu(1, 1, G) from host arrays', 'seconds_per_call': [round(t, 4) for t in e2e_t], 'statistic': 'median'},
         'gpu_launches': int(launches), 'clocks': clk,
     }
     print(json.dumps(line))
+    if parity['ok'] is False:
+        sys.stderr.write('PARITY FAILURE: {}\n'.format(json.dumps(parity)))
+        return 1
     return 0
+
+
+def _row(key):
+    from gprmax_b200 import _lib
+    return _lib.RX_ROWS.index(key.split('_')[1])
 
 
 def main():
@@ -248,13 +403,15 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--size', type=int, default=300, help='cube side of the single-GPU benchmark model')
     ap.add_argument('--iters', type=int, default=None, help='iterations per step (default: the model\'s own 1559)')
-    ap.add_argument('--cpu-iters', type=int, default=40, help='iterations of the CPU baseline sample')
+    ap.add_argument('--cpu-iters', type=int, default=300, help='iterations of the CPU baseline sample (about 10 s on 32 threads at 300^3)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-slab', action='store_true', help='skip the weak-scaling baseline (the 256 x 2048 x 1024 slab on one GPU)')
     ap.add_argument('--workload', default='auto', choices=['auto', 'slab'], help="'slab' at N=1: run the sharded runs' per-GPU slab on one GPU")
     args = ap.parse_args()
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     if args.impl == 'reference':
         return run_reference_arm(args)
+    pin_openmp()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.gpus > 1 or world > 1 or args.workload == 'slab':
         # N = 1 with --workload slab: the per-GPU slab of the sharded runs on one GPU (weak-scaling baseline)

@@ -23,7 +23,7 @@ import decimal as d
 import numpy as np
 from scipy.constants import c, epsilon_0 as e0, mu_0 as m0
 
-from .model_io import PMLSlab, Receiver, SolverGrid, Source
+from gprmax_b200.model_io import PMLSlab, Receiver, SolverGrid, Source
 
 z0 = np.sqrt(m0 / e0)
 _SCALING = {'constant': 0, 'linear': 1, 'quadratic': 2, 'cubic': 3, 'quartic': 4, 'quintic': 5, 'sextic': 6, 'septic': 7, 'octic': 8}
@@ -170,6 +170,7 @@ def homogeneous_model(n, dcell=0.001, time_window=3e-9, iterations=None, real=np
     real = np.dtype(real)
     dx = dy = dz = float(dcell)
     dt = time_step(dx, dy, dz, nx, ny, nz)
+    window_given = iterations is None
     if iterations is None:
         iterations = int(np.ceil(time_window / dt)) + 1
     G = SolverGrid(nx=nx, ny=ny, nz=nz, dx=dx, dy=dy, dz=dz, dt=dt, iterations=int(iterations),
@@ -206,9 +207,12 @@ def homogeneous_model(n, dcell=0.001, time_window=3e-9, iterations=None, real=np
     sc = [_round_half_down(float(v) / dcell) for v in src]
     wt, amp, freq = waveform
     whole, half = sample_waveform(wt, amp, freq, dt, G.iterations, real)
-    tw = time_window if iterations is None else (G.iterations - 1) * dt
+    # the source stops at the time window (input_cmds_multiuse.py:213-216); with a float window iterations = ceil(tw / dt) + 1,
+    # so the last iteration lies after it and its waveform sample is zero (sources.py:62-63)
+    tw = time_window if window_given else (G.iterations - 1) * dt
+    whole, half = sample_waveform(wt, amp, freq, dt, G.iterations, real, stop=float(tw))
     G.hertziandipoles = [Source(xcoord=sc[0], ycoord=sc[1], zcoord=sc[2], polarisation=src_pol, dl=dcell,
-                                start=0.0, stop=float(max(tw, (G.iterations - 1) * dt)), ID='HertzianDipole',
+                                start=0.0, stop=float(tw), ID='HertzianDipole',
                                 waveformvalues_wholestep=whole, waveformvalues_halfstep=half)]
     for r in (rxs if rxs is not None else [src]):
         rc = [_round_half_down(float(v) / dcell) for v in r]

@@ -181,6 +181,7 @@ struct SolverBase {
     virtual int set_field(int comp, const void *in, size_t bytes) = 0;
     virtual int halo(int which, void **a, void **b, size_t *bytes) = 0;
     virtual int profile(int n, double *ms4) = 0;
+    virtual std::string kernel_path() const = 0;
     int device = 0;
     int iteration = 0;
     double elapsed = 0;
@@ -205,6 +206,9 @@ struct Solver : SolverBase {
     int v4_xchunk = 16;        // planes marched by one thread of the v4 kernels
     int tma_ty = 0, tma_tz = 0, tma_stages = 0, tma_xchunk = 16, tma_pw = 0;   // tile, ring depth, planes per item, dedicated producer warp
     bool tma_persist = true;   // persistent CTAs with a continuous TMA pipeline across work items
+    // diagnostic switches, read from the environment ONCE in build()
+    bool tma_nofast = false, tma_zsplit = false, tma_znocoop = false, tma_nosplit = false;
+    int tma_pf = 2;
     int *d_sched = 0;          // [2] work-item scheduler state of the persistent TMA kernels
     int sm_count = 148;
     TmaMaps4 maps_e, maps_h;
@@ -280,6 +284,7 @@ struct Solver : SolverBase {
     int build(const gpb_model_t &m);
     int setup_pml(const gpb_model_t &m);
     int setup_points(const gpb_model_t &m);
+    int set_smem_attributes();
     void set_boxes();
 
     template <typename IDT>
@@ -308,6 +313,7 @@ struct Solver : SolverBase {
     int set_field(int comp, const void *in, size_t bytes) override;
     int halo(int which, void **a, void **b, size_t *bytes) override;
     int profile(int n, double *ms4) override;
+    std::string kernel_path() const override;
 };
 
 static int choose_pitch(int nzp1)
@@ -720,6 +726,7 @@ int Solver<R>::build(const gpb_model_t &m)
     pp.srcE = srcE; pp.srcH = srcH; pp.iter = d_iter; pp.iterations = iterations;
     pp.dx = (R)m.dx; pp.dy = (R)m.dy; pp.dz = (R)m.dz;
     if (setup_points(m)) return 1;
+    if (set_smem_attributes()) return 1;
     CK(cudaStreamSynchronize(stream));
     tick("sources / receivers");
     return 0;
@@ -759,6 +766,11 @@ int Solver<R>::setup_tma()
     }
     CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));   // (cudaGetDeviceProperties took 3 - 190 ms here)
     tma_persist = !getenv("GPB_TMA_NOPERSIST");
+    tma_nofast = getenv("GPB_TMA_NOFAST") != nullptr;
+    tma_nosplit = getenv("GPB_TMA_NOSPLIT") != nullptr;
+    tma_zsplit = getenv("GPB_TMA_ZSPLIT") != nullptr;
+    tma_znocoop = getenv("GPB_TMA_ZNOCOOP") != nullptr;
+    tma_pf = getenv("GPB_TMA_PF") ? std::max(0, atoi(getenv("GPB_TMA_PF"))) : 2;
     if (dalloc(&d_sched, 2)) return 1;
     const long long tiles = (long long)((ny + 1 + TY - 1) / TY) * ((pitch + TZ - 1) / TZ);
     // planes per work item: 8 (every item pays one extra slot for its x-neighbour plane and a per-item set-up of the masks);
@@ -788,14 +800,15 @@ int Solver<R>::launch_tma(int phase, int p0, int p1)
             if (p.slab[s].minus) p.fast_i0 = std::max(p.fast_i0, p.slab[s].hi[0]);
             else p.fast_i1 = std::min(p.fast_i1, p.slab[s].lo[0]);
         }
-    if (getenv("GPB_TMA_NOFAST")) p.fast_i1 = p.fast_i0;
-    p.zfused = getenv("GPB_TMA_ZSPLIT") ? 0 : 1;
-    p.znocoop = getenv("GPB_TMA_ZNOCOOP") ? 1 : 0;
+    if (tma_nofast) p.fast_i1 = p.fast_i0;
+    p.zfused = tma_zsplit ? 0 : 1;
+    p.znocoop = tma_znocoop ? 1 : 0;
     a.maps = phase == 0 ? &maps_h : &maps_e;
     a.phase = phase;
     a.ty = tma_ty; a.tz = tma_tz; a.stages = tma_stages; a.pw = tma_pw;
     a.idbytes = idbytes;
-    a.pf_max = getenv("GPB_TMA_PF") ? std::max(0, atoi(getenv("GPB_TMA_PF"))) : 2;
+    a.pf_max = tma_pf;
+    a.nosplit = tma_nosplit ? 1 : 0;
     a.sm_count = sm_count;
     a.sched = d_sched;
     a.stream = stream;
@@ -974,32 +987,34 @@ int Solver<R>::enqueue_step(bool with_snap)
     return 0;
 }
 
+// Opt in to more than 48 KB of dynamic shared memory for the kernels that stage the coefficient rows there (models with more
+// than ~2450 materials in float32).  Called once from build(): run(), half_step() and profile() all launch these kernels.
+template <typename R>
+int Solver<R>::set_smem_attributes()
+{
+    if (!(tabsmem && smem_bytes > 48 * 1024)) return 0;
+    const int n = (int)smem_bytes;
+#define GPB_OPTIN(k) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, n))
+#define GPB_OPTIN_IDT(IDT)                      \
+    GPB_OPTIN((k_update_h4<R, IDT, true>));        \
+    GPB_OPTIN((k_update_e4<R, IDT, true, false>)); \
+    GPB_OPTIN((k_update_e4<R, IDT, true, true>));  \
+    GPB_OPTIN((k_update_h<R, IDT, true>));         \
+    GPB_OPTIN((k_update_e<R, IDT, true, false>));  \
+    GPB_OPTIN((k_update_e<R, IDT, true, true>))
+    GPB_OPTIN_IDT(uint8_t);
+    GPB_OPTIN_IDT(uint16_t);
+    GPB_OPTIN_IDT(uint32_t);
+#undef GPB_OPTIN_IDT
+#undef GPB_OPTIN
+    return 0;
+}
+
 template <typename R>
 int Solver<R>::run(int n)
 {
     CK(cudaSetDevice(device));
     if (n < 0 || iteration + n > iterations) return fail("cannot run %d iterations from %d: model has %d", n, iteration, iterations);
-    if (tabsmem && smem_bytes > 48 * 1024) {
-        // opt in to large dynamic shared memory for the coefficient rows
-        cudaFuncSetAttribute(k_update_h4<R, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_h4<R, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_h4<R, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e4<R, uint8_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e4<R, uint16_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e4<R, uint32_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e4<R, uint8_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e4<R, uint16_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e4<R, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_h<R, uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_h<R, uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_h<R, uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e<R, uint8_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e<R, uint16_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e<R, uint32_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e<R, uint8_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e<R, uint16_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cudaFuncSetAttribute(k_update_e<R, uint32_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    }
     if (use_graph && !graph && n > 1) {
         // the step is identical every iteration (the iteration index lives on the device), so it is
         // captured once and replayed: one graph launch per time step instead of 4-6 kernel launches
@@ -1032,6 +1047,22 @@ int Solver<R>::run(int n)
     elapsed += ms * 1e-3;
     CK(cudaGetLastError());
     return 0;
+}
+
+// Which kernel family each half-step runs on ("H:<kernel> E:<kernel>"), for logs and the bench line
+template <typename R>
+std::string Solver<R>::kernel_path() const
+{
+    auto name = [&](int phase) -> std::string {
+        if (use_tma && !(phase == 1 && maxpoles)) {
+            char b[96];
+            snprintf(b, sizeof b, "k_update_tma<%dx%d,PHASE=%d>", tma_ty, tma_tz, phase);
+            return b;
+        }
+        if (use_v4) return phase == 0 ? "k_update_h4" : (maxpoles ? "k_update_e4<DISP>" : "k_update_e4");
+        return phase == 0 ? "k_update_h" : (maxpoles ? "k_update_e<DISP>" : "k_update_e");
+    };
+    return "H:" + name(0) + " E:" + name(1);
 }
 
 // Per-kernel device times of `n` iterations launched WITHOUT the graph, CUDA events between the
@@ -1299,6 +1330,14 @@ int gpb_get_field(gpb_handle h, int comp, void *out, size_t bytes) { NEED(h); if
 int gpb_set_field(gpb_handle h, int comp, const void *in, size_t bytes) { NEED(h); if (!in) return fail("null argument"); return h->impl->set_field(comp, in, bytes); }
 int gpb_halo(gpb_handle h, int which, void **a, void **b, size_t *bytes) { NEED(h); if (!a || !b || !bytes) return fail("null argument"); return h->impl->halo(which, a, b, bytes); }
 int gpb_profile(gpb_handle h, int n_iters, double *ms4) { NEED(h); if (!ms4) return fail("null argument"); return h->impl->profile(n_iters, ms4); }
+int gpb_kernel_path(gpb_handle h, char *buf, size_t buf_bytes)
+{
+    NEED(h);
+    if (!buf || !buf_bytes) return fail("null argument");
+    const std::string s = h->impl->kernel_path();
+    snprintf(buf, buf_bytes, "%s", s.c_str());
+    return 0;
+}
 int gpb_stream(gpb_handle h, void **s) { NEED(h); if (!s) return fail("null argument"); *s = (void *)h->impl->stream; return 0; }
 int gpb_synchronize(gpb_handle h)
 {

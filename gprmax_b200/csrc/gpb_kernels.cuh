@@ -15,8 +15,9 @@
 //   * one thread per (j,k) column of a plane, marching XCHUNK planes along x with a register queue
 //     for the i-1 (E phase) / i+1 (H phase) operands -> every operand array is read once per phase;
 //   * the CFS-PML slab corrections are fused into the same pass (no extra sweeps over E/H/ID; the
-//     only extra traffic is the Phi state), applied in G.pmls order exactly like the slab-by-slab
-//     reference sequence;
+//     only extra traffic is the Phi state); on edge / corner cells the x and y slabs are applied in
+//     G.pmls order and the z slabs after them -- one order for every kernel family, a last-ulp
+//     difference from the reference's x0,y0,z0,xmax,ymax,zmax sequence;
 //   * dispersive part B of step n is folded into part A of step n+1 (E is untouched in between),
 //     removing one full pass over E, ID and T per step;
 //   * coefficient rows live in shared memory (no constant-cache serialisation with many materials).
@@ -303,8 +304,10 @@ __global__ void __launch_bounds__(kThreads) k_update_h(const PhaseParams<R> p)
             hz = upd3(c.a, hz, -c.bx, dEy_dx, c.by, dEx_dy);
             wz = true;
         }
-        for (int s = 0; s < p.nslabs; ++s) {
+        for (int s2 = 0; s2 < 2 * p.nslabs; ++s2) {   // x / y slabs in G.pmls order, then the z slabs (as in every kernel family)
+            const int s = s2 < p.nslabs ? s2 : s2 - p.nslabs;
             const SlabDev<R> &sl = p.slab[s];
+            if ((sl.axis == 2) != (s2 >= p.nslabs)) continue;
             if (!in_box<R>(sl.lo, sl.hi, i, j, k)) continue;
             const int a = sl.axis;
             const int pos = (a == 0) ? i : (a == 1) ? j : k;
@@ -440,8 +443,10 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
             }
             wz = true;
         }
-        for (int s = 0; s < p.nslabs; ++s) {
+        for (int s2 = 0; s2 < 2 * p.nslabs; ++s2) {   // x / y slabs in G.pmls order, then the z slabs (as in every kernel family)
+            const int s = s2 < p.nslabs ? s2 : s2 - p.nslabs;
             const SlabDev<R> &sl = p.slab[s];
+            if ((sl.axis == 2) != (s2 >= p.nslabs)) continue;
             if (!in_box<R>(sl.lo, sl.hi, i, j, k)) continue;
             const int a = sl.axis;
             const int pos = (a == 0) ? i : (a == 1) ? j : k;

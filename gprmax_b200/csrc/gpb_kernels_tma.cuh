@@ -476,8 +476,16 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     }
     const bool pf = smask6 != 0u && p.pf_depth > 0;
     auto i_of = [&](int n) { return p.x_start + (PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1)) - 1; };
-    auto prefetch = [&](V4<R> *slot, unsigned pmn, int ii) {   // Phi of the lowest-numbered slab in pmn at plane ii -> my slot
-        const SlabDev<R> &sl = p.slab[__ffs(pmn) - 1];
+    // Order of the slab corrections on a cell: x and y slabs in G.pmls order, then the z slabs -- the same order in every
+    // kernel family (the register-vectorised path applies its z slabs in a second kernel, k_pml_slabs), so that edge and
+    // corner cells, which take two or three corrections, get the same bits whichever family a grid or a shard runs on.
+    unsigned zbits = 0;
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s)
+        if (s < p.nslabs && p.slab[s].axis == 2) zbits |= 1u << s;
+    auto first_of = [&](unsigned m) { return __ffs((m & ~zbits) ? (m & ~zbits) : m) - 1; };
+    auto prefetch = [&](V4<R> *slot, unsigned pmn, int ii) {   // Phi of the first slab (in application order) of pmn at plane ii -> my slot
+        const SlabDev<R> &sl = p.slab[first_of(pmn)];
         const R *phi = sl.phi + ((long long)(ii - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
         for (int q = 0; q < 2 * PORDER; ++q) cp_async_v4<R>(slot + q * kTmaThreads, phi + q * sl.ostride);
     };
@@ -658,9 +666,11 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                     else cp_async_wait0();
                     slot = spf + (size_t)(n % p.pf_depth) * 2 * PORDER * kTmaThreads + tid;
                 }
-                // slabs any lane of this warp has to apply on this plane, in G.pmls order (warp-uniform: the cooperative z step
-                // needs every lane)
-                for (unsigned todo = __reduce_or_sync(0xffffffffu, pm) | (zact ? 1u << zs : 0u); todo; todo &= todo - 1) {
+                // slabs any lane of this warp has to apply on this plane: x / y slabs in G.pmls order, then the z slabs
+                // (warp-uniform: the cooperative z step needs every lane)
+                const unsigned wtodo = __reduce_or_sync(0xffffffffu, pm) | (zact ? 1u << zs : 0u);
+                for (int zpass = 0; zpass < 2; ++zpass)
+                for (unsigned todo = wtodo & (zpass ? zbits : ~zbits); todo; todo &= todo - 1) {
                     const int s = __ffs(todo) - 1;
                     if (zact && s == zs) {
                         // ---- cooperative z slab: one cell per lane, both components

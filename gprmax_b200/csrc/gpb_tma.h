@@ -27,6 +27,7 @@ struct TmaLaunch {
     int ty, tz, stages, pw;   // tile, ring depth, dedicated producer warp
     int idbytes;              // 1, 2, 4
     int pf_max;               // upper bound on the Phi prefetch distance (GPB_TMA_PF)
+    int nosplit;              // no half-size items at the end of a persistent launch (GPB_TMA_NOSPLIT)
     int sm_count;
     int *sched;               // [2] work-item scheduler state
     cudaStream_t stream;

@@ -45,7 +45,7 @@ static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
     // persistent: as many CTAs as fit on the GPU at once (2 per SM for fp32), pulling (tile, chunk) items from a.sched
     const int resident = (sizeof(R) == 4 ? GPB_TMA_CTAS : 1) * a.sm_count;
     // persistent launches hand the last ~wave of chunks out in halves (chunk_range)
-    const int nsplit = (p.persist && p.xchunk >= 4 && !getenv("GPB_TMA_NOSPLIT")) ? std::min(nchunks, (resident + tiles - 1) / tiles + 1) : 0;
+    const int nsplit = (p.persist && p.xchunk >= 4 && !a.nosplit) ? std::min(nchunks, (resident + tiles - 1) / tiles + 1) : 0;
     const dim3 grid = p.persist ? dim3((unsigned)std::min(tiles * (nchunks + nsplit), resident)) : dim3((unsigned)tiles, (unsigned)nchunks);
     cudaError_t e;
     if (a.phase == 0) {

@@ -221,7 +221,7 @@ def bench_sharded(args):
     homogeneous lossy-dielectric domain (BASELINE.json configs[4] at N = 8)."""
     import torch
     import torch.distributed as dist
-    from .synthetic import homogeneous_model
+    from benchkit.synthetic import homogeneous_model
 
     # stdout carries exactly one JSON line: whatever libraries print to file descriptor 1 ("NCCL version ...", NCCL_DEBUG=INFO
     # output) is sent to stderr, and the JSON line is written to the saved descriptor at the end

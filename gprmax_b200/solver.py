@@ -208,6 +208,12 @@ class Solver(object):
         self._ck(self.L.gpb_profile(self.h, int(n), ms))
         return dict(begin=ms[0], update_h=ms[1], update_e=ms[2], sources=ms[3])
 
+    @property
+    def kernel_path(self):
+        buf = C.create_string_buffer(256)
+        self._ck(self.L.gpb_kernel_path(self.h, buf, 256))
+        return buf.value.decode()
+
     def reset(self):
         self._ck(self.L.gpb_reset(self.h))
 

@@ -152,6 +152,9 @@ int gpb_reset(gpb_handle h);                            /* zero fields / PML / T
 /* Measurement aid: advance n_iters iterations with plain launches and CUDA events between the
  * kernels; ms4 = device milliseconds {step prologue, H update, E update, source kernels} summed. */
 int gpb_profile(gpb_handle h, int n_iters, double *ms4);
+/* Which kernel each half-step runs on, e.g. "H:k_update_tma<14x64,PHASE=0> E:k_update_tma<14x64,PHASE=1>" (the
+ * library picks the TMA-staged, register-vectorised or scalar family from the grid size). */
+int gpb_kernel_path(gpb_handle h, char *buf, size_t buf_bytes);
 
 /* ---- sharded stepping (one handle per x-slab; the host moves the halo planes between calls) ----
  * phase 0: rx store + snapshots + H half-step (needs the Ey,Ez ghost plane at x_start+nx_planes)

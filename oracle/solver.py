@@ -212,7 +212,6 @@ class State(object):
     """Host arrays of one run, laid out exactly as the reference holds them."""
 
     def __init__(self, G, kernels):
-        from gprmax_b200.model_io import grid_maxpoles  # attribute helper only (no compute)
         real = np.dtype(G.updatecoeffsE.dtype)
         cplx = np.dtype(np.complex64 if real == np.float32 else np.complex128)
         self.real, self.cplx = real, cplx
@@ -223,7 +222,10 @@ class State(object):
         self.cH = np.ascontiguousarray(G.updatecoeffsH, dtype=real)
         for n in ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz'):
             setattr(self, n, np.zeros(shp, dtype=real))
-        self.maxpoles = grid_maxpoles(G)
+        # Material.maxpoles (materials.py:28) = updatecoeffsdispersive.shape[1] / 3 (grid.py:190)
+        mp = getattr(G, 'maxpoles', None)
+        ucd = getattr(G, 'updatecoeffsdispersive', None)
+        self.maxpoles = int(mp) if mp is not None else (int(ucd.shape[1] // 3) if ucd is not None else 0)
         if self.maxpoles:
             self.cdc = np.ascontiguousarray(G.updatecoeffsdispersive, dtype=cplx)
             self.cd = self.cdc.view(real)

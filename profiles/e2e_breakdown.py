@@ -4,7 +4,7 @@ sys.path.insert(0, ".")
 import numpy as np
 from gprmax_b200 import GPU, Solver, solve_gpu
 from gprmax_b200.solver import PackedModel, store_results
-from gprmax_b200.synthetic import bench_model
+from benchkit.synthetic import bench_model
 G = bench_model(300)
 G.gpu = GPU(0); G.gpu.get_gpu_info()
 for rep in range(3):

@@ -2,7 +2,7 @@ import sys
 sys.path.insert(0, ".")
 import numpy as np
 from gprmax_b200 import Solver
-from gprmax_b200.synthetic import bench_model
+from benchkit.synthetic import bench_model
 for size in (200, 300):
     G = bench_model(size, real=np.float64, iterations=200)
     sv = Solver(G, device_id=0)

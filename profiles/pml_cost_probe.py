@@ -2,7 +2,7 @@
 import sys
 sys.path.insert(0, ".")
 from gprmax_b200 import Solver
-from gprmax_b200.synthetic import homogeneous_model
+from benchkit.synthetic import homogeneous_model
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 its = 300
 for label, keep in (('all six slabs', 'xyz'), ('x slabs only', 'x'), ('y slabs only', 'y'), ('z slabs only', 'z'), ('no PML', '')):

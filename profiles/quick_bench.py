@@ -2,7 +2,7 @@
 import sys
 sys.path.insert(0, ".")
 from gprmax_b200 import Solver
-from gprmax_b200.synthetic import bench_model
+from benchkit.synthetic import bench_model
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 its = int(sys.argv[2]) if len(sys.argv) > 2 else 400
 G = bench_model(size, iterations=its)

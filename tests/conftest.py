@@ -25,7 +25,7 @@ def golden_path(name, variant='f32'):
 
 
 # full-size fixtures of BASELINE.json configs 3 and 4: used by dedicated GPU tests only (minutes on the CPU oracle)
-BIG = ('bscan_gssi_trace1', 'heterogeneous_soil_full')
+BIG = ('bscan_gssi_trace1', 'heterogeneous_soil_full', 'bench_300_trace')
 
 
 def golden_names(variant='f32'):

@@ -32,12 +32,15 @@ REF = os.environ.get('GPRMAX_REFERENCE', '/root/reference')
 MODELS = {}
 
 
-def ref_file(name, rel, precisions=('f32', 'f64'), append='', replace=None):
-    MODELS[name] = dict(rel=rel, text=None, precisions=precisions, append=append, replace=replace or {})
+def ref_file(name, rel, precisions=('f32', 'f64'), append='', replace=None, trace_only=(), suffix=None):
+    """trace_only: precisions for which only the reference's traces are stored (no second copy of a big grid);
+    suffix: file name suffix per precision when it is not the precision itself."""
+    MODELS[name] = dict(rel=rel, text=None, precisions=precisions, append=append, replace=replace or {},
+                        trace_only=tuple(trace_only), suffix=suffix or {})
 
 
 def inline(name, text, precisions=('f32', 'f64')):
-    MODELS[name] = dict(rel=None, text=text, precisions=precisions, append='', replace={})
+    MODELS[name] = dict(rel=None, text=text, precisions=precisions, append='', replace={}, trace_only=(), suffix={})
 
 
 # --- the reference's own basic test models (tests/test_models.py:47) ----------------------
@@ -135,6 +138,20 @@ ref_file('heterogeneous_soil_small', 'user_models/heterogeneous_soil.in', replac
     '#geometry_view': '##geometry_view',
 })
 
+# --- FULL-SIZE fixtures of BASELINE.json configs 2-4 (minutes each on 8 cores; used by dedicated GPU tests) ----------
+# config 2: the headline benchmark model itself, all 1559 iterations -- only the reference's receiver trace is stored
+# (gprmax_b200.synthetic.bench_model rebuilds the grid bit-identically, tests/test_synthetic.py)
+ref_file('bench_300_trace', 'tests/benchmarking/bench_300x300x300.in', precisions=('f32', 'f64'), trace_only=('f32', 'f64'))
+# config 3 at full size: heterogeneous_soil.in with explicit fractal seeds (the shipped file has none, so its geometry
+# differs from run to run); float64 run stored as traces only ("truth" for compare_f32_with_truth)
+ref_file('heterogeneous_soil_full', 'user_models/heterogeneous_soil.in', replace={
+    '#fractal_box: 0 0 0 0.15 0.15 0.070 1.5 1 1 1 50 my_soil my_soil_box': '#fractal_box: 0 0 0 0.15 0.15 0.070 1.5 1 1 1 50 my_soil my_soil_box 7',
+    '#add_surface_roughness: 0 0 0.070 0.15 0.15 0.070 1.5 1 1 0.065 0.080 my_soil_box': '#add_surface_roughness: 0 0 0.070 0.15 0.15 0.070 1.5 1 1 0.065 0.080 my_soil_box 3',
+    '#geometry_view': '##geometry_view',
+}, trace_only=('f64',), suffix={'f64': 'f64_truth'})
+# config 4: trace 1 of the GSSI 1.5 GHz B-scan (current_model_run = 1), the reference's own input file unchanged
+ref_file('bscan_gssi_trace1', 'user_models/cylinder_Bscan_GSSI_1500.in', precisions=('f32',))
+
 
 def model_text(spec):
     if spec['text'] is not None:
@@ -159,6 +176,9 @@ def generate(name, variant, gprMax, outdir=HERE):
     def hooked(cur, end, G):
         from gprMax.materials import Material
         G.maxpoles = Material.maxpoles
+        if os.environ.get('GOLDEN_GEOMETRY_ONLY'):
+            cap['G'], cap['tl0'] = G, []
+            return 0.0
         # TL start state must be captured before the loop mutates it
         cap['tl0'] = [(t.voltage[:t.nl].copy(), t.current[:t.nl].copy(), t.abcv0, t.abcv1) for t in G.transmissionlines]
         cap['G'] = G
@@ -194,8 +214,18 @@ def generate(name, variant, gprMax, outdir=HERE):
         from gprMax._version import __version__
         meta = dict(reference_version=__version__, source=spec['rel'] or 'inline (tests/golden/make_golden.py)',
                     variant=variant, numpy=np.__version__)
-        path = os.path.join(outdir, '{}_{}.npz'.format(name, variant))
-        save_model(G, path, golden=golden, meta=meta)
+        path = os.path.join(outdir, '{}_{}.npz'.format(name, spec['suffix'].get(variant, variant)))
+        if os.environ.get('GOLDEN_GEOMETRY_ONLY'):
+            # regenerate only the built grid and compare it with the committed fixture (bit-exact ID / tables)
+            from gprmax_b200.model_io import load_model
+            Gold, _ = load_model(path)
+            same = all(np.array_equal(np.asarray(getattr(G, a)), np.asarray(getattr(Gold, a))) for a in ('ID', 'updatecoeffsE', 'updatecoeffsH'))
+            print('wrote nothing: rebuilt grid {} the committed {}'.format('MATCHES' if same else 'DIFFERS FROM', os.path.basename(path)))
+            return
+        if variant in spec['trace_only']:
+            np.savez_compressed(path, **{'golden_' + k: v for k, v in golden.items()})
+        else:
+            save_model(G, path, golden=golden, meta=meta)
         print('wrote {} ({:.1f} kB)'.format(path, os.path.getsize(path) / 1e3))
     finally:
         mbr.solve_cpu = orig

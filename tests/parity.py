@@ -6,6 +6,9 @@ at that receiver is scaled by that strongest peak instead: such traces are numer
 symmetry and only carry the rounding noise of the big components (in the reference as well --
 its FMA and non-FMA builds differ by more than 1e-4 of such a trace's own peak).
 """
+import json
+import os
+
 import numpy as np
 
 TOL = {'float32': 1e-4, 'float64': 1e-10}
@@ -35,7 +38,7 @@ def trace_scale(golden, key):
     return peak
 
 
-def compare_traces(result, golden, dtype, tol=None, keys=None):
+def compare_traces(result, golden, dtype, tol=None, keys=None, model=None):
     """Returns (worst_ratio, report) where ratio = max|delta| / (tol * scale)."""
     tol = TOL[np.dtype(dtype).name] if tol is None else tol
     worst, lines = 0.0, []
@@ -51,6 +54,8 @@ def compare_traces(result, golden, dtype, tol=None, keys=None):
         else:
             ratio = err / (tol * scale)
         worst = max(worst, ratio)
+        if model:
+            _log(dict(kind='direct', model=model, dtype=np.dtype(dtype).name, key=key, rel=err / scale if scale else 0.0, tol=tol))
         lines.append('{:>14s} peak {:.3e} err {:.3e} rel {:.2e}'.format(key, scale, err, err / scale if scale else 0))
     return worst, '\n'.join(lines)
 
@@ -81,7 +86,15 @@ def oracle_outputs_as_golden(G, o):
     return out
 
 
-def compare_f32_with_truth(result, golden32, golden64, keys=None):
+def _log(rec):
+    """GPB_PARITY_LOG=<file>: one JSON line per compared trace (summarised into profiles/parity_r2.json)."""
+    path = os.environ.get('GPB_PARITY_LOG')
+    if path:
+        with open(path, 'a') as f:
+            f.write(json.dumps(rec) + '\n')
+
+
+def compare_f32_with_truth(result, golden32, golden64, keys=None, model=None):
     """float32 acceptance on one model.  A trace passes when EITHER
         (a) max|cuda32 - ref32| <= 1e-4 * scale                      (the north_star bar), OR
         (b) max|cuda32 - ref64| <= 3 * max|ref32 - ref64| + 1e-5 * scale
@@ -113,6 +126,8 @@ def compare_f32_with_truth(result, golden32, golden64, keys=None):
         a = e_direct <= 1e-4
         b = e_cuda <= 3.0 * e_ref + 1e-5
         ok &= (a or b)
+        _log(dict(kind='f32_with_truth', model=model, key=key, cuda32_vs_ref32=e_direct, cuda32_vs_ref64=e_cuda, ref32_vs_ref64=e_ref,
+                  criterion='a' if a else ('b' if b else 'FAIL')))
         lines.append('{:>14s} |cuda32-ref32| {:.2e}  |cuda32-ref64| {:.2e}  |ref32-ref64| {:.2e}  {}'.format(
             key, e_direct, e_cuda, e_ref, 'a' if a else ('b' if b else 'FAIL')))
     return ok, '\n'.join(lines)

@@ -15,7 +15,7 @@ def build(spec):
     from gprmax_b200.model_io import load_model
     if not spec.startswith('synthetic'):
         return load_model(spec)[0]
-    from gprmax_b200.synthetic import homogeneous_model
+    from benchkit.synthetic import homogeneous_model
     nx, ny, nz, its = [int(v) for v in spec.split(':')[1].split(',')]
     if spec.startswith('synthetic_cut:'):
         # y-directed Hertzian dipole ON the first plane of the rank that owns the middle of the domain for 2 and 4 ranks: its

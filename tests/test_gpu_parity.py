@@ -30,7 +30,7 @@ def test_f64_against_reference_golden(name):
     from gprmax_b200.model_io import load_model
     G, golden = load_model(golden_path(name, 'f64'))
     out = _solve(G)
-    worst, rep = compare_traces(out, golden, np.float64, tol=tolerance(G, np.float64))
+    worst, rep = compare_traces(out, golden, np.float64, tol=tolerance(G, np.float64), model=name)
     print(rep)
     assert worst <= 1.0, rep
 
@@ -42,11 +42,11 @@ def test_f32_against_reference_golden(name):
     out = _solve(G)
     if os.path.exists(golden_path(name, 'f64')):
         _, golden64 = load_model(golden_path(name, 'f64'))
-        ok, rep = compare_f32_with_truth(out, golden, golden64)
+        ok, rep = compare_f32_with_truth(out, golden, golden64, model=name)
         print(rep)
         assert ok, rep
     else:
-        worst, rep = compare_traces(out, golden, np.float32)
+        worst, rep = compare_traces(out, golden, np.float32, model=name)
         print(rep)
         assert worst <= 1.0, rep
 
@@ -98,6 +98,26 @@ def test_restart_and_chunked_run_bit_identical():
     assert np.array_equal(a, b)
 
 
+def test_config2_bench_300_full_trace():
+    """BASELINE.json configs[1], the headline benchmark at its own size: tests/benchmarking/bench_300x300x300.in, all 1559
+    iterations, against the trace of the unmodified reference CPU solver (tests/golden/make_golden.py `bench_300_trace`, float32
+    and float64 runs, 3 and 6 minutes on 8 cores).  The grid is rebuilt by benchkit.synthetic (bit-identical to the reference
+    build) -- or by the reference front end itself when baseline/_ref is present."""
+    p32, p64 = golden_path('bench_300_trace', 'f32'), golden_path('bench_300_trace', 'f64')
+    if not (os.path.exists(p32) and os.path.exists(p64)):
+        pytest.skip('fixture not present')
+    from benchkit.synthetic import bench_model
+    z32, z64 = np.load(p32), np.load(p64)
+    golden = {k[len('golden_'):]: z32[k] for k in z32.files}
+    golden64 = {k[len('golden_'):]: z64[k] for k in z64.files}
+    G = bench_model(300)
+    assert G.iterations == 1559 and len(golden['rx0_Ex']) == 1559
+    out = _solve(G)
+    ok, rep = compare_f32_with_truth(out, golden, golden64, model='bench_300 (config 2, full size, 1559 iterations)')
+    print(rep)
+    assert ok, rep
+
+
 def test_config4_gssi_bscan_trace(tmp_path):
     """BASELINE.json configs[3]: user_models/cylinder_Bscan_GSSI_1500.in, trace 1 of the B-scan at full size
     (480 x 148 x 235 cells, 3117 iterations, GSSI 1.5 GHz antenna model: 24 materials, PEC plates, a 230-ohm
@@ -111,7 +131,7 @@ def test_config4_gssi_bscan_trace(tmp_path):
     t0 = time.perf_counter()
     out = _solve(G)
     print('config 4 trace: {:.2f} s end to end, {} cells x {} iterations'.format(time.perf_counter() - t0, G.nx * G.ny * G.nz, G.iterations))
-    worst, rep = compare_traces(out, golden, np.float32)
+    worst, rep = compare_traces(out, golden, np.float32, model='bscan_gssi_trace1 (config 4, full size)')
     print(rep)
     assert worst <= 1.0, rep
 
@@ -131,7 +151,7 @@ def test_config3_heterogeneous_soil_full_size():
     t0 = time.perf_counter()
     out = _solve(G)
     print('config 3: {:.2f} s end to end, {} cells x {} iterations, {} materials'.format(time.perf_counter() - t0, G.nx * G.ny * G.nz, G.iterations, G.updatecoeffsE.shape[0]))
-    ok, rep = compare_f32_with_truth(out, golden, golden64)
+    ok, rep = compare_f32_with_truth(out, golden, golden64, model='heterogeneous_soil_full (config 3, full size)')
     print(rep)
     assert ok, rep
 
@@ -183,10 +203,12 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
     import sys
     sys.path.insert(0, sys_path)
     from gprmax_b200 import Solver
-    from gprmax_b200.synthetic import homogeneous_model, material_rows
-    nx, ny, nz, its = 160, 144, 128, 30
-    G = homogeneous_model((nx, ny, nz), iterations=its, er=6.0, se=0.01, src=(nx // 2 * 1e-3, ny // 2 * 1e-3, nz // 2 * 1e-3), src_pol='z',
-                          rxs=[((nx // 2 + 3) * 1e-3, (ny // 2 + 2) * 1e-3, nz // 2 * 1e-3)])
+    from benchkit.synthetic import homogeneous_model, material_rows
+    nx, ny, nz, its = 160, 144, 128, 70
+    # the source sits 3 cells outside the x0 / ymax / z0 PML slabs, so that within the run a non-zero field fills the edges and
+    # the corner where two and three slab corrections hit the same cell (every family must apply them in the same order)
+    G = homogeneous_model((nx, ny, nz), iterations=its, er=6.0, se=0.01, src=(13e-3, (ny - 13) * 1e-3, 13e-3), src_pol='z',
+                          rxs=[(5e-3, (ny - 4) * 1e-3, 3e-3), (16e-3, (ny - 15) * 1e-3, 14e-3)])
     real = G.updatecoeffsE.dtype
     rows = [material_rows(er, se, 1.0, 0.0, G.dx, G.dy, G.dz, G.dt, real) for er, se in ((3.0, 0.001), (9.0, 0.02), (4.5, 0.0), (12.0, 0.05))]
     G.updatecoeffsE = np.concatenate([G.updatecoeffsE, np.stack([r[0] for r in rows])])
@@ -205,6 +227,9 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
 
     ref = run({'GPB_NO_TMA': '1'})
     assert np.abs(ref[-1]).max() > 0
+    # the field has reached the x0 / ymax / z0 corner region of the PML (all three slabs overlap there)
+    for c in range(6):
+        assert np.abs(ref[c][1:9, ny - 9:ny - 1, 1:9]).max() > 0, c
     for env in ({}, {}, {'GPB_TMA_NOPERSIST': '1'}, {'GPB_TMA_PW': '0'}, {'GPB_TMA_ZSPLIT': '1'}, {'GPB_TMA_ZNOCOOP': '1'}):
         out = run(env)
         for c, (a, b) in enumerate(zip(out, ref)):

@@ -7,7 +7,7 @@ import pytest
 
 from conftest import golden_path
 from gprmax_b200.model_io import load_model
-from gprmax_b200.synthetic import bench_model
+from benchkit.synthetic import bench_model
 
 
 @pytest.mark.parametrize('variant', ['f32', 'f64'])
