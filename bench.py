@@ -86,15 +86,25 @@ class ClockSampler(object):
                 'reasons': sorted(reasons), 'samples': len(self.rows)}
 
 
+def _usable_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# taken at import, before any OpenMP runtime is loaded: with OMP_PROC_BIND=TRUE (which the reference sets for every model,
+# input_cmds_singleuse.py:78-80) libgomp binds the main thread to one core when it starts, and the affinity mask read after
+# that says "1 core"
+_CORES_AT_START = _usable_cores()
+
+
 def host_threads():
     """Threads for the CPU legs: the cores this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers; that
     is a launcher default, not a property of the host, so it is ignored (GPB_CPU_THREADS overrides)."""
     if os.environ.get('GPB_CPU_THREADS'):
         return int(os.environ['GPB_CPU_THREADS'])
-    try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+    return _CORES_AT_START
 
 
 def cpu_reference_run(G, iterations):
@@ -139,6 +149,7 @@ def bench_grid(N, iterations=None):
     if iterations is None and os.environ.get('GPB_BENCH_MODEL', 'reference') == 'reference' and refmodel.reference_available():
         try:
             G = refmodel.build_with_reference(refmodel.reference_input('tests/benchmarking/bench_{0}x{0}x{0}.in'.format(N)))
+            G.progressbars = False   # stdout carries exactly one JSON line
             return G, 'reference front end (baseline/_ref, gprMax v3.1.7 unmodified) stopped at the solve_gpu seam'
         except Exception as e:   # e.g. the input file of that size does not exist
             sys.stderr.write('reference front end unavailable for this model ({}); using benchkit.synthetic\n'.format(e))
@@ -217,26 +228,32 @@ def committed_traffic(N):
     return float(t[key]['dram_bytes_per_launch']), t[key].get('file')
 
 
-def trace_parity(rx, G, ref_outputs, iters, what):
-    """max |gpu - ref| / peak(ref) over the first `iters` samples of every receiver component (rows of fields_outputs.py:81-105)."""
+def trace_errors(rx, G, ref_outputs, iters):
+    """{component: max |gpu - ref| / scale} over the first `iters` samples; scale = the component's own peak in `ref`, or 10 %
+    of the strongest component of the same kind (E, H) at that receiver when that is larger (tests/parity.py: a component that
+    is zero by symmetry only carries the rounding noise of the big ones)."""
     from gprmax_b200 import _lib
-    worst, comp = 0.0, None
+    out = {}
     for n, r in enumerate(G.rxs):
         for name in r.outputs:
             key = 'rx{}_{}'.format(n, name)
             if key not in ref_outputs:
                 continue
             ref = np.asarray(ref_outputs[key], dtype=np.float64)[:iters]
-            mine = rx[_lib.RX_ROWS.index(name), :iters, n].astype(np.float64)
+            mine = np.asarray(rx[_lib.RX_ROWS.index(name), :iters, n] if isinstance(rx, np.ndarray) else rx[key], dtype=np.float64)[:iters]
             peaks = [float(np.abs(np.asarray(ref_outputs[k], dtype=np.float64)[:iters]).max()) for k in ref_outputs
                      if k.startswith('rx{}_'.format(n)) and k.split('_')[1][0] == name[0]]
-            scale = max(float(np.abs(ref).max()), 0.1 * max(peaks))   # tests/parity.py: numerically-zero components
-            if scale == 0:
-                continue
-            rel = float(np.abs(mine - ref).max()) / scale
-            if rel >= worst:
-                worst, comp = rel, key
-    return {'max_rel': worst, 'component': comp, 'iters': int(iters), 'against': what}
+            scale = max(float(np.abs(ref).max()), 0.1 * max(peaks))
+            if scale > 0:
+                out[key] = float(np.abs(mine - ref).max()) / scale
+    return out
+
+
+def trace_parity(rx, G, ref_outputs, iters, what):
+    errs = trace_errors(rx, G, ref_outputs, iters)
+    worst = max(errs, key=errs.get) if errs else None
+    return {'max_rel': errs[worst] if worst else 0.0, 'component': worst, 'iters': int(iters), 'against': what,
+            'per_component': {k: float('{:.3e}'.format(v)) for k, v in errs.items()}}
 
 
 def run_single_gpu(args):
@@ -338,21 +355,30 @@ def run_single_gpu(args):
         parity['full'] = trace_parity(rx_gpu, G, g32, its, 'tests/golden/bench_{}_trace_f32.npz: all {} iterations, unmodified reference CPU solver'.format(N, its))
         t64 = gold.replace('_f32.npz', '_f64.npz')
         if os.path.exists(t64):
+            # criterion (b) of tests/parity.py, per component: against the reference's own float64 run, the GPU's float32 trace is
+            # as close as the reference's float32 trace is (x3: two realisations of the same rounding noise)
             z64 = np.load(t64)
             g64 = {k[len('golden_'):]: z64[k] for k in z64.files}
-            e_cuda = trace_parity(rx_gpu, G, g64, its, 'float64 reference')['max_rel']
-            e_ref = max(float(np.abs(g32[k].astype(np.float64) - g64[k]).max()) / max(float(np.abs(g64[k]).max()), 1e-300) for k in g32 if np.abs(g64[k]).max() > 0)
-            parity['full'].update(vs_f64_truth=e_cuda, ref32_vs_f64_truth=e_ref)
+            e_cuda = trace_errors(rx_gpu, G, g64, its)
+            e_ref = trace_errors(g32, G, g64, its)
+            parity['full'].update(gpu32_vs_ref64={k: float('{:.3e}'.format(v)) for k, v in e_cuda.items()},
+                                  ref32_vs_ref64={k: float('{:.3e}'.format(v)) for k, v in e_ref.items()})
         # the end-to-end call must give the same bits as the device-resident run
         parity['e2e_equals_resident'] = bool(all(np.array_equal(rx_e2e[k], rx_gpu[_row(k), :, int(k[2:k.index('_')])]) for k in rx_e2e))
     tol = 1e-4
-    checks = [parity[k]['max_rel'] for k in ('prefix', 'full') if k in parity]
-    ok_a = all(c <= tol for c in checks)
-    ok_b = 'full' in parity and 'vs_f64_truth' in parity['full'] and parity['full']['vs_f64_truth'] <= 3 * parity['full']['ref32_vs_f64_truth'] + 1e-5 \
-        and parity.get('prefix', {'max_rel': 0})['max_rel'] <= tol
-    parity['criterion'] = 'a: max|gpu32 - ref32| <= 1e-4 of trace peak' if ok_a else ('b: |gpu32 - ref64| <= 3 |ref32 - ref64| + 1e-5 (tests/parity.py)' if ok_b else 'FAIL')
+    verdicts = {}
+    for k, v in parity.get('prefix', {}).get('per_component', {}).items():
+        verdicts['prefix:' + k] = 'a' if v <= tol else 'FAIL'
+    for k, v in parity.get('full', {}).get('per_component', {}).items():
+        b_ok = 'gpu32_vs_ref64' in parity['full'] and parity['full']['gpu32_vs_ref64'].get(k, 1e9) <= 3 * parity['full']['ref32_vs_ref64'].get(k, 0.0) + 1e-5
+        verdicts['full:' + k] = 'a' if v <= tol else ('b' if b_ok else 'FAIL')
+    parity['per_component_criterion'] = verdicts
+    parity['criterion'] = ('a = max|gpu32 - ref32| <= 1e-4 of trace peak (north_star); b = |gpu32 - ref64| <= 3 |ref32 - ref64| + 1e-5: as close to the '
+                           "reference's float64 result as the reference's own float32 result is (tests/parity.py)")
+    checks = list(verdicts.values())
+    ok_a = ok_b = False
     parity['tolerance'] = tol
-    parity['ok'] = bool(ok_a or ok_b) if checks else None
+    parity['ok'] = ('FAIL' not in checks) if checks else None
 
     # ---- weak-scaling baseline: the per-GPU slab of the sharded runs on this one GPU (so that v_N / (N v_1) is like for like)
     wsb = None
@@ -420,7 +446,7 @@ def main():
             os.environ.setdefault('MASTER_PORT', '29517')
             os.environ.setdefault('RANK', '0')
             os.environ.setdefault('WORLD_SIZE', '1')
-        from gprmax_b200.sharded import bench_sharded
+        from benchkit.sharded_bench import bench_sharded
         return bench_sharded(args)
     return run_single_gpu(args)
 

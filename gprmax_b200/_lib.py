@@ -8,7 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.environ.get('GPB_LIB') or os.path.join(HERE, 'libgprmax_b200.so')
 
-GPB_ABI_VERSION = 2
+GPB_ABI_VERSION = 3
 GPB_F32, GPB_F64 = 0, 1
 GPB_HORIPML, GPB_MRIPML = 0, 1
 GPB_SRC_HERTZIAN, GPB_SRC_MAGNETIC, GPB_SRC_VOLTAGE = 0, 1, 2
@@ -18,7 +18,7 @@ RX_ROWS = ['Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz', 'Ix', 'Iy', 'Iz']
 # every symbol include/gprmax_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['gpb_device_count', 'gpb_device_info', 'gpb_create', 'gpb_destroy', 'gpb_run', 'gpb_iteration',
            'gpb_elapsed_seconds', 'gpb_mem_used', 'gpb_kernel_launches', 'gpb_reset', 'gpb_profile', 'gpb_kernel_path', 'gpb_half_step', 'gpb_halo',
-           'gpb_stream', 'gpb_synchronize', 'gpb_get_receivers', 'gpb_get_snapshot', 'gpb_get_tline',
+           'gpb_stream', 'gpb_synchronize', 'gpb_create_sharded', 'gpb_link_info', 'gpb_link', 'gpb_get_receivers', 'gpb_get_snapshot', 'gpb_get_tline',
            'gpb_get_field', 'gpb_set_field', 'gpb_release_cached', 'gpb_last_error', 'gpb_version']
 
 
@@ -55,13 +55,20 @@ class Snapshot(C.Structure):
                 ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32), ('time', C.c_int32)]
 
 
+class Link(C.Structure):
+    _fields_ = [('process_id', C.c_uint64), ('device_id', C.c_int32), ('dtype', C.c_int32),
+                ('x_start', C.c_int32), ('nx_planes', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
+                ('plane_elems', C.c_uint64), ('array_elems', C.c_uint64), ('fields_ptr', C.c_uint64), ('flags_ptr', C.c_uint64),
+                ('fields_ipc', C.c_ubyte * 64), ('flags_ipc', C.c_ubyte * 64)]
+
+
 class Model(C.Structure):
     _fields_ = [('abi_version', C.c_int32), ('dtype', C.c_int32),
                 ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
                 ('x_start', C.c_int32), ('nx_planes', C.c_int32),
                 ('dx', C.c_double), ('dy', C.c_double), ('dz', C.c_double), ('dt', C.c_double),
                 ('iterations', C.c_int32), ('nmaterials', C.c_int32),
-                ('ID', C.c_void_p), ('uniform_id', C.c_int32), ('updatecoeffsE', C.c_void_p), ('updatecoeffsH', C.c_void_p),
+                ('ID', C.c_void_p), ('id_comp_stride', C.c_int64), ('uniform_id', C.c_int32), ('updatecoeffsE', C.c_void_p), ('updatecoeffsH', C.c_void_p),
                 ('maxpoles', C.c_int32), ('updatecoeffsdispersive', C.c_void_p),
                 ('pml_formulation', C.c_int32), ('pml_order', C.c_int32),
                 ('npml', C.c_int32), ('pmls', C.POINTER(Pml)),
@@ -89,6 +96,9 @@ def lib():
     L.gpb_device_count.argtypes = [C.POINTER(C.c_int)]
     L.gpb_device_info.argtypes = [C.c_int, C.POINTER(DeviceInfo)]
     L.gpb_create.argtypes = [C.POINTER(Model), C.c_int, C.POINTER(H)]
+    L.gpb_create_sharded.argtypes = [C.POINTER(Model), C.POINTER(C.c_int), C.c_int, C.POINTER(H)]
+    L.gpb_link_info.argtypes = [H, C.POINTER(Link)]
+    L.gpb_link.argtypes = [H, C.POINTER(Link), C.POINTER(Link)]
     L.gpb_destroy.argtypes = [H]
     L.gpb_run.argtypes = [H, C.c_int]
     L.gpb_half_step.argtypes = [H, C.c_int, C.c_int]

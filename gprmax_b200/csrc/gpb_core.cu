@@ -20,6 +20,9 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
 #include <vector>
 
 using namespace gpb;
@@ -162,7 +165,17 @@ void parallel_copy(char *dst, const char *src, size_t bytes, int nthreads)
     for (int t = 0; t < nthreads; ++t) {
         const size_t o = (size_t)t * part;
         if (o >= bytes) break;
-        th.emplace_back([=] { memcpy(dst + o, src + o, std::min(part, bytes - o)); });
+        th.emplace_back([=] {
+            // the caller's thread is often pinned to ONE core (the reference sets OMP_PROC_BIND=TRUE for every model,
+            // input_cmds_singleuse.py:78-80, and the OpenMP runtime then binds the main thread): helper threads inherit that
+            // mask and would all share the core (upload 22 -> 85 ms at 300^3).  Ask for every CPU; the kernel keeps the
+            // process's cpuset.
+            cpu_set_t all;
+            CPU_ZERO(&all);
+            for (int c = 0; c < CPU_SETSIZE; ++c) CPU_SET(c, &all);
+            pthread_setaffinity_np(pthread_self(), sizeof all, &all);
+            memcpy(dst + o, src + o, std::min(part, bytes - o));
+        });
     }
     for (auto &t : th) t.join();
 }
@@ -182,6 +195,8 @@ struct SolverBase {
     virtual int halo(int which, void **a, void **b, size_t *bytes) = 0;
     virtual int profile(int n, double *ms4) = 0;
     virtual std::string kernel_path() const = 0;
+    virtual int link_info(gpb_link_t *out) = 0;
+    virtual int link(const gpb_link_t *left, const gpb_link_t *right) = 0;
     int device = 0;
     int iteration = 0;
     double elapsed = 0;
@@ -244,6 +259,30 @@ struct Solver : SolverBase {
     PointParams<R> pp;
     std::vector<std::pair<R *, size_t>> phis;
     bool v4_ok = true;
+    // linked x-slab shards (halo pushed into the neighbours' ghost planes over peer memory, gpb_link)
+    struct Peer {
+        bool present = false;
+        R *F = nullptr;              // base of the neighbour's field allocation (component c at F + c * narr_peer)
+        unsigned *flags = nullptr;   // the neighbour's flag words
+        long long narr = 0;
+        int x_start = 0, nplanes = 0;
+        void *ipc_F = nullptr, *ipc_flags = nullptr;   // mappings opened with cudaIpcOpenMemHandle (closed on unlink)
+    };
+    Peer left, right;
+    bool linked = false;
+    unsigned *d_flags = nullptr;   // [GPB_NFLAGS] written by the neighbours (peer stores) and by this shard's own kernels
+    cudaStream_t stream2 = nullptr;   // halo pushes run beside the interior update
+    cudaEvent_t evl[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long link_timeout_ns = 20000000000ull;
+    bool snap_needs_right = false;
+    bool snap_unlinked_ok = true;    // every snapshot cell of this slab averages planes of this slab only   // some snapshot cell of this shard reads planes of the right neighbour
+    int begin_run(int n);
+    int enqueue_iterations(int n);
+    int end_run();
+    int finish_run();
+    int unlink();
+    int enqueue_linked_step(bool with_snap);
+    int check_link_timeout();
     // graph
     cudaGraphExec_t graph = nullptr;
     bool use_graph = true;
@@ -256,6 +295,11 @@ struct Solver : SolverBase {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamSynchronize(stream);   // cached blocks are handed to the next solver, which runs on another stream
+        unlink();
+        for (auto &e : evl)
+            if (e) cudaEventDestroy(e);
+        if (stream2) cudaStreamDestroy(stream2);
+        if (d_flags) cudaFree(d_flags);
         for (void *p : allocs) g_pool.free(p);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -292,7 +336,7 @@ struct Solver : SolverBase {
     template <typename IDT>
     int launch_e(int p0, int p1);
     int launch_phase(int phase, int p0, int p1);
-    int launch_sources(int phase, int p0, int p1, bool tl_on);
+    int launch_sources(int phase, int p0, int p1, int t0, int t1);
     int launch_begin();
     int launch_snapshots();
     int enqueue_step(bool with_snap);
@@ -314,6 +358,8 @@ struct Solver : SolverBase {
     int halo(int which, void **a, void **b, size_t *bytes) override;
     int profile(int n, double *ms4) override;
     std::string kernel_path() const override;
+    int link_info(gpb_link_t *out) override;
+    int link(const gpb_link_t *left, const gpb_link_t *right) override;
 };
 
 static int choose_pitch(int nzp1)
@@ -385,6 +431,8 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
     const long long total_rows = rows_per_plane * nplanes;
     const size_t row_bytes = (size_t)(nz + 1) * 4;
     const long long chunk_rows = std::max<long long>(1, (long long)(kBounceBytes / row_bytes));
+    // a shard may point into the caller's global ID array (component stride of the whole grid): no second host copy of the slab
+    const size_t comp_stride = m.id_comp_stride > 0 ? (size_t)m.id_comp_stride : (size_t)total_rows * (nz + 1);
     uint32_t *stage[2] = {nullptr, nullptr};
     unsigned *d_max = nullptr;
     void *bounce[2] = {nullptr, nullptr};
@@ -401,7 +449,9 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
     allocs.push_back(idbase);
     mem += (size_t)narr * idbytes * 6;
     CK(cudaMemsetAsync(idbase, 0, (size_t)narr * idbytes * 6, stream));
-    const int nthreads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    // (configured CPUs, not std::thread::hardware_concurrency(): that one follows the calling thread's affinity mask, which is a
+    //  single core once the OpenMP runtime has pinned the main thread)
+    const int nthreads = (int)std::max(1l, std::min(8l, sysconf(_SC_NPROCESSORS_CONF) / 2));
     long long q = 0;
     for (int c = 0; c < 6; ++c) {
         void *dst = (char *)idbase + (size_t)c * narr * idbytes;
@@ -410,7 +460,7 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
             const int b = (int)(q & 1);
             const long long rows = std::min(chunk_rows, total_rows - r0);
             const size_t bytes = (size_t)rows * row_bytes;
-            const char *src = (const char *)(m.ID + ((size_t)c * total_rows + r0) * (nz + 1));
+            const char *src = (const char *)(m.ID + (size_t)c * comp_stride + (size_t)r0 * (nz + 1));
             if (q >= 2) CK(cudaEventSynchronize(ev[b]));   // the transfer out of this bounce buffer two chunks ago
             parallel_copy((char *)bounce[b], src, bytes, nthreads);
             CK(cudaMemcpyAsync(stage[b], bounce[b], bytes, cudaMemcpyHostToDevice, stream));
@@ -678,6 +728,8 @@ int Solver<R>::build(const gpb_model_t &m)
         if (upload(&dcoef, (const Cplx<R> *)m.updatecoeffsdispersive, (size_t)nmat * 3 * maxpoles)) return 1;
     }
     if (dalloc(&d_iter, 2)) return 1;
+    CK(cudaMalloc((void **)&d_flags, GPB_NFLAGS * sizeof(unsigned)));
+    CK(cudaMemsetAsync(d_flags, 0, GPB_NFLAGS * sizeof(unsigned), stream));
 
     for (PhaseParams<R> *ph : {&ph_h, &ph_e}) {
         memset(ph, 0, sizeof *ph);
@@ -726,6 +778,13 @@ int Solver<R>::build(const gpb_model_t &m)
     pp.srcE = srcE; pp.srcH = srcH; pp.iter = d_iter; pp.iterations = iterations;
     pp.dx = (R)m.dx; pp.dy = (R)m.dy; pp.dz = (R)m.dz;
     if (setup_points(m)) return 1;
+    // an unlinked slab cannot average snapshot cells with planes it does not own (gpb_link checks the linked case)
+    snap_unlinked_ok = true;
+    for (auto &sn : snaps)
+        for (int i = 0; i < sn.nx; ++i) {
+            const int gi = sn.xs + i * sn.dx;
+            if (gi >= x_start && gi < x_start + nplanes && gi + sn.dx >= x_start + nplanes) snap_unlinked_ok = false;
+        }
     if (set_smem_attributes()) return 1;
     CK(cudaStreamSynchronize(stream));
     tick("sources / receivers");
@@ -937,15 +996,17 @@ int Solver<R>::launch_phase(int phase, int p0, int p1)
 }
 
 template <typename R>
-int Solver<R>::launch_sources(int phase, int p0, int p1, bool tl_on)
+int Solver<R>::launch_sources(int phase, int p0, int p1, int t0, int t1)
 {
-    // point sources on the owned planes [p0, p1) (local indices) and, if tl_on, the transmission lines
+    // point sources on the owned planes [p0, p1) and transmission lines on the owned planes [t0, t1) (local indices)
     if (phase == 0 ? !has_hsrc : !has_esrc) return 0;
-    const int i_lo = x_start + p0, i_hi = x_start + p1;
-    if (i_hi <= i_lo && !(tl_on && ntl)) return 0;
-    if (idbytes == 1) k_sources<R, uint8_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls, i_lo, i_hi, tl_on ? 1 : 0);
-    else if (idbytes == 2) k_sources<R, uint16_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls, i_lo, i_hi, tl_on ? 1 : 0);
-    else k_sources<R, uint32_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl, d_tls, i_lo, i_hi, tl_on ? 1 : 0);
+    const int i_lo = x_start + p0, i_hi = x_start + p1, tl_lo = x_start + t0, tl_hi = x_start + t1;
+    const bool tl_any = ntl && tl_hi > tl_lo;
+    if ((i_hi <= i_lo || !nsrc) && !tl_any) return 0;
+    const int ntl_ = tl_any ? ntl : 0;
+    if (idbytes == 1) k_sources<R, uint8_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi);
+    else if (idbytes == 2) k_sources<R, uint16_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi);
+    else k_sources<R, uint32_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi);
     CK(cudaGetLastError());
     ++launches;
     return 0;
@@ -981,11 +1042,202 @@ int Solver<R>::enqueue_step(bool with_snap)
     if (launch_begin()) return 1;
     if (with_snap && launch_snapshots()) return 1;
     if (launch_phase(0, 0, nplanes)) return 1;
-    if (launch_sources(0, 0, nplanes, true)) return 1;
+    if (launch_sources(0, 0, nplanes, 0, nplanes)) return 1;
     if (launch_phase(1, 0, nplanes)) return 1;
-    if (launch_sources(1, 0, nplanes, true)) return 1;
+    if (launch_sources(1, 0, nplanes, 0, nplanes)) return 1;
     return 0;
 }
+
+// One iteration of a LINKED shard (gpb_link): same kernels on the same operands as enqueue_step, boundary plane first, with the
+// halo planes pushed into the neighbours' ghost planes by k_halo_push on a second stream while the interior runs, and
+// one-thread flag waits where a phase needs the neighbour's plane.  Flag protocol (values = iteration + 1, monotonic):
+//   my H_READY  <- left neighbour:  its Hy,Hz of this iteration are in my ghost plane x_start-1     (before my E half-step)
+//   my E_READY  <- right neighbour: its Ey,Ez of the previous iteration are in my ghost plane x_end (before my H half-step)
+//   my H_FREE   <- right neighbour: it has finished reading the H ghost plane I filled last iteration (before I refill it)
+// The Ey,Ez ghost needs no such credit: the right neighbour pushes E(it) only after it has seen my H(it), which I send after
+// the only kernel that reads that ghost plane (the H update of my last plane).
+template <typename R>
+int Solver<R>::enqueue_linked_step(bool with_snap)
+{
+    const int n = nplanes;
+    const int *it = d_iter;
+    if (launch_begin()) return 1;
+    if (left.present) {   // the step prologue was the last reader of my H ghost plane (receiver currents on my first plane)
+        k_flag_signal<<<1, 1, 0, stream>>>(left.flags + GPB_FLAG_H_FREE, it, 0);
+        ++launches;
+    }
+    if (with_snap && snapshot_due(iteration)) {
+        // snapshot cells on my last planes average with planes of the right neighbour, read straight from its memory: it must
+        // have finished the previous iteration and must not start this one before I am done
+        if (left.present) { k_flag_signal<<<1, 1, 0, stream>>>(left.flags + GPB_FLAG_SNAP_READY, it, 1); ++launches; }
+        if (right.present) { k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_SNAP_READY, it, 1, d_flags, GPB_FLAG_SNAP_READY, link_timeout_ns); ++launches; }
+        if (launch_snapshots()) return 1;
+        if (right.present) { k_flag_signal<<<1, 1, 0, stream>>>(right.flags + GPB_FLAG_SNAP_DONE, it, 1); ++launches; }
+        if (left.present) { k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_SNAP_DONE, it, 1, d_flags, GPB_FLAG_SNAP_DONE, link_timeout_ns); ++launches; }
+    }
+    // ---- H half-step: last owned plane first (its Hy,Hz feed the right neighbour)
+    if (right.present) {
+        k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_E_READY, it, 0, d_flags, GPB_FLAG_E_READY, link_timeout_ns);
+        ++launches;
+        if (launch_phase(0, n - 1, n) || launch_sources(0, n - 1, n, 0, 0)) return 1;
+        CK(cudaEventRecord(evl[0], stream));
+        CK(cudaStreamWaitEvent(stream2, evl[0], 0));
+        k_flag_wait<<<1, 1, 0, stream2>>>(d_flags + GPB_FLAG_H_FREE, it, 0, d_flags, GPB_FLAG_H_FREE, link_timeout_ns);
+        k_halo_push<R><<<64, 256, 0, stream2>>>(F[4] + plane * n, F[5] + plane * n, right.F + 4 * right.narr, right.F + 5 * right.narr, plane,
+                                                right.flags + GPB_FLAG_H_READY, it, 1, d_flags + GPB_FLAG_PUSH_COUNT);
+        CK(cudaGetLastError());
+        launches += 2;
+        CK(cudaEventRecord(evl[1], stream2));
+        if (launch_phase(0, 0, n - 1) || launch_sources(0, 0, n - 1, 0, 0)) return 1;
+    } else {
+        if (launch_phase(0, 0, n) || launch_sources(0, 0, n, 0, 0)) return 1;
+    }
+    // ---- E half-step: first owned plane first (its Ey,Ez feed the left neighbour)
+    if (left.present) {
+        k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_H_READY, it, 1, d_flags, GPB_FLAG_H_READY, link_timeout_ns);
+        ++launches;
+    }
+    // transmission-line currents after the wait: a line on my first plane reads H of the ghost plane (sources.py:444-452)
+    if (ntl && launch_sources(0, 0, 0, 0, n)) return 1;
+    if (left.present) {
+        if (launch_phase(1, 0, 1) || launch_sources(1, 0, 1, 0, 1)) return 1;
+        CK(cudaEventRecord(evl[2], stream));
+        CK(cudaStreamWaitEvent(stream2, evl[2], 0));
+        k_halo_push<R><<<64, 256, 0, stream2>>>(F[1] + plane, F[2] + plane, left.F + 1 * left.narr + plane * (left.nplanes + 1),
+                                                left.F + 2 * left.narr + plane * (left.nplanes + 1), plane, left.flags + GPB_FLAG_E_READY, it, 1,
+                                                d_flags + GPB_FLAG_PUSH_COUNT + 1);
+        CK(cudaGetLastError());
+        ++launches;
+        CK(cudaEventRecord(evl[3], stream2));
+        if (launch_phase(1, 1, n) || launch_sources(1, 1, n, 1, n)) return 1;
+    } else {
+        if (launch_phase(1, 0, n) || launch_sources(1, 0, n, 0, n)) return 1;
+    }
+    // join: the next iteration may change the planes the pushes read
+    if (right.present) CK(cudaStreamWaitEvent(stream, evl[1], 0));
+    if (left.present) CK(cudaStreamWaitEvent(stream, evl[3], 0));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::check_link_timeout()
+{
+    if (!linked) return 0;
+    unsigned t = 0;
+    CK(cudaMemcpyAsync(&t, d_flags + GPB_FLAG_TIMEOUT, sizeof t, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (t) return fail("linked shard [%d, %d): a halo flag wait timed out (mask 0x%x: bit 0 H_READY, 1 E_READY, 2 H_FREE, 3 SNAP_READY, 4 SNAP_DONE) -- "
+                       "a neighbouring shard stopped or was never started", x_start, x_start + nplanes, t);
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::link_info(gpb_link_t *out)
+{
+    CK(cudaSetDevice(device));
+    memset(out, 0, sizeof *out);
+    out->process_id = (uint64_t)getpid();
+    out->device_id = device;
+    out->dtype = sizeof(R) == 4 ? GPB_F32 : GPB_F64;
+    out->x_start = x_start; out->nx_planes = nplanes; out->ny = ny; out->nz = nz;
+    out->plane_elems = (uint64_t)plane; out->array_elems = (uint64_t)narr;
+    out->fields_ptr = (uint64_t)(uintptr_t)F[0];
+    out->flags_ptr = (uint64_t)(uintptr_t)d_flags;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "gpb_link_t carries 64-byte IPC handles");
+    cudaIpcMemHandle_t hF, hG;
+    // (a process that only ever links shards of its own does not need the handles: failure to export is not an error here)
+    if (cudaIpcGetMemHandle(&hF, F[0]) == cudaSuccess && cudaIpcGetMemHandle(&hG, d_flags) == cudaSuccess) {
+        memcpy(out->fields_ipc, &hF, 64);
+        memcpy(out->flags_ipc, &hG, 64);
+    } else {
+        cudaGetLastError();
+    }
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::unlink()
+{
+    if (!linked) return 0;
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    if (stream2) cudaStreamSynchronize(stream2);
+    for (Peer *p : {&left, &right}) {
+        if (p->ipc_F) cudaIpcCloseMemHandle(p->ipc_F);
+        if (p->ipc_flags) cudaIpcCloseMemHandle(p->ipc_flags);
+        *p = Peer();
+    }
+    if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
+    for (int c = 0; c < 6; ++c) pp.Fr[c] = nullptr;
+    linked = false;
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::link(const gpb_link_t *l, const gpb_link_t *r)
+{
+    CK(cudaSetDevice(device));
+    unlink();
+    if (!l && !r) return 0;
+    if (const char *e = getenv("GPB_LINK_TIMEOUT_MS")) link_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+    if (!stream2) CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    for (auto &e : evl)
+        if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const uint64_t me = (uint64_t)getpid();
+    for (int side = 0; side < 2; ++side) {
+        const gpb_link_t *q = side == 0 ? l : r;
+        if (!q) continue;
+        Peer &p = side == 0 ? left : right;
+        if (q->dtype != (sizeof(R) == 4 ? GPB_F32 : GPB_F64) || q->ny != ny || q->nz != nz || (long long)q->plane_elems != plane)
+            return fail("neighbour shard has another grid or float type");
+        if (side == 0 ? (q->x_start + q->nx_planes != x_start) : (q->x_start != x_start + nplanes))
+            return fail("%s neighbour owns planes [%d, %d), which do not adjoin mine [%d, %d)", side == 0 ? "left" : "right", q->x_start, q->x_start + q->nx_planes,
+                        x_start, x_start + nplanes);
+        if (q->process_id == me) {
+            if (q->device_id != device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, device, q->device_id));
+                if (!can) return fail("device %d cannot access the memory of device %d (no peer path)", device, q->device_id);
+                cudaError_t e = cudaDeviceEnablePeerAccess(q->device_id, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess(%d) failed: %s", q->device_id, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            p.F = (R *)(uintptr_t)q->fields_ptr;
+            p.flags = (unsigned *)(uintptr_t)q->flags_ptr;
+        } else {
+            cudaIpcMemHandle_t hF, hG;
+            memcpy(&hF, q->fields_ipc, 64);
+            memcpy(&hG, q->flags_ipc, 64);
+            CK(cudaIpcOpenMemHandle(&p.ipc_F, hF, cudaIpcMemLazyEnablePeerAccess));
+            CK(cudaIpcOpenMemHandle(&p.ipc_flags, hG, cudaIpcMemLazyEnablePeerAccess));
+            p.F = (R *)p.ipc_F;
+            p.flags = (unsigned *)p.ipc_flags;
+        }
+        p.narr = (long long)q->array_elems;
+        p.x_start = q->x_start;
+        p.nplanes = q->nx_planes;
+        p.present = true;
+    }
+    // snapshots: cells of my planes average with plane gi + dx, which may belong to the right neighbour
+    snap_needs_right = false;
+    for (auto &sn : snaps)
+        for (int i = 0; i < sn.nx; ++i) {
+            const int gi = sn.xs + i * sn.dx;
+            if (gi < x_start || gi >= x_start + nplanes || gi + sn.dx < x_start + nplanes) continue;
+            if (!right.present || gi + sn.dx >= right.x_start + right.nplanes)
+                return fail("snapshot plane %d + %d lies beyond the right neighbour's planes: shards thinner than the snapshot stride are not supported", gi, sn.dx);
+            snap_needs_right = true;
+        }
+    for (int c = 0; c < 6; ++c) pp.Fr[c] = right.present ? right.F + (size_t)c * right.narr : nullptr;
+    pp.xr_start = right.x_start;
+    pp.xr_planes = right.nplanes;
+    CK(cudaMemsetAsync(d_flags, 0, GPB_NFLAGS * sizeof(unsigned), stream));
+    CK(cudaStreamSynchronize(stream));
+    linked = true;
+    return 0;
+}
+
 
 // Opt in to more than 48 KB of dynamic shared memory for the kernels that stage the coefficient rows there (models with more
 // than ~2450 materials in float32).  Called once from build(): run(), half_step() and profile() all launch these kernels.
@@ -1013,6 +1265,14 @@ int Solver<R>::set_smem_attributes()
 template <typename R>
 int Solver<R>::run(int n)
 {
+    if (begin_run(n) || enqueue_iterations(n) || end_run()) return 1;
+    return finish_run();
+}
+
+// run() in four steps, so that a sharded run can interleave the slabs' launches (ShardedSolver::run)
+template <typename R>
+int Solver<R>::begin_run(int n)
+{
     CK(cudaSetDevice(device));
     if (n < 0 || iteration + n > iterations) return fail("cannot run %d iterations from %d: model has %d", n, iteration, iterations);
     if (use_graph && !graph && n > 1) {
@@ -1021,7 +1281,7 @@ int Solver<R>::run(int n)
         cudaGraph_t g = nullptr;
         const uint64_t l0 = launches;
         CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_step(false);
+        int rc = linked ? enqueue_linked_step(false) : enqueue_step(false);
         cudaError_t e = cudaStreamEndCapture(stream, &g);
         graph_launches = launches - l0;
         launches = l0;
@@ -1031,22 +1291,43 @@ int Solver<R>::run(int n)
         cudaGraphDestroy(g);
     }
     CK(cudaEventRecord(ev0, stream));
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::enqueue_iterations(int n)
+{
+    CK(cudaSetDevice(device));
     for (int s = 0; s < n; ++s) {
         if (graph && !snapshot_due(iteration)) {
             CK(cudaGraphLaunch(graph, stream));
             launches += graph_launches;
-        } else if (enqueue_step(true)) {
+        } else if (linked ? enqueue_linked_step(true) : enqueue_step(true)) {
             return 1;
         }
         ++iteration;
     }
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::end_run()
+{
+    CK(cudaSetDevice(device));
     CK(cudaEventRecord(ev1, stream));
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::finish_run()
+{
+    CK(cudaSetDevice(device));
     CK(cudaEventSynchronize(ev1));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
     elapsed += ms * 1e-3;
     CK(cudaGetLastError());
-    return 0;
+    return check_link_timeout();
 }
 
 // Which kernel family each half-step runs on ("H:<kernel> E:<kernel>"), for logs and the bench line
@@ -1073,6 +1354,7 @@ int Solver<R>::profile(int n, double *ms4)
 {
     CK(cudaSetDevice(device));
     if (n < 0 || iteration + n > iterations) return fail("cannot profile %d iterations from %d: model has %d", n, iteration, iterations);
+    if (linked) return fail("gpb_profile works on unlinked handles only");
     cudaEvent_t ev[6];
     for (auto &e : ev) CK(cudaEventCreate(&e));
     for (int q = 0; q < 4; ++q) ms4[q] = 0;
@@ -1082,11 +1364,11 @@ int Solver<R>::profile(int n, double *ms4)
         CK(cudaEventRecord(ev[1], stream));
         if (launch_phase(0, 0, nplanes)) return 1;
         CK(cudaEventRecord(ev[2], stream));
-        if (launch_sources(0, 0, nplanes, true)) return 1;
+        if (launch_sources(0, 0, nplanes, 0, nplanes)) return 1;
         CK(cudaEventRecord(ev[3], stream));
         if (launch_phase(1, 0, nplanes)) return 1;
         CK(cudaEventRecord(ev[4], stream));
-        if (launch_sources(1, 0, nplanes, true)) return 1;
+        if (launch_sources(1, 0, nplanes, 0, nplanes)) return 1;
         CK(cudaEventRecord(ev[5], stream));
         CK(cudaEventSynchronize(ev[5]));
         float t01, t12, t23, t34, t45;
@@ -1105,7 +1387,14 @@ int Solver<R>::profile(int n, double *ms4)
 template <typename R>
 int Solver<R>::half_step(int phase, int part)
 {
+    // Host-driven sharded stepping (the caller moves the halo planes between the calls, e.g. over NCCL).  Transmission-line
+    // currents are advanced at the start of phase 1, i.e. after the caller has received the H halo: a line on the first owned
+    // plane reads H of the ghost plane (sources.py:444-452).
     CK(cudaSetDevice(device));
+    if (linked) return fail("this shard is linked to its neighbours: advance it with gpb_run");
+    if (!snaps.empty() && !snap_unlinked_ok)
+        return fail("a snapshot spans the cut plane at x = %d: link the shards (gpb_link / gpb_create_sharded), host-driven half-steps cannot reach the neighbour's planes",
+                    x_start + nplanes);
     const bool first = part != 1, second = part != 0;
     if (phase == 0) {
         if (first) {
@@ -1114,14 +1403,14 @@ int Solver<R>::half_step(int phase, int part)
             // boundary plane first (its Hy,Hz feed the right neighbour) so the host can start the halo
             // transfer while the interior runs
             // (with the point sources that sit on it: the plane is sent as soon as this part is done)
-            if (launch_phase(0, nplanes - 1, nplanes) || launch_sources(0, nplanes - 1, nplanes, false)) return 1;
+            if (launch_phase(0, nplanes - 1, nplanes) || launch_sources(0, nplanes - 1, nplanes, 0, 0)) return 1;
         }
-        if (second && (launch_phase(0, 0, nplanes - 1) || launch_sources(0, 0, nplanes - 1, true))) return 1;
+        if (second && (launch_phase(0, 0, nplanes - 1) || launch_sources(0, 0, nplanes - 1, 0, 0))) return 1;
     } else {
         // first owned plane: its Ey,Ez feed the left neighbour
-        if (first && (launch_phase(1, 0, 1) || launch_sources(1, 0, 1, false))) return 1;
+        if (first && ((ntl && launch_sources(0, 0, 0, 0, nplanes)) || launch_phase(1, 0, 1) || launch_sources(1, 0, 1, 0, 1))) return 1;
         if (second) {
-            if (launch_phase(1, 1, nplanes) || launch_sources(1, 1, nplanes, true)) return 1;
+            if (launch_phase(1, 1, nplanes) || launch_sources(1, 1, nplanes, 1, nplanes)) return 1;
             ++iteration;
         }
     }
@@ -1138,6 +1427,8 @@ int Solver<R>::reset()
     for (auto &ph : phis) CK(cudaMemsetAsync(ph.first, 0, ph.second * sizeof(R), stream));
     CK(cudaMemsetAsync(d_rxs, 0, (size_t)GPB_NRXOUT * iterations * std::max(nrx, 1) * sizeof(R), stream));
     CK(cudaMemsetAsync(d_iter, 0, 2 * sizeof(int), stream));
+    // (linked shards: the caller resets all of them before any runs again -- the flags count iterations)
+    CK(cudaMemsetAsync(d_flags, 0, GPB_NFLAGS * sizeof(unsigned), stream));
     for (int t = 0; t < ntl; ++t) {
         CK(cudaMemcpyAsync(h_tls[t].voltage, tl_v0[t].data(), tl_v0[t].size() * sizeof(R), cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(h_tls[t].current, tl_c0[t].data(), tl_c0[t].size() * sizeof(R), cudaMemcpyHostToDevice, stream));
@@ -1228,8 +1519,186 @@ int Solver<R>::halo(int which, void **a, void **b, size_t *bytes)
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ one domain over several devices
+// gpb_create_sharded: the nx + 1 node planes are cut into contiguous x-slabs, one Solver per device, neighbouring slabs linked
+// over peer memory (Solver::link).  Every slab advances with its own CUDA graph on its own stream; the only coupling is the
+// flag-announced halo pushes, so the host just replays one graph per device and iteration.  The reference has no
+// counterpart: it rejects a model that does not fit one GPU (grid.py:239-241) and keeps only gpus[0] (gprMax.py:141-144).
+template <typename R>
+struct ShardedSolver : SolverBase {
+    std::vector<Solver<R> *> sh;
+    int nx = 0, ny = 0, nz = 0, iterations = 0, nrx = 0, ntl = 0;
+    std::vector<gpb_snapshot_t> snaps;
+
+    ~ShardedSolver()
+    {
+        for (auto *s : sh)
+            if (s) { cudaSetDevice(s->device); if (s->stream) cudaStreamSynchronize(s->stream); }
+        for (auto *s : sh)
+            if (s) s->unlink();
+        for (auto *s : sh) delete s;
+    }
+
+    int build(const gpb_model_t &m, const int *devices, int ndev)
+    {
+        nx = m.nx; ny = m.ny; nz = m.nz; iterations = m.iterations; nrx = m.nrx; ntl = m.ntlines;
+        snaps.assign(m.snapshots, m.snapshots + m.nsnapshots);
+        if (m.x_start != 0 || m.nx_planes != m.nx + 1) return fail("gpb_create_sharded takes the global model (x_start 0, nx_planes nx + 1)");
+        if (ndev < 1 || ndev > m.nx + 1) return fail("cannot cut %d planes into %d slabs", m.nx + 1, ndev);
+        sh.assign(ndev, nullptr);
+        // balanced contiguous ranges of the nx + 1 node planes (the first slabs take the remainder)
+        std::vector<int> x0(ndev + 1, 0);
+        for (int d = 0; d < ndev; ++d) x0[d + 1] = x0[d] + (m.nx + 1) / ndev + (d < (m.nx + 1) % ndev ? 1 : 0);
+        const size_t gplane = (size_t)(m.ny + 1) * (m.nz + 1);
+        std::vector<std::string> errs(ndev);
+        std::vector<int> rcs(ndev, 0);
+        std::vector<std::thread> th;
+        for (int d = 0; d < ndev; ++d) {
+            sh[d] = new Solver<R>();
+            sh[d]->device = devices[d];
+            th.emplace_back([&, d] {
+                gpb_model_t ms = m;
+                ms.x_start = x0[d];
+                ms.nx_planes = x0[d + 1] - x0[d];
+                if (m.ID) {   // slab by slab straight out of the caller's array
+                    ms.ID = m.ID + (size_t)x0[d] * gplane;
+                    ms.id_comp_stride = m.id_comp_stride > 0 ? m.id_comp_stride : (int64_t)((size_t)(m.nx + 1) * gplane);
+                }
+                rcs[d] = sh[d]->build(ms);
+                if (rcs[d]) errs[d] = g_err;
+            });
+        }
+        for (auto &t : th) t.join();
+        for (int d = 0; d < ndev; ++d)
+            if (rcs[d]) return fail("slab %d (device %d, planes [%d, %d)): %s", d, devices[d], x0[d], x0[d + 1], errs[d].c_str());
+        std::vector<gpb_link_t> info(ndev);
+        for (int d = 0; d < ndev; ++d)
+            if (sh[d]->link_info(&info[d])) return 1;
+        if (ndev > 1)
+            for (int d = 0; d < ndev; ++d)
+                if (sh[d]->link(d > 0 ? &info[d - 1] : nullptr, d + 1 < ndev ? &info[d + 1] : nullptr)) return 1;
+        for (auto *s : sh) mem += s->mem;
+        device = devices[0];
+        stream = sh[0]->stream;
+        return 0;
+    }
+
+    int run(int n) override
+    {
+        if (n < 0 || iteration + n > iterations) return fail("cannot run %d iterations from %d: model has %d", n, iteration, iterations);
+        // the slabs' iterations are enqueued interleaved, a few at a time: the flags order the slabs among themselves on the
+        // devices, but a slab whose launches all sat in front of its neighbour's in a full launch queue would wait for work the
+        // host could not submit yet
+        for (auto *s : sh)
+            if (s->begin_run(n)) return 1;
+        for (int done = 0; done < n; done += 16)
+            for (auto *s : sh)
+                if (s->enqueue_iterations(std::min(16, n - done))) return 1;
+        for (auto *s : sh)
+            if (s->end_run()) return 1;
+        double worst = 0;
+        int rc = 0;
+        for (auto *s : sh) {
+            const double e0 = s->elapsed;
+            if (s->finish_run()) rc = 1;
+            worst = std::max(worst, s->elapsed - e0);
+        }
+        if (rc) return 1;
+        elapsed += worst;
+        iteration += n;
+        launches = 0;
+        for (auto *s : sh) launches += s->launches;
+        return 0;
+    }
+    int half_step(int, int) override { return fail("a sharded handle advances with gpb_run"); }
+    int profile(int, double *) override { return fail("gpb_profile works on single-device handles only"); }
+    int halo(int, void **, void **, size_t *) override { return fail("a sharded handle exchanges its halo planes itself"); }
+    int link_info(gpb_link_t *) override { return fail("a sharded handle is already linked internally"); }
+    int link(const gpb_link_t *, const gpb_link_t *) override { return fail("a sharded handle is already linked internally"); }
+    std::string kernel_path() const override
+    {
+        char b[64];
+        snprintf(b, sizeof b, "%d x-slabs, each ", (int)sh.size());
+        return b + sh[0]->kernel_path();
+    }
+    int reset() override
+    {
+        for (auto *s : sh)
+            if (s->reset()) return 1;
+        iteration = 0;
+        elapsed = 0;
+        return 0;
+    }
+    // every receiver / transmission line / snapshot cell is owned by exactly one slab and zero in the others: the sum is exact
+    int sum_into(std::vector<R> &acc, const std::vector<R> &part)
+    {
+        for (size_t q = 0; q < acc.size(); ++q) acc[q] += part[q];
+        return 0;
+    }
+    int get_receivers(void *out, size_t bytes) override
+    {
+        const size_t n = (size_t)GPB_NRXOUT * iterations * nrx;
+        if (bytes != n * sizeof(R)) return fail("receiver buffer is %zu bytes, expected %zu", bytes, n * sizeof(R));
+        std::vector<R> acc(n, (R)0), part(n);
+        for (auto *s : sh) {
+            if (s->get_receivers(part.data(), bytes)) return 1;
+            sum_into(acc, part);
+        }
+        memcpy(out, acc.data(), bytes);
+        return 0;
+    }
+    int get_snapshot(int idx, void *out6[6], size_t bytes_each) override
+    {
+        if (idx < 0 || idx >= (int)snaps.size()) return fail("snapshot index %d out of range", idx);
+        const size_t n = (size_t)snaps[idx].nx * snaps[idx].ny * snaps[idx].nz;
+        if (bytes_each != n * sizeof(R)) return fail("snapshot buffer is %zu bytes, expected %zu", bytes_each, n * sizeof(R));
+        std::vector<std::vector<R>> acc(6, std::vector<R>(n, (R)0)), part(6, std::vector<R>(n));
+        void *pp6[6];
+        for (int c = 0; c < 6; ++c) pp6[c] = part[c].data();
+        for (auto *s : sh) {
+            if (s->get_snapshot(idx, pp6, bytes_each)) return 1;
+            for (int c = 0; c < 6; ++c) sum_into(acc[c], part[c]);
+        }
+        for (int c = 0; c < 6; ++c) memcpy(out6[c], acc[c].data(), bytes_each);
+        return 0;
+    }
+    int get_tline(int idx, void *v, void *i, size_t bytes_each) override
+    {
+        if (idx < 0 || idx >= ntl) return fail("transmission line index %d out of range", idx);
+        const size_t n = (size_t)iterations;
+        if (bytes_each != n * sizeof(R)) return fail("transmission line buffer is %zu bytes, expected %zu", bytes_each, n * sizeof(R));
+        std::vector<R> av(n, (R)0), ai(n, (R)0), pv(n), pi(n);
+        for (auto *s : sh) {
+            if (s->get_tline(idx, pv.data(), pi.data(), bytes_each)) return 1;
+            sum_into(av, pv);
+            sum_into(ai, pi);
+        }
+        memcpy(v, av.data(), bytes_each);
+        memcpy(i, ai.data(), bytes_each);
+        return 0;
+    }
+    int get_field(int comp, void *out, size_t bytes) override
+    {
+        const size_t gplane = (size_t)(ny + 1) * (nz + 1) * sizeof(R);
+        if (bytes != gplane * (nx + 1)) return fail("field buffer is %zu bytes, expected %zu", bytes, gplane * (nx + 1));
+        for (auto *s : sh)
+            if (s->get_field(comp, (char *)out + gplane * s->x_start, gplane * s->nplanes)) return 1;
+        return 0;
+    }
+    int set_field(int comp, const void *in, size_t bytes) override
+    {
+        const size_t gplane = (size_t)(ny + 1) * (nz + 1) * sizeof(R);
+        if (bytes != gplane * (nx + 1)) return fail("field buffer is %zu bytes, expected %zu", bytes, gplane * (nx + 1));
+        for (auto *s : sh)
+            if (s->set_field(comp, (const char *)in + gplane * s->x_start, gplane * s->nplanes)) return 1;
+        return 0;
+    }
+};
+
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
+
+#define NEED(h) if (!(h) || !(h)->impl) return fail("null handle")
 
 int gpb_release_cached(void)
 {
@@ -1306,6 +1775,45 @@ int gpb_create(const gpb_model_t *model, int device_id, gpb_handle *out)
     return 0;
 }
 
+int gpb_create_sharded(const gpb_model_t *model, const int *device_ids, int ndevices, gpb_handle *out)
+{
+    if (!model || !out || !device_ids) return fail("null argument");
+    *out = nullptr;
+    if (model->abi_version != GPB_ABI_VERSION) return fail("ABI version mismatch: library %d, caller %d", GPB_ABI_VERSION, model->abi_version);
+    int n = 0;
+    if (gpb_device_count(&n)) return 1;
+    for (int d = 0; d < ndevices; ++d) {
+        if (device_ids[d] < 0 || device_ids[d] >= n) return fail("GPU with device ID %d does not exist (%d device(s) present)", device_ids[d], n);
+        for (int e = 0; e < d; ++e)
+            if (device_ids[e] == device_ids[d] && !getenv("GPB_ALLOW_SAME_DEVICE")) return fail("device %d is listed twice", device_ids[d]);
+    }
+    SolverBase *s = nullptr;
+    int rc;
+    if (model->dtype == GPB_F32) {
+        auto *p = new ShardedSolver<float>();
+        rc = p->build(*model, device_ids, ndevices);
+        s = p;
+    } else if (model->dtype == GPB_F64) {
+        auto *p = new ShardedSolver<double>();
+        rc = p->build(*model, device_ids, ndevices);
+        s = p;
+    } else {
+        return fail("unknown dtype %d", model->dtype);
+    }
+    if (rc) {
+        std::string keep = g_err;
+        delete s;
+        cudaGetLastError();
+        g_err = keep;
+        return 1;
+    }
+    *out = new gpb_solver{s};
+    return 0;
+}
+
+int gpb_link_info(gpb_handle h, gpb_link_t *out) { NEED(h); if (!out) return fail("null argument"); return h->impl->link_info(out); }
+int gpb_link(gpb_handle h, const gpb_link_t *left, const gpb_link_t *right) { NEED(h); return h->impl->link(left, right); }
+
 int gpb_destroy(gpb_handle h)
 {
     if (!h) return 0;
@@ -1314,7 +1822,6 @@ int gpb_destroy(gpb_handle h)
     return 0;
 }
 
-#define NEED(h) if (!(h) || !(h)->impl) return fail("null handle")
 
 int gpb_run(gpb_handle h, int n_iters) { NEED(h); return h->impl->run(n_iters); }
 int gpb_half_step(gpb_handle h, int phase, int part) { NEED(h); if (phase != 0 && phase != 1) return fail("phase must be 0 or 1"); if (part < -1 || part > 1) return fail("part must be -1, 0 or 1"); return h->impl->half_step(phase, part); }

@@ -523,6 +523,10 @@ struct PointParams {
     const int *iter;       // device iteration counter (current)
     int iterations;
     R dx, dy, dz;
+    // linked x-slab shards: field arrays of the RIGHT neighbour (peer-mapped, same plane / pitch; local plane 0 = its ghost
+    // plane) for the snapshot cells whose +x operands lie on the neighbour's planes; null when there is none
+    const R *Fr[6];
+    int xr_start, xr_planes;
 };
 
 template <typename R>
@@ -570,6 +574,7 @@ __global__ void k_step_begin(PointParams<R> p, int *iter_cur, int *iter_next, in
             for (int c = 0; c < 3; ++c) rxs[((long long)(6 + c) * p.iterations + it) * nrx + r] = current_at(p, c, i, j, k);
         }
         for (int t = threadIdx.x; t < ntl; t += blockDim.x) {
+            if (!pt_owned(p, tls[t].i)) continue;   // sharded runs sum the slabs' outputs: only the owner records
             tls[t].Vtotal[it] = tls[t].voltage[tls[t].antpos];
             tls[t].Itotal[it] = tls[t].current[tls[t].antpos];
         }
@@ -586,17 +591,17 @@ __global__ void k_step_begin(PointParams<R> p, int *iter_cur, int *iter_next, in
 // phase 0 (after H update + H-PML): transmission lines (current), magnetic dipoles   model_build_run.py:440-442
 // phase 1 (after E update + E-PML): voltage sources, transmission lines (voltage), Hertzian dipoles  :458-461
 template <typename R, typename IDT>
-__global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R> *srcs, int ntl, const TLDev<R> *tls, int i_lo, int i_hi, int tl_on)
+__global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R> *srcs, int ntl, const TLDev<R> *tls, int i_lo, int i_hi, int tl_lo, int tl_hi)
 {
     // [i_lo, i_hi): global planes whose point sources this launch applies (a sharded half-step applies the sources of its
-    // boundary plane before that plane is sent to the neighbour); tl_on: advance the transmission lines in this launch
+    // boundary plane before that plane is sent to the neighbour); [tl_lo, tl_hi): planes whose transmission lines it advances
+    // (a line belongs to exactly one plane, so every line is advanced by exactly one launch per phase)
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     const int it = *p.iter;
-    if (!tl_on) ntl = 0;
     if (phase == 0) {
         for (int t = 0; t < ntl; ++t) {
             const TLDev<R> &tl = tls[t];
-            if (it < tl.it_first || it > tl.it_last || !pt_owned(p, tl.i)) continue;
+            if (it < tl.it_first || it > tl.it_last || !pt_owned(p, tl.i) || tl.i < tl_lo || tl.i >= tl_hi) continue;
             // update_current, sources.py:379-393 (float64 arithmetic, stored as R)
             for (int n = 0; n < tl.nl - 1; ++n) {
                 const R dv = tl.voltage[n + 1] - tl.voltage[n];
@@ -627,7 +632,7 @@ __global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R>
         }
         for (int t = 0; t < ntl; ++t) {
             const TLDev<R> &tl = tls[t];
-            if (it < tl.it_first || it > tl.it_last || !pt_owned(p, tl.i)) continue;
+            if (it < tl.it_first || it > tl.it_last || !pt_owned(p, tl.i) || tl.i < tl_lo || tl.i >= tl_hi) continue;
             // update_voltage, sources.py:360-377
             for (int n = tl.nl - 1; n >= 1; --n) {
                 const R dc = tl.current[n] - tl.current[n - 1];
@@ -659,6 +664,14 @@ struct SnapDev {
     R *out[6];  // each [nx][ny][nz]
 };
 
+// value of component c at (global plane gi, in-plane offset jk): own planes, or the right neighbour's (linked shards)
+template <typename R>
+__device__ __forceinline__ R snap_at(const PointParams<R> &p, int c, int gi, long long jk)
+{
+    if (gi < p.x_start + p.nplanes) return p.F[c][(long long)(gi - p.x_start + 1) * p.plane + jk];
+    return p.Fr[c][(long long)(gi - p.xr_start + 1) * p.plane + jk];
+}
+
 template <typename R>
 __global__ void k_snapshot(PointParams<R> p, SnapDev<R> s)
 {
@@ -666,16 +679,85 @@ __global__ void k_snapshot(PointParams<R> p, SnapDev<R> s)
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(q % s.nz), j = (int)((q / s.nz) % s.ny), i = (int)(q / ((long long)s.nz * s.ny));
         const int gi = s.xs + i * s.dx, gj = s.ys + j * s.dy, gk = s.zs + k * s.dz;
-        if (!pt_owned(p, gi)) continue;
-        const long long o = pt_off(p, gi, gj, gk);
-        const long long si = (long long)s.dx * p.plane, sj = (long long)s.dy * p.pitch, sk = s.dz;
-        const R *Ex = p.F[0], *Ey = p.F[1], *Ez = p.F[2], *Hx = p.F[3], *Hy = p.F[4], *Hz = p.F[5];
-        s.out[0][q] = (Ex[o] + Ex[o + sj] + Ex[o + sk] + Ex[o + sj + sk]) / 4;
-        s.out[1][q] = (Ey[o] + Ey[o + si] + Ey[o + sk] + Ey[o + si + sk]) / 4;
-        s.out[2][q] = (Ez[o] + Ez[o + si] + Ez[o + sj] + Ez[o + si + sj]) / 4;
-        s.out[3][q] = (Hx[o] + Hx[o + si]) / 2;
-        s.out[4][q] = (Hy[o] + Hy[o + sj]) / 2;
-        s.out[5][q] = (Hz[o] + Hz[o + sk]) / 2;
+        if (!pt_owned(p, gi)) continue;   // a snapshot cell belongs to the shard that owns its plane gi
+        const long long o = (long long)gj * p.pitch + gk;
+        const long long sj = (long long)s.dy * p.pitch, sk = s.dz;
+        const int gn = gi + s.dx;
+        s.out[0][q] = (snap_at(p, 0, gi, o) + snap_at(p, 0, gi, o + sj) + snap_at(p, 0, gi, o + sk) + snap_at(p, 0, gi, o + sj + sk)) / 4;
+        s.out[1][q] = (snap_at(p, 1, gi, o) + snap_at(p, 1, gn, o) + snap_at(p, 1, gi, o + sk) + snap_at(p, 1, gn, o + sk)) / 4;
+        s.out[2][q] = (snap_at(p, 2, gi, o) + snap_at(p, 2, gn, o) + snap_at(p, 2, gi, o + sj) + snap_at(p, 2, gn, o + sj)) / 4;
+        s.out[3][q] = (snap_at(p, 3, gi, o) + snap_at(p, 3, gn, o)) / 2;
+        s.out[4][q] = (snap_at(p, 4, gi, o) + snap_at(p, 4, gi, o + sj)) / 2;
+        s.out[5][q] = (snap_at(p, 5, gi, o) + snap_at(p, 5, gi, o + sk)) / 2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Linked x-slab shards: halo planes are PUSHED into the neighbour's ghost plane with peer stores over NVLink and announced
+// with monotonic flags (value = iteration + 1) in the neighbour's memory; the neighbour's stream holds a one-thread kernel
+// that waits for the flag.  No host round trip and no collective on the data path, so a shard's whole iteration is a fixed
+// kernel sequence (the expected flag values come from the device iteration counter) that is captured into one CUDA graph.
+// ------------------------------------------------------------------------------------------
+enum { GPB_FLAG_H_READY = 0, GPB_FLAG_E_READY = 1, GPB_FLAG_H_FREE = 2, GPB_FLAG_SNAP_READY = 3, GPB_FLAG_SNAP_DONE = 4,
+       GPB_FLAG_TIMEOUT = 8, GPB_FLAG_PUSH_COUNT = 9, GPB_NFLAGS = 16 };
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// wait until *flag >= *iter + add (one thread).  A wait that lasts longer than `timeout_ns` gives up and records itself in
+// my_flags[GPB_FLAG_TIMEOUT] (checked by the host after the run): a lost neighbour must not hang the device.
+static __global__ void k_flag_wait(const unsigned *flag, const int *iter, int add, unsigned *my_flags, int which, unsigned long long timeout_ns)
+{
+    const unsigned want = (unsigned)(*iter + add);
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(flag) < want) {
+        __nanosleep(200);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+            atomicOr(my_flags + GPB_FLAG_TIMEOUT, 1u << which);
+            break;
+        }
+    }
+}
+
+// *flag = *iter + add in (peer) memory, after everything this stream did before
+static __global__ void k_flag_signal(unsigned *flag, const int *iter, int add)
+{
+    __threadfence_system();
+    st_release_sys(flag, (unsigned)(*iter + add));
+}
+
+// copy two planes (n elements each, 16-byte aligned) into the neighbour's ghost planes with 128-bit peer stores; the last
+// block to finish publishes *flag = *iter + add
+template <typename R>
+__global__ void __launch_bounds__(256) k_halo_push(const R *__restrict__ src_a, const R *__restrict__ src_b, R *__restrict__ dst_a, R *__restrict__ dst_b,
+                                                   long long n, unsigned *flag, const int *iter, int add, unsigned *counter)
+{
+    const long long nv = n * (long long)sizeof(R) / 16;
+    const uint4 *sa = reinterpret_cast<const uint4 *>(src_a), *sb = reinterpret_cast<const uint4 *>(src_b);
+    uint4 *da = reinterpret_cast<uint4 *>(dst_a), *db = reinterpret_cast<uint4 *>(dst_b);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nv; q += (long long)gridDim.x * blockDim.x) {
+        da[q] = sa[q];
+        db[q] = sb[q];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+            *counter = 0;
+            __threadfence_system();
+            st_release_sys(flag, (unsigned)(*iter + add));
+        }
     }
 }
 

@@ -11,9 +11,14 @@ Dependencies across a cut (same as the single-GPU kernels, just across devices):
 so per half-step each interface moves TWO planes in ONE direction:
     after the H half-step:  Hy,Hz of my last  plane -> right neighbour's ghost plane x0-1
     after the E half-step:  Ey,Ez of my first plane -> left  neighbour's ghost plane x1
-There is no collective on the data path, only pairwise send/recv (NCCL on GPUs, gloo in the CPU
-tests).  The boundary plane is computed first (gpb_half_step part 0), its send is posted, and the
-interior (part 1) runs while the planes travel over NVLink.
+There is no collective on the data path.  Two transports move the planes:
+
+  'p2p'   (default on GPUs) the shards are LINKED (gpb_link): every rank maps its neighbours' field arrays (CUDA IPC) and
+          the library pushes the boundary planes into the neighbour's ghost plane with peer stores over NVLink, announced by
+          flags in peer memory; a rank's whole iteration is one CUDA graph and `Solver.run(n)` advances n iterations with
+          no host round trip at all (DESIGN.md section 5);
+  'nccl'  host-driven: the boundary plane is computed first (gpb_half_step part 0), its pairwise isend/irecv is posted over
+          torch.distributed (NCCL on GPUs, gloo in the CPU tests), and the interior (part 1) runs while the planes travel.
 
 Every plane is advanced by the same kernels with the same operands as in a single-GPU run, so a
 sharded run reproduces the single-GPU result bit for bit (tests/test_gpu_sharded.py).
@@ -123,8 +128,7 @@ class GpuShard(object):
         self.torch = torch
         self.rank, self.world = rank, world
         self.x_start, self.nx_planes = partition_planes(G.nx, world)[rank]
-        if ID_local is None and getattr(G, 'ID', None) is not None:
-            ID_local = np.ascontiguousarray(G.ID[:, self.x_start:self.x_start + self.nx_planes])
+        # (ID_local None and G.ID global: the library reads the slab straight out of G.ID, solver.PackedModel)
         self.solver = Solver(G, device_id=device_id, x_start=self.x_start, nx_planes=self.nx_planes, ID=ID_local)
         self.device = torch.device('cuda', device_id)
         self.stream = torch.cuda.ExternalStream(self.solver.stream, device=self.device)
@@ -176,148 +180,66 @@ def run_sharded_local(shards, iterations):
         torch.cuda.synchronize()
 
 
-def solve_gpu_sharded(G, iterations=None, overlap=True, ID_local=None, timing=None):
+def link_neighbours(solver, rank, world, group=None):
+    """Exchange gpb_link_t records between the ranks and link `solver` to its x-neighbours (transport 'p2p')."""
+    import torch.distributed as dist
+    infos = [None] * world
+    dist.all_gather_object(infos, solver.link_info(), group=group)
+    solver.link(left=infos[rank - 1] if rank > 0 else None, right=infos[rank + 1] if rank < world - 1 else None)
+
+
+def solve_gpu_sharded(G, iterations=None, overlap=True, ID_local=None, timing=None, transport=None, results=None):
     """Run `G` sharded over all ranks of the default process group (call under torchrun).
     Returns (rxs, seconds): the R[9][iterations][nrx] receiver array (identical on every rank) and
-    the loop time (max over ranks, device-timed)."""
+    the loop time (max over ranks, device-timed).  `results` (a dict) additionally receives the gathered snapshots
+    ('snapshots': [6 arrays each]) and transmission-line totals ('tlines': [(V, I)])."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     local = int(os.environ.get('LOCAL_RANK', rank))
     torch.cuda.set_device(local)
+    transport = transport or os.environ.get('GPB_SHARD_TRANSPORT', 'p2p')
     shard = GpuShard(G, rank, world, local, ID_local=ID_local)
-    halo = HaloExchange(rank, world)
     nit = int(G.iterations if iterations is None else iterations)
-    with torch.cuda.stream(shard.stream):
-        # one untimed exchange sets up the NCCL channels
-        halo.wait(halo.post_h(*[shard._t[k] for k in ('send_h_a', 'send_h_b', 'recv_h_a', 'recv_h_b')]))
+    dev = shard.device
+    if transport == 'p2p':
+        link_neighbours(shard.solver, rank, world)
         torch.cuda.synchronize()
         dist.barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        run_sharded(shard, halo, nit, overlap=overlap)
-        ev1.record()
-        ev1.synchronize()
-        seconds = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], device=shard.device)
-        dist.all_reduce(seconds, op=dist.ReduceOp.MAX)
-        rxs = torch.from_numpy(shard.solver.receivers()).to(shard.device)
-        # a receiver is owned by exactly one rank and zero elsewhere: the sum is exact
-        dist.all_reduce(rxs, op=dist.ReduceOp.SUM)
-        # read back on the SAME stream: the library's stream is non-blocking, so a copy on torch's default stream outside this
-        # block is not ordered after the all-reduce (seen as a 1-in-20 flake: rank 0 stored its own receivers only)
-        out = rxs.cpu().numpy()
-        seconds_host = float(seconds.item())
-    torch.cuda.synchronize()
-    if timing is not None:
-        timing['launches'] = shard.solver.kernel_launches
-        timing['mem'] = shard.solver.mem_used
-    shard.close()
-    return out, seconds_host
-
-
-# ------------------------------------------------------------------------------------------ bench
-def bench_sharded(args):
-    """bench.py --gpus N (N > 1), launched by torchrun: weak-scaling x-slab sharded run of the synthetic
-    homogeneous lossy-dielectric domain (BASELINE.json configs[4] at N = 8)."""
-    import torch
-    import torch.distributed as dist
-    from benchkit.synthetic import homogeneous_model
-
-    # stdout carries exactly one JSON line: whatever libraries print to file descriptor 1 ("NCCL version ...", NCCL_DEBUG=INFO
-    # output) is sent to stderr, and the JSON line is written to the saved descriptor at the end
-    sys.stdout.flush()
-    out_fd = os.dup(1)
-    os.dup2(2, 1)
-    local = int(os.environ.get('LOCAL_RANK', os.environ.get('RANK', '0')))
-    torch.cuda.set_device(local)
-    if not dist.is_initialized():
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    rank, world = dist.get_rank(), dist.get_world_size()
-    per_gpu = int(os.environ.get('GPB_SHARD_PLANES', '256'))
-    ny, nz = int(os.environ.get('GPB_SHARD_NY', '2048')), int(os.environ.get('GPB_SHARD_NZ', '1024'))
-    nx = per_gpu * world
-    iters = args.iters or 20
-    total_its = iters * (args.warmup + args.steps)
-    # z-directed Hertzian dipole at the centre; one receiver on a cut plane, one inside a slab
-    cx, cy, cz = nx // 2, ny // 2, nz // 2
-    x_start, nplanes = partition_planes(nx, world)[rank]
-    cut = partition_planes(nx, world)[world // 2][0]   # first plane of the middle rank: its trace needs halo data
-    G = homogeneous_model((nx, ny, nz), iterations=total_its, er=6.0, se=0.01, src=(cx * 1e-3, cy * 1e-3, cz * 1e-3), src_pol='z',
-                          rxs=[(cut * 1e-3, (cy + 100) * 1e-3, cz * 1e-3), ((cx + 37) * 1e-3, (cy + 50) * 1e-3, cz * 1e-3)],
-                          x_range=(x_start, nplanes), build_id=False)
-    shard = GpuShard(G, rank, world, local)   # homogeneous: no host ID array, the library fills uniform_id
-    halo = HaloExchange(rank, world)
-    plane_bytes = shard.solver.halo(0)[2]
-    cells = nx * ny * nz
-    times = []
-    with torch.cuda.stream(shard.stream):
-        halo.wait(halo.post_h(*[shard._t[k] for k in ('send_h_a', 'send_h_b', 'recv_h_a', 'recv_h_b')]))
-        for s in range(args.warmup + args.steps):
+        shard.solver.run(nit)                      # graph-replayed iterations, halo pushed over peer memory
+        seconds = torch.tensor([shard.solver.elapsed], device=dev, dtype=torch.float64)
+    else:
+        halo = HaloExchange(rank, world)
+        with torch.cuda.stream(shard.stream):
+            # one untimed exchange sets up the NCCL channels
+            halo.wait(halo.post_h(*[shard._t[k] for k in ('send_h_a', 'send_h_b', 'recv_h_a', 'recv_h_b')]))
             torch.cuda.synchronize()
             dist.barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-            run_sharded(shard, halo, iters)
+            run_sharded(shard, halo, nit, overlap=overlap)
             ev1.record()
             ev1.synchronize()
-            torch.cuda.synchronize()
-            dist.barrier()
-            t = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], device=shard.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            if s >= args.warmup:
-                times.append(float(t.item()))
-    launches = torch.tensor([shard.solver.kernel_launches], device=shard.device, dtype=torch.int64)
-    dist.all_reduce(launches)
-    # ---- end-to-end leg: the public sharded call from HOST tables -- every call creates the shard (coefficient / PML /
-    # waveform tables host -> device, homogeneous ID fill on the device), runs `iters` iterations with halo exchange and
-    # copies the receiver traces back; host wall clock between barriers, max over ranks.  (The domain is homogeneous, so
-    # there is no per-cell host array to upload; the N = 1 benchmark is the one that moves a 654 MB ID array.)
+            seconds = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], device=dev, dtype=torch.float64)
+    torch.cuda.synchronize()
+    dist.all_reduce(seconds, op=dist.ReduceOp.MAX)
+
+    def gather(a):
+        # owned by exactly one rank and zero elsewhere: the sum is exact
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    out = gather(shard.solver.receivers())
+    if results is not None:
+        results['snapshots'] = [[gather(c) for c in shard.solver.snapshot(n)] for n in range(len(G.snapshots))]
+        results['tlines'] = [tuple(gather(v) for v in shard.solver.tline(n)) for n in range(len(G.transmissionlines))]
+    seconds_host = float(seconds.item())
+    torch.cuda.synchronize()
+    dist.barrier()                                 # nobody unlinks while a neighbour may still push into its planes
+    if timing is not None:
+        timing['launches'] = shard.solver.kernel_launches
+        timing['mem'] = shard.solver.mem_used
+        timing['transport'] = transport
     shard.close()
-    shard = None
-    e2e_t = []
-    for s in range(1 + max(args.steps, 3)):
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        rx_e2e, _ = solve_gpu_sharded(G, iterations=iters)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device=torch.device('cuda', local), dtype=torch.float64)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        if s >= 1:
-            e2e_t.append(float(dt.item()))
-    e2e_value = cells * iters / (float(np.median(e2e_t)) * 1e6)
-    real_bytes = np.dtype(G.updatecoeffsE.dtype).itemsize
-    h2d = G.updatecoeffsE.nbytes + G.updatecoeffsH.nbytes + sum(8 * p.ERA.nbytes for p in G.pmls) \
-        + sum(s_.waveformvalues_wholestep.nbytes for s_ in G.hertziandipoles) + 12 * len(G.rxs)
-    d2h = 9 * total_its * len(G.rxs) * real_bytes
-    t_step = float(np.mean(times))
-    value = cells * iters / (t_step * 1e6)
-    if rank == 0:
-        S = 2 * 10 * (ny * nz + nx * nz + nx * ny)
-        b_alg = 96.0 + 32.0 * S / cells
-        peak = 6456.8
-        try:
-            with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')) as f:
-                peak = float(json.load(f)['hbm_gbs'])
-        except Exception:
-            pass
-        line = {
-            'metric': 'FDTD throughput', 'value': value, 'unit': 'Mcells/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'synthetic {}x{}x{} lossy dielectric (er=6, sigma=0.01), x-slab sharded {} planes per GPU, z Hertzian dipole, '
-                                   '10-cell HORIPML, one-plane Ey/Ez and Hy/Hz halo per half-step over NCCL'.format(nx, ny, nz, per_gpu),
-                       'cells': cells, 'iterations_per_step': iters, 'l2': 'working set per GPU >> 126 MB L2', 'alg_bytes_per_cell_step': b_alg,
-                       'halo_bytes_per_interface_per_iteration': int(4 * plane_bytes)},
-            'roofline': {'bound': 'hbm', 'kernel': 'whole step (all ranks)', 'achieved': value * 1e6 * b_alg / 1e9 / world, 'peak': peak, 'unit': 'GB/s',
-                         'frac': value * 1e6 * b_alg / 1e9 / world / peak, 'traffic': None},
-            'cpu_baseline': None,
-            'e2e': {'value': e2e_value, 'unit': 'Mcells/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                    'call': 'gprmax_b200.sharded.solve_gpu_sharded(G, iterations) from host tables on every rank (homogeneous domain: '
-                            'IDs are filled on the device)', 'seconds_per_call': [round(t_, 4) for t_ in e2e_t], 'statistic': 'median'},
-            'gpu_launches': int(launches.item()),
-        }
-        sys.stdout.flush()
-        os.write(out_fd, (json.dumps(line) + '\n').encode())
-    dist.barrier()
-    dist.destroy_process_group()
-    return 0
+    return out, seconds_host

@@ -60,15 +60,24 @@ class PackedModel(object):
         m.iterations = int(G.iterations)
         if ID is None:
             ID = getattr(G, 'ID', None)
+        m.id_comp_stride = 0
         if ID is None:
             # homogeneous synthetic domain (synthetic.homogeneous_model(build_id=False)): no ID array at all
             m.ID = None
             m.uniform_id = int(G.fill_id)
         else:
             want = (6, m.nx_planes, m.ny + 1, m.nz + 1)
-            if tuple(ID.shape) != want:
+            whole = (6, m.nx + 1, m.ny + 1, m.nz + 1)
+            if tuple(ID.shape) == whole and want != whole:
+                # an x-slab of the global array: hand the library a pointer INTO G.ID with the global component stride -- the
+                # slab goes to the device plane by plane without a second host copy (gpb_model_t::id_comp_stride)
+                ID = self._hold(ID, np.uint32)
+                m.ID = C.c_void_p(ID.ctypes.data + m.x_start * ID.strides[1])
+                m.id_comp_stride = ID.strides[0] // 4
+            elif tuple(ID.shape) != want:
                 raise GeneralError('ID array has shape {}, expected {}'.format(tuple(ID.shape), want))
-            m.ID = _ptr(self._hold(ID, np.uint32))
+            else:
+                m.ID = _ptr(self._hold(ID, np.uint32))
         cE = self._hold(G.updatecoeffsE, real)
         cH = self._hold(G.updatecoeffsH, real)
         m.nmaterials = int(cE.shape[0])
@@ -159,13 +168,22 @@ class PackedModel(object):
 class Solver(object):
     """Handle-owning wrapper around one gpb_handle."""
 
-    def __init__(self, G, device_id=None, x_start=0, nx_planes=None, ID=None):
+    def __init__(self, G, device_id=None, x_start=0, nx_planes=None, ID=None, devices=None):
+        """device_id: CUDA runtime ordinal (default: G.gpu).  devices: a list of ordinals = ONE domain cut into x-slabs over
+        those devices inside this process (gpb_create_sharded); the handle then stands for the whole domain."""
         self.L = _lib.lib()
         self.G = G
-        if device_id is None:
-            gpu = getattr(G, 'gpu', None)
-            device_id = int(getattr(gpu, 'deviceID', 0) or 0)
+        gpu = getattr(G, 'gpu', None)
+        if device_id is None and devices is None:
+            ords = list(getattr(gpu, 'shard_ordinals', None) or [])
+            if len(ords) > 1:
+                devices = ords
+            else:
+                device_id = int(getattr(gpu, 'ordinal', getattr(gpu, 'deviceID', 0)) or 0)
+        if devices is not None and len(devices) == 1:
+            device_id, devices = int(devices[0]), None
         self.device_id = device_id
+        self.devices = None if devices is None else [int(d) for d in devices]
         packed = PackedModel(G, x_start=x_start, nx_planes=nx_planes, ID=ID)
         self.real = packed.real
         self.iterations = int(G.iterations)
@@ -173,7 +191,11 @@ class Solver(object):
         self.x_start = int(packed.model.x_start)
         self.nx_planes = int(packed.model.nx_planes)
         self.h = C.c_void_p()
-        rc = self.L.gpb_create(C.byref(packed.model), int(device_id), C.byref(self.h))
+        if self.devices is not None:
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            rc = self.L.gpb_create_sharded(C.byref(packed.model), arr, len(self.devices), C.byref(self.h))
+        else:
+            rc = self.L.gpb_create(C.byref(packed.model), int(device_id), C.byref(self.h))
         del packed  # the library has copied everything it needs
         if rc:
             self.h = None
@@ -250,6 +272,18 @@ class Solver(object):
         self._ck(self.L.gpb_stream(self.h, C.byref(v)))
         return v.value
 
+    def link_info(self):
+        """This slab's gpb_link_t (plain bytes: send it to the neighbouring ranks)."""
+        info = _lib.Link()
+        self._ck(self.L.gpb_link_info(self.h, C.byref(info)))
+        return bytes(info)
+
+    def link(self, left=None, right=None):
+        """Link this slab to its x-neighbours (their link_info() bytes, or None at a domain face); link() unlinks."""
+        l = _lib.Link.from_buffer_copy(left) if left is not None else None
+        r = _lib.Link.from_buffer_copy(right) if right is not None else None
+        self._ck(self.L.gpb_link(self.h, C.byref(l) if l is not None else None, C.byref(r) if r is not None else None))
+
     def halo(self, which):
         a, b, n = C.c_void_p(), C.c_void_p(), C.c_size_t(0)
         self._ck(self.L.gpb_halo(self.h, int(which), C.byref(a), C.byref(b), C.byref(n)))
@@ -313,7 +347,7 @@ def solve_gpu(currentmodelrun, modelend, G):
         tsolve (float): Time taken to execute solving (time loop incl. the final receiver copy)
         memsolve (int): device memory used by the solver in bytes
     """
-    solver = Solver(G)
+    solver = Solver(G)   # G.gpu decides: one device, or x-slabs over G.gpu.shard_ordinals (gprmax_b200/gpu.py)
     try:
         progress = bool(getattr(G, 'progressbars', False))
         total = int(G.iterations)

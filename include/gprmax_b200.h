@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GPB_ABI_VERSION 2
+#define GPB_ABI_VERSION 3
 
 enum { GPB_F32 = 0, GPB_F64 = 1 };
 enum { GPB_HORIPML = 0, GPB_MRIPML = 1 };                       /* pml.py:155 */
@@ -110,6 +110,9 @@ typedef struct gpb_model_t {
     int32_t iterations;
     int32_t nmaterials;
     const uint32_t *ID;                /* [6][nx_planes][ny+1][nz+1]; NULL = homogeneous: every edge is `uniform_id` */
+    int64_t id_comp_stride;            /* elements between the six components of ID; 0 = dense (nx_planes*(ny+1)*(nz+1)).  A shard
+                                          may point into the caller's global G.ID: ID = &G.ID[0][x_start][0][0] with the global
+                                          component stride (nx+1)*(ny+1)*(nz+1) -- no second host copy of the slab */
     int32_t uniform_id;                /* used only when ID == NULL (synthetic multi-billion-cell domains) */
     const void *updatecoeffsE;         /* R[nmaterials][5]  materials.py:200 */
     const void *updatecoeffsH;         /* R[nmaterials][5]  materials.py:201 */
@@ -173,6 +176,34 @@ int gpb_half_step(gpb_handle h, int phase, int part);
 int gpb_halo(gpb_handle h, int which, void **dptr_a, void **dptr_b, size_t *bytes_each);
 int gpb_stream(gpb_handle h, void **cuda_stream);
 int gpb_synchronize(gpb_handle h);
+
+/* ---- one domain over several GPUs of ONE process (the reference rejects models larger than one GPU, grid.py:239-241) ----
+ * gpb_create_sharded takes the GLOBAL model (x_start = 0, nx_planes = nx + 1, ID = the whole G.ID or NULL) and the
+ * device list of `-gpu 0 1 ...`; it cuts the nx + 1 node planes into contiguous x-slabs (one per device, slab by slab
+ * straight out of the caller's ID array), links neighbouring slabs over peer memory and returns ONE handle: gpb_run,
+ * gpb_get_receivers / _snapshot / _tline / _field, gpb_reset, gpb_mem_used ... then act on the whole domain.  Results are
+ * bit-identical to a single-GPU run of the same model. */
+int gpb_create_sharded(const gpb_model_t *global_model, const int *device_ids, int ndevices, gpb_handle *out);
+
+/* ---- linking shards that live in DIFFERENT processes (one process per GPU, e.g. under torchrun) ----
+ * Every rank creates its own slab handle (gpb_create with x_start / nx_planes), publishes gpb_link_info() to its two
+ * neighbours (any byte transport: the struct is plain data and carries CUDA IPC handles) and calls gpb_link with what it
+ * received.  From then on gpb_run advances the shard with the halo planes pushed into the neighbours' ghost planes by peer
+ * stores over NVLink and announced by flags in peer memory: no host round trip, no collective, the whole iteration is one
+ * CUDA graph.  gpb_link(h, NULL, NULL) unlinks.  Snapshots and transmission lines on a cut plane are supported in linked
+ * mode only (they need the neighbour's planes). */
+typedef struct gpb_link_t {
+    uint64_t process_id;               /* owner process */
+    int32_t device_id;                 /* CUDA runtime ordinal in the owner process */
+    int32_t dtype;
+    int32_t x_start, nx_planes, ny, nz;
+    uint64_t plane_elems, array_elems; /* elements per (padded) plane / per component array incl. the two ghost planes */
+    uint64_t fields_ptr, flags_ptr;    /* device addresses, valid inside the owner process */
+    unsigned char fields_ipc[64];      /* cudaIpcMemHandle_t of the field allocation */
+    unsigned char flags_ipc[64];       /* cudaIpcMemHandle_t of the flag words */
+} gpb_link_t;
+int gpb_link_info(gpb_handle h, gpb_link_t *out);
+int gpb_link(gpb_handle h, const gpb_link_t *left, const gpb_link_t *right);
 
 /* ---- results ---- */
 /* out: R[GPB_NRXOUT][iterations][nrx] (rows of fields_outputs.py:81-105 + Ix,Iy,Iz).  For a shard,

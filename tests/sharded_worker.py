@@ -34,11 +34,15 @@ def main():
     from gprmax_b200.model_io import load_model
     from gprmax_b200.sharded import solve_gpu_sharded
     fixture, out, overlap = sys.argv[1], sys.argv[2], sys.argv[3] == '1'
+    transport = sys.argv[4] if len(sys.argv) > 4 else 'nccl'
     dist.init_process_group('nccl')
     G = build(fixture)
-    rxs, seconds = solve_gpu_sharded(G, overlap=overlap)
+    res = {}
+    rxs, seconds = solve_gpu_sharded(G, overlap=overlap, transport=transport, results=res)
     if dist.get_rank() == 0:
         np.save(out, rxs)
+        if res.get('snapshots'):
+            np.savez(out + '.snaps.npz', **{'s{}_{}'.format(k, c): a for k, sn in enumerate(res['snapshots']) for c, a in enumerate(sn)})
     dist.barrier()
     dist.destroy_process_group()
 
