@@ -151,6 +151,28 @@ struct DevicePool {
 };
 DevicePool g_pool;
 
+// The reference sets OMP_PROC_BIND=TRUE for every model (input_cmds_singleuse.py:78-80), so by the time solve_gpu is called
+// the OpenMP runtime has bound the calling thread to ONE core.  Threads created from it inherit that mask: the CUDA driver's
+// helper threads (created when the context is initialised) and this library's upload threads would all share the caller's
+// core.  Entry points that may initialise CUDA or start threads therefore widen the calling thread's affinity to every CPU of
+// the process's cpuset for their duration and restore it on return.
+struct ScopedFullAffinity {
+    cpu_set_t saved;
+    bool have = false;
+    ScopedFullAffinity()
+    {
+        if (sched_getaffinity(0, sizeof saved, &saved) != 0) return;
+        cpu_set_t all;
+        CPU_ZERO(&all);
+        for (int c = 0; c < CPU_SETSIZE; ++c) CPU_SET(c, &all);
+        have = sched_setaffinity(0, sizeof all, &all) == 0;
+    }
+    ~ScopedFullAffinity()
+    {
+        if (have) sched_setaffinity(0, sizeof saved, &saved);
+    }
+};
+
 constexpr size_t kBounceBytes = 32u << 20;   // pinned bounce buffer / device stage of the ID upload
 
 // host -> pinned copy split over a few threads (one thread saturates at ~10 GB/s)
@@ -238,8 +260,11 @@ struct Solver : SolverBase {
     void *ID[6] = {0, 0, 0, 0, 0, 0};
     Coef4<R> *coefE = 0, *coefH = 0;
     R *srcE = 0, *srcH = 0;
-    Cplx<R> *T[3] = {0, 0, 0};
-    Cplx<R> *dcoef = 0;
+    Cplx<R> *T[3] = {0, 0, 0};   // treal: the allocation holds R[maxpoles][narr] instead
+    Cplx<R> *dcoef = 0;          // treal: R[nmat][maxpoles][3]
+    bool treal = false;          // all dispersive coefficients real (Debye media): real-valued T
+    bool tma_disp = false;       // dispersive E half-step on the TMA kernels
+    int tma_tpf = 2;
     int *d_iter = 0;  // [0] current, [1] next
     // receivers / sources / snapshots
     int nrx = 0;
@@ -723,9 +748,31 @@ int Solver<R>::build(const gpb_model_t &m)
     tabsmem = smem_bytes <= 96 * 1024;
     if (!tabsmem) smem_bytes = 0;
     if (maxpoles) {
-        for (int c = 0; c < 3; ++c)
-            if (dalloc(&T[c], (size_t)narr * maxpoles)) return 1;
-        if (upload(&dcoef, (const Cplx<R> *)m.updatecoeffsdispersive, (size_t)nmat * 3 * maxpoles)) return 1;
+        // Debye poles give real coefficients (materials.py:102-108: w, q real), Lorentz / Drude complex ones.  If every entry
+        // of the table is real, Im(T) stays zero for the whole run and T is held as a real array: half the traffic of the part
+        // that dominates a dispersive half-step, the same E bits (GPB_DISP_COMPLEX keeps the complex form)
+        const Cplx<R> *hc = (const Cplx<R> *)m.updatecoeffsdispersive;
+        const size_t ncoef = (size_t)nmat * 3 * maxpoles;
+        treal = !getenv("GPB_DISP_COMPLEX");
+        for (size_t q = 0; q < ncoef && treal; ++q)
+            if (hc[q].im != (R)0) treal = false;
+        if (treal) {
+            std::vector<R> re(ncoef);
+            for (size_t q = 0; q < ncoef; ++q) re[q] = hc[q].re;
+            R *d = nullptr;
+            if (upload(&d, re.data(), ncoef)) return 1;
+            CK(cudaStreamSynchronize(stream));
+            dcoef = reinterpret_cast<Cplx<R> *>(d);
+            for (int c = 0; c < 3; ++c) {
+                R *t = nullptr;
+                if (dalloc(&t, (size_t)narr * maxpoles)) return 1;
+                T[c] = reinterpret_cast<Cplx<R> *>(t);
+            }
+        } else {
+            for (int c = 0; c < 3; ++c)
+                if (dalloc(&T[c], (size_t)narr * maxpoles)) return 1;
+            if (upload(&dcoef, hc, ncoef)) return 1;
+        }
     }
     if (dalloc(&d_iter, 2)) return 1;
     CK(cudaMalloc((void **)&d_flags, GPB_NFLAGS * sizeof(unsigned)));
@@ -741,7 +788,7 @@ int Solver<R>::build(const gpb_model_t &m)
     }
     for (int c = 0; c < 3; ++c) { ph_e.ID[c] = ID[c]; ph_h.ID[c] = ID[3 + c]; }
     ph_e.coef = coefE; ph_e.src = srcE; ph_h.coef = coefH; ph_h.src = srcH;
-    ph_e.maxpoles = maxpoles; ph_e.dcoef = dcoef; ph_e.tstride = narr;
+    ph_e.maxpoles = maxpoles; ph_e.dcoef = dcoef; ph_e.tstride = narr; ph_e.treal = treal ? 1 : 0;
     for (int c = 0; c < 3; ++c) ph_e.T[c] = T[c];
     set_boxes();
     tick("coefficient tables");
@@ -764,6 +811,10 @@ int Solver<R>::build(const gpb_model_t &m)
     use_tma = use_v4 && nz + 1 >= 32 && ny + 1 >= 8 && !getenv("GPB_NO_TMA") && (size_t)nmat * (sizeof(Coef4<R>) + sizeof(R)) <= 32 * 1024 &&
               ((long long)nplanes * plane >= 2500000ll || getenv("GPB_FORCE_TMA"));
     if (use_tma && setup_tma()) return 1;
+    // dispersive E half-step on the TMA kernels: default tile, coefficient triples small enough for shared memory
+    tma_disp = use_tma && maxpoles > 0 && tma_ty == 14 && tma_tz == 64 && tma_stages == 3 && tma_pw == 1 && !getenv("GPB_DISP_V4") &&
+               (size_t)nmat * maxpoles * 3 * (treal ? 1 : 2) * sizeof(R) <= 24 * 1024;
+    tma_tpf = getenv("GPB_TMA_TPF") ? std::max(0, atoi(getenv("GPB_TMA_TPF"))) : 2;
     tick("tensor maps");
     if (use_v4) {
         for (int s = 0; s < ph_e.nslabs; ++s)
@@ -868,6 +919,8 @@ int Solver<R>::launch_tma(int phase, int p0, int p1)
     a.idbytes = idbytes;
     a.pf_max = tma_pf;
     a.nosplit = tma_nosplit ? 1 : 0;
+    a.disp = (phase == 1 && maxpoles) ? (treal ? 2 : 1) : 0;
+    a.t_max = tma_tpf;
     a.sm_count = sm_count;
     a.sched = d_sched;
     a.stream = stream;
@@ -982,9 +1035,7 @@ template <typename R>
 int Solver<R>::launch_phase(int phase, int p0, int p1)
 {
     if (p1 <= p0) return 0;
-    if (use_tma && !(phase == 1 && maxpoles)) {   // dispersive E half-step: register-vectorised kernel (T arrays are not TMA-staged)
-        return launch_tma(phase, p0, p1);
-    }
+    if (use_tma && !(phase == 1 && maxpoles && !tma_disp)) return launch_tma(phase, p0, p1);
     if (phase == 0) {
         if (idbytes == 1) return launch_h<uint8_t>(p0, p1);
         if (idbytes == 2) return launch_h<uint16_t>(p0, p1);
@@ -1335,13 +1386,15 @@ template <typename R>
 std::string Solver<R>::kernel_path() const
 {
     auto name = [&](int phase) -> std::string {
-        if (use_tma && !(phase == 1 && maxpoles)) {
+        const char *dn = treal ? "DISP=real" : "DISP=complex";
+        if (use_tma && !(phase == 1 && maxpoles && !tma_disp)) {
             char b[96];
-            snprintf(b, sizeof b, "k_update_tma<%dx%d,PHASE=%d>", tma_ty, tma_tz, phase);
+            if (phase == 1 && maxpoles) snprintf(b, sizeof b, "k_update_tma<%dx%d,PHASE=1,%s>", tma_ty, tma_tz, dn);
+            else snprintf(b, sizeof b, "k_update_tma<%dx%d,PHASE=%d>", tma_ty, tma_tz, phase);
             return b;
         }
-        if (use_v4) return phase == 0 ? "k_update_h4" : (maxpoles ? "k_update_e4<DISP>" : "k_update_e4");
-        return phase == 0 ? "k_update_h" : (maxpoles ? "k_update_e<DISP>" : "k_update_e");
+        if (use_v4) return phase == 0 ? "k_update_h4" : (maxpoles ? std::string("k_update_e4<") + dn + ">" : "k_update_e4");
+        return phase == 0 ? "k_update_h" : (maxpoles ? std::string("k_update_e<") + dn + ">" : "k_update_e");
     };
     return "H:" + name(0) + " E:" + name(1);
 }
@@ -1423,7 +1476,7 @@ int Solver<R>::reset()
     CK(cudaSetDevice(device));
     for (int c = 0; c < 6; ++c) CK(cudaMemsetAsync(F[c], 0, (size_t)narr * sizeof(R), stream));
     for (int c = 0; c < 3; ++c)
-        if (T[c]) CK(cudaMemsetAsync(T[c], 0, (size_t)narr * maxpoles * sizeof(Cplx<R>), stream));
+        if (T[c]) CK(cudaMemsetAsync(T[c], 0, (size_t)narr * maxpoles * (treal ? sizeof(R) : sizeof(Cplx<R>)), stream));
     for (auto &ph : phis) CK(cudaMemsetAsync(ph.first, 0, ph.second * sizeof(R), stream));
     CK(cudaMemsetAsync(d_rxs, 0, (size_t)GPB_NRXOUT * iterations * std::max(nrx, 1) * sizeof(R), stream));
     CK(cudaMemsetAsync(d_iter, 0, 2 * sizeof(int), stream));
@@ -1712,6 +1765,7 @@ const char *gpb_version(void) { return "gprmax_b200 0.1 (sm_100a)"; }
 int gpb_device_count(int *count)
 {
     if (!count) return fail("null argument");
+    ScopedFullAffinity aff;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) {
@@ -1726,6 +1780,7 @@ int gpb_device_count(int *count)
 int gpb_device_info(int device_id, gpb_device_info_t *out)
 {
     if (!out) return fail("null argument");
+    ScopedFullAffinity aff;
     cudaDeviceProp pr;
     CK(cudaGetDeviceProperties(&pr, device_id));
     memset(out, 0, sizeof *out);
@@ -1744,6 +1799,7 @@ int gpb_device_info(int device_id, gpb_device_info_t *out)
 int gpb_create(const gpb_model_t *model, int device_id, gpb_handle *out)
 {
     if (!model || !out) return fail("null argument");
+    ScopedFullAffinity aff;
     *out = nullptr;
     if (model->abi_version != GPB_ABI_VERSION) return fail("ABI version mismatch: library %d, caller %d", GPB_ABI_VERSION, model->abi_version);
     int n = 0;
@@ -1778,6 +1834,7 @@ int gpb_create(const gpb_model_t *model, int device_id, gpb_handle *out)
 int gpb_create_sharded(const gpb_model_t *model, const int *device_ids, int ndevices, gpb_handle *out)
 {
     if (!model || !out || !device_ids) return fail("null argument");
+    ScopedFullAffinity aff;
     *out = nullptr;
     if (model->abi_version != GPB_ABI_VERSION) return fail("ABI version mismatch: library %d, caller %d", GPB_ABI_VERSION, model->abi_version);
     int n = 0;

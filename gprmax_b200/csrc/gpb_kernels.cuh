@@ -84,9 +84,11 @@ struct PhaseParams {
     SlabDev<R> slab[kMaxSlabs];
     // dispersive (E phase only)
     int maxpoles;
-    Cplx<R> *T[3];            // [maxpoles][nplanes+2][ny+1][pitch]
-    const Cplx<R> *dcoef;     // [nmat][maxpoles][3]
+    Cplx<R> *T[3];            // [maxpoles][nplanes+2][ny+1][pitch]   (treal: the same memory holds R instead of complex)
+    const Cplx<R> *dcoef;     // [nmat][maxpoles][3]                  (treal: R[nmat][maxpoles][3], the real parts)
     long long tstride;        // elements between poles
+    int treal;                // every dispersive coefficient is real (Debye media): T is stored and advanced as a real array --
+                              // half the bytes of the part that dominates a dispersive half-step; same E bits as the complex form
     // sub-range of owned planes processed by this launch (for halo overlap): [p0, p1)
     int p0, p1;
     int xchunk;               // planes marched by one CTA of the TMA kernels
@@ -96,6 +98,7 @@ struct PhaseParams {
     int tmax;                 // TMA kernels: row length of the shared-memory copies of the PML R tables (max thickness)
     int pf_depth;             // TMA kernels: Phi prefetch distance in planes (cp.async ring per thread), 0 = direct loads
     int persist;              // TMA kernels: persistent CTAs pulling (tile, x-chunk) items from an atomic counter
+    int t_depth;              // TMA kernels, dispersive E half-step: T prefetch distance in planes (cp.async ring per thread), 0 = direct loads
 };
 
 // ------------------------------------------------------------------------------------------
@@ -345,28 +348,63 @@ __global__ void __launch_bounds__(kThreads) k_update_h(const PhaseParams<R> p)
 }
 
 // ------------------------------------------------------------------------------------------
-// Dispersive helper: fold part B of the previous step (fields_updates_ext.pyx:183-235) into part A
-// of this one (:113-179).  `phi` is a float even in the float64 build (:143), reproduced here.
+// Dispersive media.  Part B of the previous step (fields_updates_ext.pyx:183-235: T -= c2 E, after the PML and the sources)
+// is folded into part A of this one (:113-179), because E is not touched in between: one pass over E, ID and T per step
+// disappears.  Per cell and pole, with c0 = Re(e0 eqt2), c1 = eqt, c2 = zt (materials.py:204-208):
+//     t    = T - c2 E_old                 (part B, deferred)
+//     phi += c0 Re(t)                     (`phi` is a C float in the reference even in its float64 build, :143)
+//     T    = c1 t + c2 E_old              (part A)
+// and E_new = (base update) - srce phi.  The products and sums are placed explicitly (mul_ / fma_), identically in every
+// kernel family, like the field update itself.  When every coefficient of the model is real (Debye poles), Im(T) stays zero
+// and T is kept as a real array (PhaseParams::treal): the real form below gives the same bits as the complex one.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float phi_acc(float phi, float c0, float re) { return fma_(c0, re, phi); }
+__device__ __forceinline__ float phi_acc(float phi, double c0, double re) { return (float)fma_(c0, re, (double)phi); }
+
 template <typename R>
-__device__ __forceinline__ R dispersive_AB(const PhaseParams<R> &p, int comp, unsigned m, long long off, R e_old)
+__device__ __forceinline__ void disp_cell_c(const Cplx<R> *dc, R e_old, R &tre, R &tim, float &phi)
+{
+    const Cplx<R> c0 = dc[0], c1 = dc[1], c2 = dc[2];
+    const R re = fma_(-c2.re, e_old, tre), im = fma_(-c2.im, e_old, tim);
+    phi = phi_acc(phi, c0.re, re);
+    tre = fma_(c2.re, e_old, fma_(-c1.im, im, mul_(c1.re, re)));
+    tim = fma_(c2.im, e_old, fma_(c1.im, re, mul_(c1.re, im)));
+}
+template <typename R>
+__device__ __forceinline__ void disp_cell_r(const R *dc, R e_old, R &t, float &phi)
+{
+    const R c0 = dc[0], c1 = dc[1], c2 = dc[2];
+    const R re = fma_(-c2, e_old, t);
+    phi = phi_acc(phi, c0, re);
+    t = fma_(c2, e_old, mul_(c1, re));
+}
+// E_new = base - srce phi
+template <typename R>
+__device__ __forceinline__ R disp_sub(R base, R srce, float phi) { return fma_(-srce, (R)phi, base); }
+
+// one cell, all poles, T in global memory (scalar kernels)
+template <typename R>
+__device__ __forceinline__ float dispersive_AB(const PhaseParams<R> &p, int comp, unsigned m, long long off, R e_old)
 {
     float phi = 0;
-    const Cplx<R> *dc = p.dcoef + (long long)m * p.maxpoles * 3;
-    Cplx<R> *T = p.T[comp] + off;
-    for (int q = 0; q < p.maxpoles; ++q, T += p.tstride, dc += 3) {
-        const Cplx<R> c0 = dc[0], c1 = dc[1], c2 = dc[2];
-        Cplx<R> t = *T;
-        // part B of the previous step: T -= c2 * E   (E unchanged since then)
-        t.re = t.re - c2.re * e_old;
-        t.im = t.im - c2.im * e_old;
-        phi = phi + c0.re * t.re;
-        Cplx<R> tn;
-        tn.re = (c1.re * t.re - c1.im * t.im) + c2.re * e_old;
-        tn.im = (c1.re * t.im + c1.im * t.re) + c2.im * e_old;
-        *T = tn;
+    if (p.treal) {
+        const R *dc = reinterpret_cast<const R *>(p.dcoef) + (long long)m * p.maxpoles * 3;
+        R *T = reinterpret_cast<R *>(p.T[comp]) + off;
+        for (int q = 0; q < p.maxpoles; ++q, T += p.tstride, dc += 3) {
+            R t = *T;
+            disp_cell_r(dc, e_old, t, phi);
+            *T = t;
+        }
+    } else {
+        const Cplx<R> *dc = p.dcoef + (long long)m * p.maxpoles * 3;
+        Cplx<R> *T = p.T[comp] + off;
+        for (int q = 0; q < p.maxpoles; ++q, T += p.tstride, dc += 3) {
+            Cplx<R> t = *T;
+            disp_cell_c(dc, e_old, t.re, t.im, phi);
+            *T = t;
+        }
     }
-    return (R)phi;
+    return phi;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -414,8 +452,8 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
             mx = ld_id<IDT>(p.ID[0], off);
             const Coef4<R> c = coef[mx];
             if (DISP) {
-                const R phi = dispersive_AB(p, 0, mx, off, ex);
-                ex = upd3(c.a, ex, c.by, dHz_dy, -c.bz, dHy_dz) - srce[mx] * phi;
+                const float phi = dispersive_AB(p, 0, mx, off, ex);
+                ex = disp_sub(upd3(c.a, ex, c.by, dHz_dy, -c.bz, dHy_dz), srce[mx], phi);
             } else {
                 ex = upd3(c.a, ex, c.by, dHz_dy, -c.bz, dHy_dz);
             }
@@ -425,8 +463,8 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
             my = ld_id<IDT>(p.ID[1], off);
             const Coef4<R> c = coef[my];
             if (DISP) {
-                const R phi = dispersive_AB(p, 1, my, off, ey);
-                ey = upd3(c.a, ey, c.bz, dHx_dz, -c.bx, dHz_dx) - srce[my] * phi;
+                const float phi = dispersive_AB(p, 1, my, off, ey);
+                ey = disp_sub(upd3(c.a, ey, c.bz, dHx_dz, -c.bx, dHz_dx), srce[my], phi);
             } else {
                 ey = upd3(c.a, ey, c.bz, dHx_dz, -c.bx, dHz_dx);
             }
@@ -436,8 +474,8 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
             mz = ld_id<IDT>(p.ID[2], off);
             const Coef4<R> c = coef[mz];
             if (DISP) {
-                const R phi = dispersive_AB(p, 2, mz, off, ez);
-                ez = upd3(c.a, ez, c.bx, dHy_dx, -c.by, dHx_dy) - srce[mz] * phi;
+                const float phi = dispersive_AB(p, 2, mz, off, ez);
+                ez = disp_sub(upd3(c.a, ez, c.bx, dHy_dx, -c.by, dHx_dy), srce[mz], phi);
             } else {
                 ez = upd3(c.a, ez, c.bx, dHy_dx, -c.by, dHx_dy);
             }

@@ -263,7 +263,7 @@ __device__ __forceinline__ void pml_comp(int form, int order, const R *tb, int t
 #ifndef GPB_TMA_CTAS
 #define GPB_TMA_CTAS 2
 #endif
-template <typename R, typename IDT, int TY, int TZ, int kStages, int PHASE, int PW, int PV>
+template <typename R, typename IDT, int TY, int TZ, int kStages, int PHASE, int PW, int PV, int DISP = 0>
 __global__ void __launch_bounds__(TY * TZ / 4 + 32 * PW, (sizeof(R) == 4 ? GPB_TMA_CTAS : 1))
 k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int tiles_k, int tiles, int nchunks, int nsplit, int *sched)
 {
@@ -272,6 +272,10 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     // PML formulation and order are compile-time (PV = 2 * form + order - 1): with both at run time the four inlined variants of
     // every correction spilled ~500 bytes of the straight-line update of every thread (47 -> 15 Gcells/s at 300^3)
     constexpr int PFORM = PV >> 1, PORDER = (PV & 1) + 1;
+    // DISP (electric half-step only): 0 no dispersive media, 1 complex T, 2 real T (Debye media) -- the polarisation arrays are
+    // read and written once per step by the thread that owns the cells, prefetched like Phi (per-thread cp.async, p.t_depth)
+    static_assert(DISP == 0 || PHASE == 1, "dispersive update belongs to the electric half-step");
+    constexpr int TW = DISP == 1 ? 2 : 1;   // V4 vectors per 4 cells of T
     using L = StageLayout<R, IDT, TY, TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);   // [kStages] TMA bytes landed
@@ -284,7 +288,13 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     const int tab_bytes = (int)((p.nslabs * 4 * PORDER * p.tmax * sizeof(R) + 127) / 128 * 128);
     V4<R> *spf = reinterpret_cast<V4<R> *>(smem_raw + 128 + coef_bytes + tab_bytes);   // Phi prefetch [pf_depth][2*order][threads]
     const int pf_bytes = p.pf_depth * 2 * PORDER * kTmaThreads * (int)sizeof(V4<R>);
-    unsigned char *stages = smem_raw + 128 + coef_bytes + tab_bytes + pf_bytes;
+    // dispersive: coefficient triples [nmat][poles][3] (R or complex) and the T prefetch slots [t_depth][3 comps][poles][TW][threads]
+    R *sdc = reinterpret_cast<R *>(smem_raw + 128 + coef_bytes + tab_bytes + pf_bytes);
+    const int dc_bytes = DISP ? (int)((p.nmat * p.maxpoles * 3 * TW * sizeof(R) + 127) / 128 * 128) : 0;
+    V4<R> *stf = reinterpret_cast<V4<R> *>(smem_raw + 128 + coef_bytes + tab_bytes + pf_bytes + dc_bytes);
+    const int tslot = DISP ? 3 * p.maxpoles * TW * kTmaThreads : 0;   // V4 vectors per plane of T slots
+    const int tf_bytes = DISP ? p.t_depth * tslot * (int)sizeof(V4<R>) : 0;
+    unsigned char *stages = smem_raw + 128 + coef_bytes + tab_bytes + pf_bytes + dc_bytes + tf_bytes;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int W = tiles * (nchunks + nsplit);
@@ -305,6 +315,10 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     for (int m = tid; m < p.nmat; m += kTmaThreads + 32 * PW) {
         scoef[m] = p.coef[m];
         ssrc[m] = p.src[m];
+    }
+    if (DISP) {
+        const R *src = reinterpret_cast<const R *>(p.dcoef);
+        for (int m = tid; m < p.nmat * p.maxpoles * 3 * TW; m += kTmaThreads + 32 * PW) sdc[m] = src[m];
     }
     for (int s = 0; s < p.nslabs; ++s) {
         const SlabDev<R> &sl = p.slab[s];
@@ -502,17 +516,77 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     }
     const bool act_same = act_all == act_some;
     auto act_of = [&](int n) { return act_same ? act_all : slabs_on_plane(p, i_of(n)); };
-    if (pf && p.pf_depth == 2) {
-        if (act_of(0) & smask6) prefetch(spf + tid, act_of(0) & smask6, i_of(0));
+    // T prefetch (dispersive): every thread with cells on the grid fetches its 4 cells of every pole and component
+    const bool tpf = DISP && p.t_depth > 0 && any;
+    auto tprefetch = [&](V4<R> *slot, int n) {   // T of plane n of this item -> my slots [comp][pole][TW]
+        const long long off = (long long)(PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1)) * p.plane + eoff;
+        for (int cq = 0; cq < 3 * p.maxpoles; ++cq) {
+            const R *g = reinterpret_cast<const R *>(p.T[cq / p.maxpoles]) + ((long long)(cq % p.maxpoles) * p.tstride + off) * TW;
+            for (int w = 0; w < TW; ++w) cp_async_v4<R>(slot + (cq * TW + w) * kTmaThreads, g + 4 * w);
+        }
+    };
+    // One cp.async group per plane, committed at the top of the loop body, holds whatever is fetched then: Phi and / or T of
+    // this plane (distance 1) or of the next one (distance 2).  Data of distance 2 is complete after wait_group 1, of distance 1
+    // after wait_group 0.  A distance-2 user needs one group in front of the loop for plane 0.
+    const bool pf2 = pf && p.pf_depth == 2, tpf2 = tpf && p.t_depth == 2;
+    // (the commits are uniform per thread; whether a thread has anything in the group does not matter)
+    const bool grouped = (p.pf_depth > 0 && p.nslabs > 0) || (DISP && p.t_depth > 0);
+    const bool lead_group = (p.pf_depth == 2 && p.nslabs > 0) || (DISP && p.t_depth == 2);
+    if (lead_group) {
+        if (pf2 && (act_of(0) & smask6)) prefetch(spf + tid, act_of(0) & smask6, i_of(0));
+        if (tpf2) tprefetch(stf + tid, 0);
         cp_async_commit();
     }
 
+    // dispersive sum of one component on my 4 cells (all poles): T from my prefetch slot or from global memory, advanced and
+    // written back; u = base update - srce * phi on the cells inside the component's update box
+    auto disp_apply = [&](int comp, const IdQ<IDT> &idq, unsigned m, const V4<R> &eold, V4<R> &u, int n, int pl) {
+        if (!m) return;
+        float ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0;
+        const unsigned i0 = idq.at(0);
+        unsigned i1 = i0, i2 = i0, i3 = i0;
+        if (!idq.uniform()) { i1 = idq.at(1); i2 = idq.at(2); i3 = idq.at(3); }
+        const int P = p.maxpoles;
+        R *Tg = reinterpret_cast<R *>(p.T[comp]) + ((long long)pl * p.plane + eoff) * TW;
+        const V4<R> *slot = tpf ? stf + (size_t)(n % p.t_depth) * tslot + (size_t)comp * P * TW * kTmaThreads + tid : nullptr;
+        for (int q = 0; q < P; ++q) {
+            R *Tq = Tg + (long long)q * p.tstride * TW;
+            if (DISP == 2) {
+                V4<R> t = slot ? slot[(size_t)q * kTmaThreads] : ld4(Tq);
+                if (m & 1u) disp_cell_r(sdc + ((size_t)i0 * P + q) * 3, eold.x, t.x, ph0);
+                if (m & 2u) disp_cell_r(sdc + ((size_t)i1 * P + q) * 3, eold.y, t.y, ph1);
+                if (m & 4u) disp_cell_r(sdc + ((size_t)i2 * P + q) * 3, eold.z, t.z, ph2);
+                if (m & 8u) disp_cell_r(sdc + ((size_t)i3 * P + q) * 3, eold.w, t.w, ph3);
+                st4(Tq, t);
+            } else {
+                const Cplx<R> *dc = reinterpret_cast<const Cplx<R> *>(sdc);
+                V4<R> t01 = slot ? slot[(size_t)(2 * q) * kTmaThreads] : ld4(Tq), t23 = slot ? slot[(size_t)(2 * q + 1) * kTmaThreads] : ld4(Tq + 4);
+                if (m & 1u) disp_cell_c(dc + ((size_t)i0 * P + q) * 3, eold.x, t01.x, t01.y, ph0);
+                if (m & 2u) disp_cell_c(dc + ((size_t)i1 * P + q) * 3, eold.y, t01.z, t01.w, ph1);
+                if (m & 4u) disp_cell_c(dc + ((size_t)i2 * P + q) * 3, eold.z, t23.x, t23.y, ph2);
+                if (m & 8u) disp_cell_c(dc + ((size_t)i3 * P + q) * 3, eold.w, t23.z, t23.w, ph3);
+                st4(Tq, t01);
+                st4(Tq + 4, t23);
+            }
+        }
+        u.x = disp_sub(u.x, ssrc[i0], ph0);
+        u.y = disp_sub(u.y, ssrc[i1], ph1);
+        u.z = disp_sub(u.z, ssrc[i2], ph2);
+        u.w = disp_sub(u.w, ssrc[i3], ph3);
+    };
+
     for (int n = 0; n < nl; ++n, ++g) {
         const unsigned act = act_of(n);
-        if (pf) {
-            const int np = n + p.pf_depth - 1;   // plane fetched now
-            const unsigned pmn = (p.pf_depth == 2 ? (n + 1 < nl ? act_of(n + 1) : 0u) : act) & smask6;
-            if (pmn) prefetch(spf + (size_t)(np % p.pf_depth) * 2 * PORDER * kTmaThreads + tid, pmn, i_of(np));
+        if (grouped) {
+            if (pf) {
+                const int np = n + p.pf_depth - 1;   // plane fetched now
+                const unsigned pmn = (p.pf_depth == 2 ? (n + 1 < nl ? act_of(n + 1) : 0u) : act) & smask6;
+                if (pmn) prefetch(spf + (size_t)(np % p.pf_depth) * 2 * PORDER * kTmaThreads + tid, pmn, i_of(np));
+            }
+            if (tpf) {
+                const int np = n + p.t_depth - 1;
+                if (np < nl) tprefetch(stf + (size_t)(np % p.t_depth) * tslot + tid, np);
+            }
             cp_async_commit();
         }
         const int pl = PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1);
@@ -601,6 +675,10 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                     u.z = upd3(q2.a, f0.z, -q2.by, dC_dy.z, q2.bz, dB_dz.z);
                     u.w = upd3(q3.a, f0.w, -q3.by, dC_dy.w, q3.bz, dB_dz.w);
                 }
+                if (DISP) {
+                    if (tpf) { if (p.t_depth == 2) cp_async_wait1(); else cp_async_wait0(); }
+                    disp_apply(0, id0, m0, f0, u, n, pl);
+                }
                 if (!fast) { u.x = sel(m0, 0, u.x, f0.x); u.y = sel(m0, 1, u.y, f0.y); u.z = sel(m0, 2, u.z, f0.z); u.w = sel(m0, 3, u.w, f0.w); }
                 f0 = u;
             }
@@ -627,6 +705,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                     u.z = upd3(q2.a, f1.z, -q2.bz, dA_dz.z, q2.bx, dC_dx.z);
                     u.w = upd3(q3.a, f1.w, -q3.bz, dA_dz.w, q3.bx, dC_dx.w);
                 }
+                if (DISP) disp_apply(1, id1, m1, f1, u, n, pl);
                 if (!fast) { u.x = sel(m1, 0, u.x, f1.x); u.y = sel(m1, 1, u.y, f1.y); u.z = sel(m1, 2, u.z, f1.z); u.w = sel(m1, 3, u.w, f1.w); }
                 f1 = u;
             }
@@ -653,6 +732,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
                     u.z = upd3(q2.a, f2.z, -q2.bx, dB_dx.z, q2.by, dA_dy.z);
                     u.w = upd3(q3.a, f2.w, -q3.bx, dB_dx.w, q3.by, dA_dy.w);
                 }
+                if (DISP) disp_apply(2, id2, m2, f2, u, n, pl);
                 if (!fast) { u.x = sel(m2, 0, u.x, f2.x); u.y = sel(m2, 1, u.y, f2.y); u.z = sel(m2, 2, u.z, f2.z); u.w = sel(m2, 3, u.w, f2.w); }
                 f2 = u;
             }

@@ -266,34 +266,36 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(cons
     }
 }
 
-// Dispersive sum for 4 cells of one component: part B of the previous step folded into part A of this one,
-// same arithmetic as dispersive_AB() in gpb_kernels.cuh (fields_updates_ext.pyx:113-235; `phi` is a C float
-// there even in the float64 build).  T is complex[pole][cells]; 4 cells = two 128-bit (fp32) accesses.
+// Dispersive sum for 4 cells of one component: part B of the previous step folded into part A of this one, the per-cell
+// arithmetic of gpb_kernels.cuh (disp_cell_c / disp_cell_r).  Complex T: complex[pole][cells], 4 cells = two 128-bit (fp32)
+// accesses; real T (Debye media, p.treal): R[pole][cells], one access.  Cells outside the update box keep their T.
 template <typename R>
-__device__ __forceinline__ void disp4(const PhaseParams<R> &p, int comp, const Ids4 &id, long long off, unsigned m, const V4<R> &e, V4<R> &phi)
+__device__ __forceinline__ void disp4(const PhaseParams<R> &p, int comp, const Ids4 &id, long long off, unsigned m, const V4<R> &e, float (&ph)[4])
 {
-    float ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0;
-    R *T = reinterpret_cast<R *>(p.T[comp] + off);
-    for (int q = 0; q < p.maxpoles; ++q, T += 2 * p.tstride) {
-        V4<R> t01 = ld4(T), t23 = ld4(T + 4);
-#define GPB_DCELL(bit, idv, ev, tre, tim, ph)                                              \
-    if ((m >> bit) & 1u) {                                                                 \
-        const Cplx<R> *dc = p.dcoef + ((long long)(idv) * p.maxpoles + q) * 3;             \
-        const Cplx<R> c0 = dc[0], c1 = dc[1], c2 = dc[2];                                  \
-        const R re = tre - c2.re * (ev), im = tim - c2.im * (ev);                          \
-        ph = ph + c0.re * re;                                                              \
-        tre = (c1.re * re - c1.im * im) + c2.re * (ev);                                    \
-        tim = (c1.re * im + c1.im * re) + c2.im * (ev);                                    \
+    ph[0] = ph[1] = ph[2] = ph[3] = 0;
+    if (p.treal) {
+        R *T = reinterpret_cast<R *>(p.T[comp]) + off;
+        const R *dc = reinterpret_cast<const R *>(p.dcoef);
+        for (int q = 0; q < p.maxpoles; ++q, T += p.tstride) {
+            V4<R> t = ld4(T);
+            if (m & 1u) disp_cell_r(dc + ((long long)id.a * p.maxpoles + q) * 3, e.x, t.x, ph[0]);
+            if (m & 2u) disp_cell_r(dc + ((long long)id.b * p.maxpoles + q) * 3, e.y, t.y, ph[1]);
+            if (m & 4u) disp_cell_r(dc + ((long long)id.c * p.maxpoles + q) * 3, e.z, t.z, ph[2]);
+            if (m & 8u) disp_cell_r(dc + ((long long)id.d * p.maxpoles + q) * 3, e.w, t.w, ph[3]);
+            st4(T, t);
+        }
+    } else {
+        R *T = reinterpret_cast<R *>(p.T[comp] + off);
+        for (int q = 0; q < p.maxpoles; ++q, T += 2 * p.tstride) {
+            V4<R> t01 = ld4(T), t23 = ld4(T + 4);
+            if (m & 1u) disp_cell_c(p.dcoef + ((long long)id.a * p.maxpoles + q) * 3, e.x, t01.x, t01.y, ph[0]);
+            if (m & 2u) disp_cell_c(p.dcoef + ((long long)id.b * p.maxpoles + q) * 3, e.y, t01.z, t01.w, ph[1]);
+            if (m & 4u) disp_cell_c(p.dcoef + ((long long)id.c * p.maxpoles + q) * 3, e.z, t23.x, t23.y, ph[2]);
+            if (m & 8u) disp_cell_c(p.dcoef + ((long long)id.d * p.maxpoles + q) * 3, e.w, t23.z, t23.w, ph[3]);
+            st4(T, t01);
+            st4(T + 4, t23);
+        }
     }
-        GPB_DCELL(0, id.a, e.x, t01.x, t01.y, ph0)
-        GPB_DCELL(1, id.b, e.y, t01.z, t01.w, ph1)
-        GPB_DCELL(2, id.c, e.z, t23.x, t23.y, ph2)
-        GPB_DCELL(3, id.d, e.w, t23.z, t23.w, ph3)
-#undef GPB_DCELL
-        st4(T, t01);
-        st4(T + 4, t23);
-    }
-    phi = {(R)ph0, (R)ph1, (R)ph2, (R)ph3};
 }
 
 // ------------------------------------------------------------------------------------------
@@ -383,12 +385,12 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
                 Coef4<R> c0, c1, c2, c3;
                 coef4(coef, idx_, c0, c1, c2, c3);
                 if (DISP) {
-                    V4<R> ph;
+                    float ph[4];
                     disp4(p, 0, idx_, off, mx, ex, ph);
-                    ex.x = sel(mx, 0, upd3(c0.a, ex.x, c0.by, dHz_dy.x, -c0.bz, dHy_dz.x) - srce[idx_.a] * ph.x, ex.x);
-                    ex.y = sel(mx, 1, upd3(c1.a, ex.y, c1.by, dHz_dy.y, -c1.bz, dHy_dz.y) - srce[idx_.b] * ph.y, ex.y);
-                    ex.z = sel(mx, 2, upd3(c2.a, ex.z, c2.by, dHz_dy.z, -c2.bz, dHy_dz.z) - srce[idx_.c] * ph.z, ex.z);
-                    ex.w = sel(mx, 3, upd3(c3.a, ex.w, c3.by, dHz_dy.w, -c3.bz, dHy_dz.w) - srce[idx_.d] * ph.w, ex.w);
+                    ex.x = sel(mx, 0, disp_sub(upd3(c0.a, ex.x, c0.by, dHz_dy.x, -c0.bz, dHy_dz.x), srce[idx_.a], ph[0]), ex.x);
+                    ex.y = sel(mx, 1, disp_sub(upd3(c1.a, ex.y, c1.by, dHz_dy.y, -c1.bz, dHy_dz.y), srce[idx_.b], ph[1]), ex.y);
+                    ex.z = sel(mx, 2, disp_sub(upd3(c2.a, ex.z, c2.by, dHz_dy.z, -c2.bz, dHy_dz.z), srce[idx_.c], ph[2]), ex.z);
+                    ex.w = sel(mx, 3, disp_sub(upd3(c3.a, ex.w, c3.by, dHz_dy.w, -c3.bz, dHy_dz.w), srce[idx_.d], ph[3]), ex.w);
                 } else {
                 ex.x = sel(mx, 0, upd3(c0.a, ex.x, c0.by, dHz_dy.x, -c0.bz, dHy_dz.x), ex.x);
                 ex.y = sel(mx, 1, upd3(c1.a, ex.y, c1.by, dHz_dy.y, -c1.bz, dHy_dz.y), ex.y);
@@ -400,12 +402,12 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
                 Coef4<R> c0, c1, c2, c3;
                 coef4(coef, idy_, c0, c1, c2, c3);
                 if (DISP) {
-                    V4<R> ph;
+                    float ph[4];
                     disp4(p, 1, idy_, off, my, ey, ph);
-                    ey.x = sel(my, 0, upd3(c0.a, ey.x, c0.bz, dHx_dz.x, -c0.bx, dHz_dx.x) - srce[idy_.a] * ph.x, ey.x);
-                    ey.y = sel(my, 1, upd3(c1.a, ey.y, c1.bz, dHx_dz.y, -c1.bx, dHz_dx.y) - srce[idy_.b] * ph.y, ey.y);
-                    ey.z = sel(my, 2, upd3(c2.a, ey.z, c2.bz, dHx_dz.z, -c2.bx, dHz_dx.z) - srce[idy_.c] * ph.z, ey.z);
-                    ey.w = sel(my, 3, upd3(c3.a, ey.w, c3.bz, dHx_dz.w, -c3.bx, dHz_dx.w) - srce[idy_.d] * ph.w, ey.w);
+                    ey.x = sel(my, 0, disp_sub(upd3(c0.a, ey.x, c0.bz, dHx_dz.x, -c0.bx, dHz_dx.x), srce[idy_.a], ph[0]), ey.x);
+                    ey.y = sel(my, 1, disp_sub(upd3(c1.a, ey.y, c1.bz, dHx_dz.y, -c1.bx, dHz_dx.y), srce[idy_.b], ph[1]), ey.y);
+                    ey.z = sel(my, 2, disp_sub(upd3(c2.a, ey.z, c2.bz, dHx_dz.z, -c2.bx, dHz_dx.z), srce[idy_.c], ph[2]), ey.z);
+                    ey.w = sel(my, 3, disp_sub(upd3(c3.a, ey.w, c3.bz, dHx_dz.w, -c3.bx, dHz_dx.w), srce[idy_.d], ph[3]), ey.w);
                 } else {
                 ey.x = sel(my, 0, upd3(c0.a, ey.x, c0.bz, dHx_dz.x, -c0.bx, dHz_dx.x), ey.x);
                 ey.y = sel(my, 1, upd3(c1.a, ey.y, c1.bz, dHx_dz.y, -c1.bx, dHz_dx.y), ey.y);
@@ -417,12 +419,12 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
                 Coef4<R> c0, c1, c2, c3;
                 coef4(coef, idz_, c0, c1, c2, c3);
                 if (DISP) {
-                    V4<R> ph;
+                    float ph[4];
                     disp4(p, 2, idz_, off, mz, ez, ph);
-                    ez.x = sel(mz, 0, upd3(c0.a, ez.x, c0.bx, dHy_dx.x, -c0.by, dHx_dy.x) - srce[idz_.a] * ph.x, ez.x);
-                    ez.y = sel(mz, 1, upd3(c1.a, ez.y, c1.bx, dHy_dx.y, -c1.by, dHx_dy.y) - srce[idz_.b] * ph.y, ez.y);
-                    ez.z = sel(mz, 2, upd3(c2.a, ez.z, c2.bx, dHy_dx.z, -c2.by, dHx_dy.z) - srce[idz_.c] * ph.z, ez.z);
-                    ez.w = sel(mz, 3, upd3(c3.a, ez.w, c3.bx, dHy_dx.w, -c3.by, dHx_dy.w) - srce[idz_.d] * ph.w, ez.w);
+                    ez.x = sel(mz, 0, disp_sub(upd3(c0.a, ez.x, c0.bx, dHy_dx.x, -c0.by, dHx_dy.x), srce[idz_.a], ph[0]), ez.x);
+                    ez.y = sel(mz, 1, disp_sub(upd3(c1.a, ez.y, c1.bx, dHy_dx.y, -c1.by, dHx_dy.y), srce[idz_.b], ph[1]), ez.y);
+                    ez.z = sel(mz, 2, disp_sub(upd3(c2.a, ez.z, c2.bx, dHy_dx.z, -c2.by, dHx_dy.z), srce[idz_.c], ph[2]), ez.z);
+                    ez.w = sel(mz, 3, disp_sub(upd3(c3.a, ez.w, c3.bx, dHy_dx.w, -c3.by, dHx_dy.w), srce[idz_.d], ph[3]), ez.w);
                 } else {
                 ez.x = sel(mz, 0, upd3(c0.a, ez.x, c0.bx, dHy_dx.x, -c0.by, dHx_dy.x), ez.x);
                 ez.y = sel(mz, 1, upd3(c1.a, ez.y, c1.bx, dHy_dx.y, -c1.by, dHx_dy.y), ez.y);

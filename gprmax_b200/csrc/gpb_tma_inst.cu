@@ -24,7 +24,7 @@ static int tma_fail(std::string *err, const char *what, cudaError_t e)
     return 1;
 }
 
-template <typename R, int PV, typename IDT, int TY, int TZ, int S, int PW>
+template <typename R, int PV, typename IDT, int TY, int TZ, int S, int PW, int DISP = 0>
 static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
 {
     using L = StageLayout<R, IDT, TY, TZ>;
@@ -38,9 +38,25 @@ static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
                          (size_t)((p.nslabs * 4 * order * p.tmax * sizeof(R) + 127) / 128 * 128) + (size_t)S * L::bytes;
     const size_t pf_unit = (size_t)2 * order * (TY * TZ / 4) * 4 * sizeof(R);   // one plane of Phi per thread
     const size_t smem_cap = (sizeof(R) == 4 ? (size_t)(227 * 1024) / GPB_TMA_CTAS : (size_t)227 * 1024) - 1024;
-    p.pf_depth = p.nslabs == 0 ? 0 : (fixed + 2 * pf_unit <= smem_cap ? 2 : (fixed + pf_unit <= smem_cap ? 1 : 0));
+    // dispersive E half-step: coefficient triples + T prefetch slots; T is touched by every cell, Phi only inside the slabs, so T
+    // gets the first call on the shared memory that is left
+    size_t disp_fixed = 0, t_unit = 0;
+    p.t_depth = 0;
+    if (DISP) {
+        const int tw = DISP == 1 ? 2 : 1;
+        disp_fixed = (size_t)((p.nmat * p.maxpoles * 3 * tw * sizeof(R) + 127) / 128 * 128);
+        t_unit = (size_t)3 * p.maxpoles * tw * (TY * TZ / 4) * 4 * sizeof(R);
+        if (fixed + disp_fixed > smem_cap) {
+            if (err) *err = "dispersive coefficient table does not fit the shared memory of the TMA kernels";
+            return 1;
+        }
+        p.t_depth = fixed + disp_fixed + 2 * t_unit <= smem_cap ? 2 : (fixed + disp_fixed + t_unit <= smem_cap ? 1 : 0);
+        p.t_depth = std::min(p.t_depth, a.t_max);
+    }
+    const size_t fixed2 = fixed + disp_fixed + p.t_depth * t_unit;
+    p.pf_depth = p.nslabs == 0 ? 0 : (fixed2 + 2 * pf_unit <= smem_cap ? 2 : (fixed2 + pf_unit <= smem_cap ? 1 : 0));
     p.pf_depth = std::min(p.pf_depth, a.pf_max);
-    const size_t smem = fixed + p.pf_depth * pf_unit;
+    const size_t smem = fixed2 + p.pf_depth * pf_unit;
     const int tiles = tiles_k * tiles_j, nchunks = (p.p1 - p.p0 + p.xchunk - 1) / p.xchunk;
     // persistent: as many CTAs as fit on the GPU at once (2 per SM for fp32), pulling (tile, chunk) items from a.sched
     const int resident = (sizeof(R) == 4 ? GPB_TMA_CTAS : 1) * a.sm_count;
@@ -53,7 +69,7 @@ static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return tma_fail(err, "cudaFuncSetAttribute", e);
         kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, nsplit, a.sched);
     } else {
-        auto kern = k_update_tma<R, IDT, TY, TZ, S, 1, PW, PV>;
+        auto kern = k_update_tma<R, IDT, TY, TZ, S, 1, PW, PV, DISP>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return tma_fail(err, "cudaFuncSetAttribute", e);
         kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, nsplit, a.sched);
     }
@@ -64,6 +80,13 @@ static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
 template <typename R, int PV, typename IDT>
 static int tma_launch_idt(const TmaLaunch<R> &a, std::string *err)
 {
+    // dispersive electric half-step (a.disp: 1 complex T, 2 real T): instantiated for the default tile only
+    if (a.disp && a.phase == 1) {
+        if (a.ty == 14 && a.tz == 64 && a.stages == 3 && a.pw == 1)
+            return a.disp == 1 ? tma_launch_cfg<R, PV, IDT, 14, 64, 3, 1, 1>(a, err) : tma_launch_cfg<R, PV, IDT, 14, 64, 3, 1, 2>(a, err);
+        if (err) *err = "the dispersive TMA kernels exist for the 14 x 64 tile only";
+        return 1;
+    }
 #define GPB_TMA_CASE(TY_, TZ_, S_, PW_) \
     if (a.ty == TY_ && a.tz == TZ_ && a.stages == S_ && a.pw == PW_) return tma_launch_cfg<R, PV, IDT, TY_, TZ_, S_, PW_>(a, err)
     GPB_TMA_CASE(14, 64, 3, 1);

@@ -157,11 +157,12 @@ def test_config3_heterogeneous_soil_full_size():
 
 
 TMA_FIXTURES = ['pml_HORIPML_1', 'pml_HORIPML_2', 'pml_MRIPML_1', 'pml_MRIPML_2', 'sources_mixed', 'transmission_line',
-                'snapshots', 'hertzian_dipole_hs', 'dispersive_multipole']
+                'snapshots', 'hertzian_dipole_hs', 'dispersive_multipole', 'hertzian_dipole_dispersive', 'heterogeneous_soil_small']
 
 
 @pytest.mark.parametrize('name', TMA_FIXTURES)
-@pytest.mark.parametrize('mode', ['tma', 'tma_nopersist', 'tma_pw0', 'tma_tile8x128', 'tma_zsplit', 'tma_znocoop', 'tma_ids16', 'tma_ids32', 'v4_ids16', 'scalar'])
+@pytest.mark.parametrize('mode', ['tma', 'tma_nopersist', 'tma_pw0', 'tma_tile8x128', 'tma_zsplit', 'tma_znocoop', 'tma_ids16', 'tma_ids32', 'v4_ids16', 'scalar',
+                                  'tma_tpf1', 'tma_tpf0', 'tma_disp_v4', 'tma_disp_complex', 'v4_disp_complex'])
 def test_f64_every_kernel_path(name, mode, monkeypatch):
     """The small fixtures normally run on the register-vectorised kernels (the TMA kernels are only selected above
     2.5 M nodes); force each kernel family in turn so that all of them are held to the 1e-10 bar:
@@ -186,6 +187,17 @@ def test_f64_every_kernel_path(name, mode, monkeypatch):
         monkeypatch.setenv('GPB_TMA_TZ', '128')
     if mode == 'scalar':
         monkeypatch.setenv('GPB_SCALAR', '1')
+    # dispersive E half-step: T prefetch distance 1 / direct loads, register-vectorised E kernel next to the TMA H kernel,
+    # complex T even for Debye media
+    if mode in ('tma_tpf1', 'tma_tpf0', 'tma_disp_v4', 'tma_disp_complex', 'v4_disp_complex'):
+        if name not in ('dispersive_multipole', 'hertzian_dipole_dispersive', 'heterogeneous_soil_small'):
+            pytest.skip('dispersive models only')
+        if mode.startswith('tma_tpf'):
+            monkeypatch.setenv('GPB_TMA_TPF', mode[-1])
+        if mode == 'tma_disp_v4':
+            monkeypatch.setenv('GPB_DISP_V4', '1')
+        if mode.endswith('disp_complex'):
+            monkeypatch.setenv('GPB_DISP_COMPLEX', '1')
     G, golden = load_model(golden_path(name, 'f64'))
     out = _solve(G)
     worst, rep = compare_traces(out, golden, np.float64, tol=tolerance(G, np.float64))
@@ -234,6 +246,36 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
         out = run(env)
         for c, (a, b) in enumerate(zip(out, ref)):
             assert np.array_equal(a, b), (env, c, int((a != b).sum()))
+
+
+def test_dispersive_families_and_real_T_bit_identical(monkeypatch):
+    """Dispersive E half-step: the TMA-staged kernel (T prefetched per thread, distance 2 / 1 / direct), the register-vectorised
+    kernel and the scalar kernel, with real-valued T (Debye media) and with complex T, must all produce the same bits: the
+    per-cell arithmetic is one explicitly rounded routine (disp_cell_r / disp_cell_c), and with real coefficients Im(T) stays zero.
+    Model: the 50-material Peplinski soil fixture (1-pole Debye, rough surface, PML) in float32, fields compared everywhere."""
+    from gprmax_b200 import Solver
+    from gprmax_b200.model_io import load_model
+    G, _ = load_model(golden_path('heterogeneous_soil_small', 'f32'))
+    keys = ('GPB_FORCE_TMA', 'GPB_NO_TMA', 'GPB_SCALAR', 'GPB_DISP_V4', 'GPB_DISP_COMPLEX', 'GPB_TMA_TPF')
+
+    def run(env):
+        for k in keys:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Solver(G, device_id=0) as sv:
+            path = sv.kernel_path
+            sv.run()
+            return path, [sv.get_field(c) for c in range(6)] + [sv.receivers()]
+
+    pref, ref = run({'GPB_FORCE_TMA': '1'})
+    assert 'k_update_tma' in pref and 'DISP=real' in pref, pref
+    assert np.abs(ref[-1]).max() > 0
+    for env in ({'GPB_FORCE_TMA': '1', 'GPB_TMA_TPF': '1'}, {'GPB_FORCE_TMA': '1', 'GPB_TMA_TPF': '0'}, {'GPB_FORCE_TMA': '1', 'GPB_DISP_COMPLEX': '1'},
+                {'GPB_FORCE_TMA': '1', 'GPB_DISP_V4': '1'}, {'GPB_NO_TMA': '1'}, {'GPB_NO_TMA': '1', 'GPB_DISP_COMPLEX': '1'}):
+        path, out = run(env)
+        for c, (a, b) in enumerate(zip(out, ref)):
+            assert np.array_equal(a, b), (env, path, c, int((a != b).sum()))
 
 
 def test_device_memory_cache_reuse_and_release():
