@@ -17,7 +17,7 @@ RX_ROWS = ['Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz', 'Ix', 'Iy', 'Iz']
 
 # every symbol include/gprmax_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['gpb_device_count', 'gpb_device_info', 'gpb_create', 'gpb_destroy', 'gpb_run', 'gpb_iteration',
-           'gpb_elapsed_seconds', 'gpb_mem_used', 'gpb_kernel_launches', 'gpb_reset', 'gpb_profile', 'gpb_kernel_path', 'gpb_half_step', 'gpb_halo',
+           'gpb_elapsed_seconds', 'gpb_mem_used', 'gpb_kernel_launches', 'gpb_reset', 'gpb_set_points', 'gpb_profile', 'gpb_kernel_path', 'gpb_half_step', 'gpb_halo',
            'gpb_stream', 'gpb_synchronize', 'gpb_create_sharded', 'gpb_link_info', 'gpb_link', 'gpb_get_receivers', 'gpb_get_snapshot', 'gpb_get_tline',
            'gpb_get_field', 'gpb_set_field', 'gpb_release_cached', 'gpb_last_error', 'gpb_version']
 
@@ -103,6 +103,7 @@ def lib():
     L.gpb_run.argtypes = [H, C.c_int]
     L.gpb_half_step.argtypes = [H, C.c_int, C.c_int]
     L.gpb_reset.argtypes = [H]
+    L.gpb_set_points.argtypes = [H, C.POINTER(Model)]
     L.gpb_profile.argtypes = [H, C.c_int, C.POINTER(C.c_double)]
     L.gpb_kernel_path.argtypes = [H, C.c_char_p, C.c_size_t]
     L.gpb_iteration.argtypes = [H, C.POINTER(C.c_int)]

@@ -217,6 +217,7 @@ struct SolverBase {
     virtual int halo(int which, void **a, void **b, size_t *bytes) = 0;
     virtual int profile(int n, double *ms4) = 0;
     virtual std::string kernel_path() const = 0;
+    virtual int set_points(const gpb_model_t &m) = 0;
     virtual int link_info(gpb_link_t *out) = 0;
     virtual int link(const gpb_link_t *left, const gpb_link_t *right) = 0;
     int device = 0;
@@ -385,6 +386,7 @@ struct Solver : SolverBase {
     std::string kernel_path() const override;
     int link_info(gpb_link_t *out) override;
     int link(const gpb_link_t *left, const gpb_link_t *right) override;
+    int set_points(const gpb_model_t &m) override;
 };
 
 static int choose_pitch(int nzp1)
@@ -600,6 +602,34 @@ int Solver<R>::setup_pml(const gpb_model_t &m)
         }
     }
     return 0;
+}
+
+// New sources / receivers / transmission lines / snapshots on the resident grid (the traces of a B-scan whose geometry is fixed
+// only step these, model_build_run.py:294-330): fields, PML and T state are cleared, ID and coefficient arrays stay on the device.
+template <typename R>
+int Solver<R>::set_points(const gpb_model_t &m)
+{
+    CK(cudaSetDevice(device));
+    if (m.nx != nx || m.ny != ny || m.nz != nz || m.iterations != iterations || m.nmaterials != nmat)
+        return fail("gpb_set_points: the model has another grid, iteration count or material table than the resident one");
+    CK(cudaStreamSynchronize(stream));
+    if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }   // the captured launches hold the old point arrays
+    has_hsrc = has_esrc = false;
+    if (setup_points(m)) return 1;
+    snap_unlinked_ok = true;
+    for (auto &sn : snaps)
+        for (int i = 0; i < sn.nx; ++i) {
+            const int gi = sn.xs + i * sn.dx;
+            if (gi >= x_start && gi < x_start + nplanes && gi + sn.dx >= x_start + nplanes) snap_unlinked_ok = false;
+        }
+    if (linked && !snaps.empty())
+        for (auto &sn : snaps)
+            for (int i = 0; i < sn.nx; ++i) {
+                const int gi = sn.xs + i * sn.dx;
+                if (gi < x_start || gi >= x_start + nplanes || gi + sn.dx < x_start + nplanes) continue;
+                if (!right.present || gi + sn.dx >= right.x_start + right.nplanes) return fail("snapshot plane %d + %d lies beyond the right neighbour's planes", gi, sn.dx);
+            }
+    return reset();
 }
 
 template <typename R>
@@ -1682,6 +1712,16 @@ struct ShardedSolver : SolverBase {
         elapsed = 0;
         return 0;
     }
+    int set_points(const gpb_model_t &m) override
+    {
+        for (auto *s : sh)
+            if (s->set_points(m)) return 1;
+        nrx = m.nrx; ntl = m.ntlines;
+        snaps.assign(m.snapshots, m.snapshots + m.nsnapshots);
+        iteration = 0;
+        elapsed = 0;
+        return 0;
+    }
     // every receiver / transmission line / snapshot cell is owned by exactly one slab and zero in the others: the sum is exact
     int sum_into(std::vector<R> &acc, const std::vector<R> &part)
     {
@@ -1868,6 +1908,13 @@ int gpb_create_sharded(const gpb_model_t *model, const int *device_ids, int ndev
     return 0;
 }
 
+int gpb_set_points(gpb_handle h, const gpb_model_t *model)
+{
+    NEED(h);
+    if (!model) return fail("null argument");
+    if (model->abi_version != GPB_ABI_VERSION) return fail("ABI version mismatch: library %d, caller %d", GPB_ABI_VERSION, model->abi_version);
+    return h->impl->set_points(*model);
+}
 int gpb_link_info(gpb_handle h, gpb_link_t *out) { NEED(h); if (!out) return fail("null argument"); return h->impl->link_info(out); }
 int gpb_link(gpb_handle h, const gpb_link_t *left, const gpb_link_t *right) { NEED(h); return h->impl->link(left, right); }
 

@@ -1,0 +1,71 @@
+"""Use the B200 core from the gprMax command line without touching the gprMax tree.
+
+    python -m gprmax_b200 model.in -gpu            one GPU
+    python -m gprmax_b200 model.in -gpu 0 1 2 3    ONE model sharded as x-slabs over four GPUs
+    python -m gprmax_b200 model.in -n 54 -gpu 0    B-scan, traces one after the other
+    (every other gprMax option is passed through unchanged)
+
+`install()` replaces the two call sites SURVEY.md 8(b) names -- `gprMax.gprMax.detect_check_gpus` (gprMax.py:136) and
+`gprMax.model_build_run.solve_gpu` (model_build_run.py:373) -- by this package's drop-ins, exactly the two assignments
+INTEGRATION.md gives a maintainer.  It also lifts the two input restrictions the reference only has because its PyCUDA
+solver lacks the features: `#transmission_line` under `-gpu` (input_cmds_multiuse.py:317-319) and the Ix/Iy/Iz receiver
+outputs (:417-418); both are CPU-only in the reference and are supported by this core.  The input commands are parsed by
+the reference's own `process_multicmds`; it merely does not see `G.gpu` while it parses.
+"""
+import os
+import sys
+
+
+def _import_reference():
+    try:
+        import gprMax  # noqa: F401
+    except ImportError:
+        # not installed: the vendored copy of this repository (baseline/_ref, see baseline/install_ref.sh)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        if root not in sys.path:
+            sys.path.insert(0, root)
+        import baseline
+        baseline.use_reference()
+        import gprMax  # noqa: F401
+    import gprMax.gprMax as top
+    import gprMax.model_build_run as mbr
+    return top, mbr
+
+
+_installed = False
+
+
+def install():
+    """Point the running gprMax at this core (idempotent).  Returns (gprMax.gprMax, gprMax.model_build_run)."""
+    global _installed
+    top, mbr = _import_reference()
+    if _installed:
+        return top, mbr
+    from . import detect_check_gpus, solve_gpu
+    # errors leave this package as the reference's own GeneralError (exceptions.py:29-36), whatever was imported first
+    from gprMax.exceptions import GeneralError as RefError
+    import gprmax_b200
+    from . import exceptions, gpu, solver
+    for mod in (gprmax_b200, exceptions, gpu, solver):
+        mod.GeneralError = RefError
+    top.detect_check_gpus = detect_check_gpus
+    mbr.solve_gpu = solve_gpu
+
+    parse = mbr.process_multicmds
+
+    def process_multicmds(multicmds, G):
+        gpu, G.gpu = G.gpu, None    # transmission lines and Ix/Iy/Iz outputs are fine on this core
+        try:
+            return parse(multicmds, G)
+        finally:
+            G.gpu = gpu
+    mbr.process_multicmds = process_multicmds
+    _installed = True
+    return top, mbr
+
+
+def main(argv=None):
+    top, _ = install()
+    if argv is not None:
+        sys.argv = [sys.argv[0]] + list(argv)
+    return top.main()

@@ -43,7 +43,7 @@ def _active_range(src, G):
 class PackedModel(object):
     """The gpb_model_t for a grid plus the NumPy arrays that back its pointers."""
 
-    def __init__(self, G, x_start=0, nx_planes=None, ID=None):
+    def __init__(self, G, x_start=0, nx_planes=None, ID=None, with_id=True):
         self.keep = []
         real = np.dtype(G.updatecoeffsE.dtype)
         if real not in (np.dtype(np.float32), np.dtype(np.float64)):
@@ -61,7 +61,10 @@ class PackedModel(object):
         if ID is None:
             ID = getattr(G, 'ID', None)
         m.id_comp_stride = 0
-        if ID is None:
+        if not with_id:
+            m.ID = None
+            m.uniform_id = 0
+        elif ID is None:
             # homogeneous synthetic domain (synthetic.homogeneous_model(build_id=False)): no ID array at all
             m.ID = None
             m.uniform_id = int(G.fill_id)
@@ -239,6 +242,15 @@ class Solver(object):
     def reset(self):
         self._ck(self.L.gpb_reset(self.h))
 
+    def set_points(self, G):
+        """Next trace on the resident geometry: new sources / receivers / transmission lines / snapshots of `G`, field state
+        cleared, ID and coefficient arrays stay on the device (gpb_set_points)."""
+        packed = PackedModel(G, x_start=self.x_start if self.devices is None else 0,
+                             nx_planes=self.nx_planes if self.devices is None else None, with_id=False)
+        self._ck(self.L.gpb_set_points(self.h, C.byref(packed.model)))
+        self.G = G
+        self.nrx = len(G.rxs)
+
     def synchronize(self):
         self._ck(self.L.gpb_synchronize(self.h))
 
@@ -347,7 +359,13 @@ def solve_gpu(currentmodelrun, modelend, G):
         tsolve (float): Time taken to execute solving (time loop incl. the final receiver copy)
         memsolve (int): device memory used by the solver in bytes
     """
-    solver = Solver(G)   # G.gpu decides: one device, or x-slabs over G.gpu.shard_ordinals (gprmax_b200/gpu.py)
+    # The same FDTDGrid object again = the reference's --geometry-fixed B-scan (model_build_run.py:109, 288-330: `G` is kept
+    # between model runs and only sources / receivers are stepped): the solver of the previous trace is still resident on the
+    # device and only takes the new points.  A new grid object gets a new solver.
+    solver = _resident_solver(G)
+    keep = solver is not None or bool(getattr(G, 'srcsteps', None) and any(G.srcsteps)) or bool(getattr(G, 'rxsteps', None) and any(G.rxsteps))
+    if solver is None:
+        solver = Solver(G)   # G.gpu decides: one device, or x-slabs over G.gpu.shard_ordinals (gprmax_b200/gpu.py)
     try:
         progress = bool(getattr(G, 'progressbars', False))
         total = int(G.iterations)
@@ -370,6 +388,44 @@ def solve_gpu(currentmodelrun, modelend, G):
         tcopy = time.perf_counter() - t0
         tsolve = solver.elapsed + tcopy
         memsolve = solver.mem_used
+    except Exception:
+        keep = False
+        raise
     finally:
-        solver.close()
+        if keep and currentmodelrun < modelend:
+            _keep_resident(G, solver)
+        else:
+            _RESIDENT.clear()
+            solver.close()
     return tsolve, memsolve
+
+
+# (id(G) -> (weak reference to G, Solver)): at most one entry
+_RESIDENT = {}
+
+
+def _resident_solver(G):
+    ent = _RESIDENT.get(id(G))
+    if ent is None:
+        for _, sv in _RESIDENT.values():   # another grid: the resident one is stale
+            sv.close()
+        _RESIDENT.clear()
+        return None
+    ref, sv = ent
+    if ref() is not G or sv.h is None:
+        _RESIDENT.clear()
+        sv.close()
+        return None
+    sv.set_points(G)
+    return sv
+
+
+def _keep_resident(G, solver):
+    import weakref
+    try:
+        ref = weakref.ref(G)
+    except TypeError:       # an object that cannot be weakly referenced: no residency
+        solver.close()
+        return
+    _RESIDENT.clear()
+    _RESIDENT[id(G)] = (ref, solver)

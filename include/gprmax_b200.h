@@ -152,6 +152,11 @@ int gpb_elapsed_seconds(gpb_handle h, double *seconds);
 int gpb_mem_used(gpb_handle h, uint64_t *bytes);        /* device bytes owned by this handle */
 int gpb_kernel_launches(gpb_handle h, uint64_t *count); /* kernels launched by gpb_run/gpb_half_step so far */
 int gpb_reset(gpb_handle h);                            /* zero fields / PML / T / rx, iteration = 0 */
+/* Next trace of a B-scan on a FIXED geometry (the reference's --geometry-fixed: the same FDTDGrid is solved again with
+ * stepped sources / receivers, model_build_run.py:294-330): take the sources, transmission lines, receivers and snapshots
+ * of `model` (grid, iteration count and material table must be the resident ones; ID / coefficient / PML arguments are
+ * ignored), clear all field state, keep the ID and coefficient arrays on the device. */
+int gpb_set_points(gpb_handle h, const gpb_model_t *model);
 /* Measurement aid: advance n_iters iterations with plain launches and CUDA events between the
  * kernels; ms4 = device milliseconds {step prologue, H update, E update, source kernels} summed. */
 int gpb_profile(gpb_handle h, int n_iters, double *ms4);
