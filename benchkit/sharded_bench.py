@@ -71,6 +71,9 @@ def bitexact_gate(rank, world, local, transport, dims=(512, 512, 256), iteration
     torch.cuda.synchronize()
     dist.barrier()
     shard_path = shard.solver.kernel_path
+    if transport == 'p2p':
+        shard.solver.link()   # unmap the neighbours before anybody frees
+        dist.barrier()
     shard.close()
     return bool(ok.item()), {'dims': list(dims), 'iterations': iterations, 'ranks': world, 'model': 'random mix of 5 dielectrics on every edge, z dipole 3 planes from the middle cut, '
                              'receiver on the cut plane', 'compared': 'all six final field arrays (every rank its slab) and the receiver traces, np.array_equal',
@@ -153,6 +156,9 @@ def bench_sharded(args):
     kpath = shard.solver.kernel_path
     torch.cuda.synchronize()
     dist.barrier()
+    if transport == 'p2p' and world > 1:
+        shard.solver.link()
+        dist.barrier()
     shard.close()
     shard = None
 

@@ -19,7 +19,7 @@ RX_ROWS = ['Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz', 'Ix', 'Iy', 'Iz']
 SYMBOLS = ['gpb_device_count', 'gpb_device_info', 'gpb_create', 'gpb_destroy', 'gpb_run', 'gpb_iteration',
            'gpb_elapsed_seconds', 'gpb_mem_used', 'gpb_kernel_launches', 'gpb_reset', 'gpb_set_points', 'gpb_profile', 'gpb_kernel_path', 'gpb_half_step', 'gpb_halo',
            'gpb_stream', 'gpb_synchronize', 'gpb_create_sharded', 'gpb_link_info', 'gpb_link', 'gpb_get_receivers', 'gpb_get_snapshot', 'gpb_get_tline',
-           'gpb_get_field', 'gpb_set_field', 'gpb_release_cached', 'gpb_last_error', 'gpb_version']
+           'gpb_get_field', 'gpb_set_field', 'gpb_release_cached', 'gpb_ids_scan', 'gpb_ids_apply', 'gpb_last_error', 'gpb_version']
 
 
 class DeviceInfo(C.Structure):
@@ -55,11 +55,16 @@ class Snapshot(C.Structure):
                 ('nx', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32), ('time', C.c_int32)]
 
 
+class IdCombo(C.Structure):
+    _fields_ = [('id', C.c_uint32 * 4), ('comp', C.c_int32), ('i', C.c_int32), ('j', C.c_int32), ('k', C.c_int32)]
+
+
 class Link(C.Structure):
     _fields_ = [('process_id', C.c_uint64), ('device_id', C.c_int32), ('dtype', C.c_int32),
                 ('x_start', C.c_int32), ('nx_planes', C.c_int32), ('ny', C.c_int32), ('nz', C.c_int32),
                 ('plane_elems', C.c_uint64), ('array_elems', C.c_uint64), ('fields_ptr', C.c_uint64), ('flags_ptr', C.c_uint64),
-                ('fields_ipc', C.c_ubyte * 64), ('flags_ipc', C.c_ubyte * 64)]
+                ('fields_ipc', C.c_ubyte * 64), ('flags_ipc', C.c_ubyte * 64),
+                ('fields_ipc_offset', C.c_uint64), ('flags_ipc_offset', C.c_uint64)]
 
 
 class Model(C.Structure):
@@ -99,6 +104,9 @@ def lib():
     L.gpb_create_sharded.argtypes = [C.POINTER(Model), C.POINTER(C.c_int), C.c_int, C.POINTER(H)]
     L.gpb_link_info.argtypes = [H, C.POINTER(Link)]
     L.gpb_link.argtypes = [H, C.POINTER(Link), C.POINTER(Link)]
+    P = C.c_void_p
+    L.gpb_ids_scan.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(IdCombo), C.c_int, C.POINTER(C.c_int)]
+    L.gpb_ids_apply.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(IdCombo), P, C.c_int]
     L.gpb_destroy.argtypes = [H]
     L.gpb_run.argtypes = [H, C.c_int]
     L.gpb_half_step.argtypes = [H, C.c_int, C.c_int]

@@ -204,6 +204,79 @@ void parallel_copy(char *dst, const char *src, size_t bytes, int nthreads)
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------
+// CUDA IPC mappings of neighbouring shards that live in other processes (gpb_link).  Two facts of cudaIpc* shape this:
+//   * a handle stands for a whole DRIVER allocation; the runtime packs small cudaMalloc requests into shared blocks, so a
+//     handle is taken for the base of the block (cuMemGetAddressRange) and the array is addressed base + offset;
+//   * a process may open a given allocation only once: mappings are reference-counted by handle.
+namespace {
+typedef CUresult (*AddrRangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+AddrRangeFn addr_range_fn()
+{
+    static AddrRangeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (AddrRangeFn)p;
+    }
+    return fn;
+}
+// handle of the allocation that contains `ptr` and the offset of `ptr` inside it
+int ipc_export(const void *ptr, unsigned char handle[64], uint64_t *offset)
+{
+    CUdeviceptr base = (CUdeviceptr)(uintptr_t)ptr;
+    size_t size = 0;
+    AddrRangeFn fn = addr_range_fn();
+    if (fn && fn(&base, &size, (CUdeviceptr)(uintptr_t)ptr) != CUDA_SUCCESS) base = (CUdeviceptr)(uintptr_t)ptr;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, (void *)(uintptr_t)base) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    memcpy(handle, &h, 64);
+    *offset = (uint64_t)((uintptr_t)ptr - (uintptr_t)base);
+    return 0;
+}
+struct IpcMappings {
+    std::mutex mu;
+    std::map<std::string, std::pair<void *, int>> open;   // handle bytes -> (mapped base, references)
+    cudaError_t acquire(const unsigned char handle[64], void **base)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        const std::string key((const char *)handle, 64);
+        auto it = open.find(key);
+        if (it != open.end()) {
+            ++it->second.second;
+            *base = it->second.first;
+            return cudaSuccess;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) open[key] = {*base, 1};
+        return e;
+    }
+    void release(void *base)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto it = open.begin(); it != open.end(); ++it)
+            if (it->second.first == base) {
+                if (--it->second.second == 0) {
+                    cudaError_t e = cudaIpcCloseMemHandle(base);
+                    if (e != cudaSuccess) {
+                        if (getenv("GPB_DEBUG")) fprintf(stderr, "[gpb] cudaIpcCloseMemHandle: %s\n", cudaGetErrorString(e));
+                        cudaGetLastError();
+                    }
+                    open.erase(it);
+                }
+                return;
+            }
+    }
+};
+IpcMappings g_ipc;
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
 struct SolverBase {
     virtual ~SolverBase() {}
     virtual int run(int n) = 0;
@@ -328,6 +401,8 @@ struct Solver : SolverBase {
         if (d_flags) cudaFree(d_flags);
         for (void *p : allocs) g_pool.free(p);
         if (stream) cudaStreamDestroy(stream);
+        cudaError_t e = cudaGetLastError();   // nothing of the tear-down may linger as the "last error" of the next call
+        if (e != cudaSuccess && getenv("GPB_DEBUG")) fprintf(stderr, "[gpb] solver tear-down left: %s\n", cudaGetErrorString(e));
     }
 
     template <typename T_>
@@ -1226,13 +1301,10 @@ int Solver<R>::link_info(gpb_link_t *out)
     out->fields_ptr = (uint64_t)(uintptr_t)F[0];
     out->flags_ptr = (uint64_t)(uintptr_t)d_flags;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "gpb_link_t carries 64-byte IPC handles");
-    cudaIpcMemHandle_t hF, hG;
     // (a process that only ever links shards of its own does not need the handles: failure to export is not an error here)
-    if (cudaIpcGetMemHandle(&hF, F[0]) == cudaSuccess && cudaIpcGetMemHandle(&hG, d_flags) == cudaSuccess) {
-        memcpy(out->fields_ipc, &hF, 64);
-        memcpy(out->flags_ipc, &hG, 64);
-    } else {
-        cudaGetLastError();
+    if (ipc_export(F[0], out->fields_ipc, &out->fields_ipc_offset) || ipc_export(d_flags, out->flags_ipc, &out->flags_ipc_offset)) {
+        memset(out->fields_ipc, 0, 64);
+        memset(out->flags_ipc, 0, 64);
     }
     return 0;
 }
@@ -1245,8 +1317,8 @@ int Solver<R>::unlink()
     if (stream) cudaStreamSynchronize(stream);
     if (stream2) cudaStreamSynchronize(stream2);
     for (Peer *p : {&left, &right}) {
-        if (p->ipc_F) cudaIpcCloseMemHandle(p->ipc_F);
-        if (p->ipc_flags) cudaIpcCloseMemHandle(p->ipc_flags);
+        if (p->ipc_F) g_ipc.release(p->ipc_F);
+        if (p->ipc_flags) g_ipc.release(p->ipc_flags);
         *p = Peer();
     }
     if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
@@ -1287,13 +1359,12 @@ int Solver<R>::link(const gpb_link_t *l, const gpb_link_t *r)
             p.F = (R *)(uintptr_t)q->fields_ptr;
             p.flags = (unsigned *)(uintptr_t)q->flags_ptr;
         } else {
-            cudaIpcMemHandle_t hF, hG;
-            memcpy(&hF, q->fields_ipc, 64);
-            memcpy(&hG, q->flags_ipc, 64);
-            CK(cudaIpcOpenMemHandle(&p.ipc_F, hF, cudaIpcMemLazyEnablePeerAccess));
-            CK(cudaIpcOpenMemHandle(&p.ipc_flags, hG, cudaIpcMemLazyEnablePeerAccess));
-            p.F = (R *)p.ipc_F;
-            p.flags = (unsigned *)p.ipc_flags;
+            static const unsigned char none[64] = {0};
+            if (!memcmp(q->fields_ipc, none, 64)) return fail("the neighbour could not export its arrays through CUDA IPC");
+            CK(g_ipc.acquire(q->fields_ipc, &p.ipc_F));
+            CK(g_ipc.acquire(q->flags_ipc, &p.ipc_flags));
+            p.F = (R *)((char *)p.ipc_F + q->fields_ipc_offset);
+            p.flags = (unsigned *)((char *)p.ipc_flags + q->flags_ipc_offset);
         }
         p.narr = (long long)q->array_elems;
         p.x_start = q->x_start;
@@ -1844,6 +1915,10 @@ int gpb_create(const gpb_model_t *model, int device_id, gpb_handle *out)
     if (model->abi_version != GPB_ABI_VERSION) return fail("ABI version mismatch: library %d, caller %d", GPB_ABI_VERSION, model->abi_version);
     int n = 0;
     if (gpb_device_count(&n)) return 1;
+    {   // a failed call of the application (or of another library in this thread) must not surface in this library's checks
+        cudaError_t stale = cudaGetLastError();
+        if (stale != cudaSuccess && getenv("GPB_DEBUG")) fprintf(stderr, "[gpb] stale CUDA error at gpb_create: %s\n", cudaGetErrorString(stale));
+    }
     if (device_id < 0 || device_id >= n) return fail("GPU with device ID %d does not exist (%d device(s) present)", device_id, n);
     SolverBase *s = nullptr;
     int rc;

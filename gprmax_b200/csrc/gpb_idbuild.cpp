@@ -1,0 +1,212 @@
+// gpb_idbuild.cpp -- host-side build of the per-edge material ID array.
+//
+// Replaces the bulk of the reference's build_electric_components / build_magnetic_components
+// (gprMax/yee_cell_build_ext.pyx:110-257): a single-threaded triple loop over the 6 N edges of the grid that, for every
+// edge not marked rigid, looks at the 4 (electric) or 2 (magnetic) cells of `solid` around it and either copies their common
+// material or asks for a dielectric-smoothed average (create_electric_average / create_magnetic_average, :31-107).
+//
+// The sequential part of that algorithm is tiny: which averaged material a combination of cell materials maps to depends on the
+// ORDER in which distinct combinations are first met (new materials are appended in that order), not on how many edges show
+// them.  So the work is split:
+//   pass 1 (here, all host cores, planes split over threads): write every edge whose surrounding cells agree and collect the
+//           distinct disagreeing combinations together with the first edge -- in the reference's scan order: component, i, j,
+//           k -- that shows each of them;
+//   host   (Python, gprmax_b200/yee_build.py): for the distinct combinations in that order call the reference's OWN
+//           create_*_average on the recorded edge (a few hundred calls), which yields exactly the material numbering of the
+//           reference;
+//   pass 2 (here, all host cores): write the resolved material on every disagreeing edge.
+// The resulting ID array is bit-identical with the reference's (tests/test_yee_build.py).
+#include "../../include/gprmax_b200.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <thread>
+#include <unistd.h>
+#include <vector>
+
+namespace {
+
+struct Grid {
+    const uint32_t *solid;   // [nx][ny][nz]
+    const int8_t *rigidE;    // [12][nx][ny][nz]
+    const int8_t *rigidH;    // [6][nx][ny][nz]
+    uint32_t *ID;            // [6][nx+1][ny+1][nz+1]
+    int nx, ny, nz;
+    size_t cell(int i, int j, int k) const { return ((size_t)i * ny + j) * nz + k; }
+    size_t node(int c, int i, int j, int k) const { return (((size_t)c * (nx + 1) + i) * (ny + 1) + j) * (nz + 1) + k; }
+    bool rE(int q, int i, int j, int k) const { return rigidE[(size_t)q * nx * ny * nz + cell(i, j, k)] != 0; }
+    bool rH(int q, int i, int j, int k) const { return rigidH[(size_t)q * nx * ny * nz + cell(i, j, k)] != 0; }
+    // yee_cell_setget_rigid_ext.pyx:24-66, 108-138 (loop ranges keep every index inside the arrays)
+    bool rigid(int comp, int i, int j, int k) const
+    {
+        switch (comp) {
+        case 0: return rE(0, i, j, k) || rE(1, i, j - 1, k) || rE(3, i, j, k - 1) || rE(2, i, j - 1, k - 1);
+        case 1: return rE(4, i, j, k) || rE(7, i - 1, j, k) || rE(5, i, j, k - 1) || rE(6, i - 1, j, k - 1);
+        case 2: return rE(8, i, j, k) || rE(9, i - 1, j, k) || rE(11, i, j - 1, k) || rE(10, i - 1, j - 1, k);
+        case 3: return rH(0, i, j, k) || rH(1, i - 1, j, k);
+        case 4: return rH(2, i, j, k) || rH(3, i, j - 1, k);
+        default: return rH(4, i, j, k) || rH(5, i, j, k - 1);
+        }
+    }
+    // the cells around an edge in the order the reference names them numID1..4 (yee_cell_build_ext.pyx:131-134, 153-156,
+    // 175-178; 210-211, 230-231, 250-251); magnetic components fill two entries
+    void around(int comp, int i, int j, int k, uint32_t id[4]) const
+    {
+        id[2] = id[3] = 0;
+        switch (comp) {
+        case 0: id[0] = solid[cell(i, j, k)]; id[1] = solid[cell(i, j - 1, k)]; id[2] = solid[cell(i, j - 1, k - 1)]; id[3] = solid[cell(i, j, k - 1)]; break;
+        case 1: id[0] = solid[cell(i, j, k)]; id[1] = solid[cell(i - 1, j, k)]; id[2] = solid[cell(i - 1, j, k - 1)]; id[3] = solid[cell(i, j, k - 1)]; break;
+        case 2: id[0] = solid[cell(i, j, k)]; id[1] = solid[cell(i - 1, j, k)]; id[2] = solid[cell(i - 1, j - 1, k)]; id[3] = solid[cell(i, j - 1, k)]; break;
+        case 3: id[0] = solid[cell(i, j, k)]; id[1] = solid[cell(i - 1, j, k)]; break;
+        case 4: id[0] = solid[cell(i, j, k)]; id[1] = solid[cell(i, j - 1, k)]; break;
+        default: id[0] = solid[cell(i, j, k)]; id[1] = solid[cell(i, j, k - 1)]; break;
+        }
+    }
+};
+
+// loop ranges of the six components (yee_cell_build_ext.pyx:123-125, 145-147, 167-169, 202-204, 222-224, 242-244)
+inline void ranges(const Grid &g, int comp, int lo[3], int hi[3])
+{
+    const int l[6][3] = {{0, 1, 1}, {1, 0, 1}, {1, 1, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int a = 0; a < 3; ++a) lo[a] = l[comp][a];
+    hi[0] = g.nx; hi[1] = g.ny; hi[2] = g.nz;
+}
+
+struct Key {
+    int comp;
+    uint32_t id[4];
+    bool operator<(const Key &o) const
+    {
+        if (comp != o.comp) return comp < o.comp;
+        return std::lexicographical_compare(id, id + 4, o.id, o.id + 4);
+    }
+};
+struct Pos {
+    int i, j, k;
+    bool before(const Pos &o) const { return i != o.i ? i < o.i : (j != o.j ? j < o.j : k < o.k); }
+};
+
+int host_threads()
+{
+    const long n = sysconf(_SC_NPROCESSORS_CONF);
+    return (int)std::max(1l, std::min(64l, n));
+}
+
+template <typename F>
+void parallel_planes(int x0, int x1, F f)
+{
+    const int nt = std::max(1, std::min(host_threads(), x1 - x0));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+        const int a = x0 + (int)((long long)(x1 - x0) * t / nt), b = x0 + (int)((long long)(x1 - x0) * (t + 1) / nt);
+        th.emplace_back([=] {
+            cpu_set_t all;   // see ScopedFullAffinity in gpb_core.cu: the caller is usually pinned to one core by OpenMP
+            CPU_ZERO(&all);
+            for (int c = 0; c < CPU_SETSIZE; ++c) CPU_SET(c, &all);
+            pthread_setaffinity_np(pthread_self(), sizeof all, &all);
+            f(t, a, b);
+        });
+    }
+    for (auto &t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpb_ids_scan(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
+                 gpb_idcombo_t *combos, int max_combos, int *ncombos)
+{
+    if (!solid || !rigidE || !rigidH || !ID || !combos || !ncombos || nx < 1 || ny < 1 || nz < 1 || x0 < 0 || x1 > nx + 1 || x1 < x0) return 1;
+    const Grid g{solid, rigidE, rigidH, ID, nx, ny, nz};
+    const int nt = std::max(1, std::min(host_threads(), std::max(1, x1 - x0)));
+    std::vector<std::map<Key, Pos>> found(nt);
+    parallel_planes(x0, x1, [&](int t, int a, int b) {
+        std::map<Key, Pos> &mine = found[t];
+        Key last{-1, {0, 0, 0, 0}};   // runs of the same combination are common: skip the map for them
+        for (int comp = 0; comp < 6; ++comp) {
+            int lo[3], hi[3];
+            ranges(g, comp, lo, hi);
+            const int nid = comp < 3 ? 4 : 2;
+            for (int i = std::max(a, lo[0]); i < std::min(b, hi[0]); ++i)
+                for (int j = lo[1]; j < hi[1]; ++j)
+                    for (int k = lo[2]; k < hi[2]; ++k) {
+                        if (g.rigid(comp, i, j, k)) continue;
+                        uint32_t id[4];
+                        g.around(comp, i, j, k, id);
+                        bool same = id[0] == id[1];
+                        if (nid == 4) same = same && id[0] == id[2] && id[0] == id[3];
+                        if (same) {
+                            ID[g.node(comp, i, j, k)] = id[0];
+                            continue;
+                        }
+                        if (last.comp == comp && !memcmp(last.id, id, sizeof id)) continue;
+                        last.comp = comp;
+                        memcpy(last.id, id, sizeof id);
+                        mine.insert({last, Pos{i, j, k}});   // keeps the first (scan order inside this thread's planes)
+                    }
+        }
+    });
+    // threads own increasing plane ranges, so the first thread that met a combination met it first in scan order
+    std::map<Key, Pos> all;
+    for (int t = 0; t < nt; ++t)
+        for (auto &kv : found[t]) all.insert(kv);
+    std::vector<std::pair<Key, Pos>> order(all.begin(), all.end());
+    std::sort(order.begin(), order.end(), [](const std::pair<Key, Pos> &x, const std::pair<Key, Pos> &y) {
+        if (x.first.comp != y.first.comp) return x.first.comp < y.first.comp;
+        return x.second.before(y.second);
+    });
+    *ncombos = (int)order.size();
+    if ((int)order.size() > max_combos) return 2;
+    for (size_t q = 0; q < order.size(); ++q) {
+        gpb_idcombo_t &c = combos[q];
+        c.comp = order[q].first.comp;
+        memcpy(c.id, order[q].first.id, sizeof c.id);
+        c.i = order[q].second.i; c.j = order[q].second.j; c.k = order[q].second.k;
+    }
+    return 0;
+}
+
+int gpb_ids_apply(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
+                  const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos)
+{
+    if (!solid || !rigidE || !rigidH || !ID || (ncombos && (!combos || !numid)) || x0 < 0 || x1 > nx + 1 || x1 < x0) return 1;
+    const Grid g{solid, rigidE, rigidH, ID, nx, ny, nz};
+    std::map<Key, uint32_t> table;
+    for (int q = 0; q < ncombos; ++q) {
+        Key k{combos[q].comp, {combos[q].id[0], combos[q].id[1], combos[q].id[2], combos[q].id[3]}};
+        table[k] = numid[q];
+    }
+    int missing = 0;
+    parallel_planes(x0, x1, [&](int, int a, int b) {
+        Key last{-1, {0, 0, 0, 0}};
+        uint32_t last_num = 0;
+        for (int comp = 0; comp < 6; ++comp) {
+            int lo[3], hi[3];
+            ranges(g, comp, lo, hi);
+            const int nid = comp < 3 ? 4 : 2;
+            for (int i = std::max(a, lo[0]); i < std::min(b, hi[0]); ++i)
+                for (int j = lo[1]; j < hi[1]; ++j)
+                    for (int k = lo[2]; k < hi[2]; ++k) {
+                        if (g.rigid(comp, i, j, k)) continue;
+                        uint32_t id[4];
+                        g.around(comp, i, j, k, id);
+                        bool same = id[0] == id[1];
+                        if (nid == 4) same = same && id[0] == id[2] && id[0] == id[3];
+                        if (same) continue;
+                        if (!(last.comp == comp && !memcmp(last.id, id, sizeof id))) {
+                            last.comp = comp;
+                            memcpy(last.id, id, sizeof id);
+                            auto it = table.find(last);
+                            if (it == table.end()) { __atomic_store_n(&missing, 1, __ATOMIC_RELAXED); last.comp = -1; continue; }
+                            last_num = it->second;
+                        }
+                        ID[g.node(comp, i, j, k)] = last_num;
+                    }
+        }
+    });
+    return missing ? 3 : 0;
+}
+
+}  // extern "C"

@@ -10,7 +10,9 @@
 INTEGRATION.md gives a maintainer.  It also lifts the two input restrictions the reference only has because its PyCUDA
 solver lacks the features: `#transmission_line` under `-gpu` (input_cmds_multiuse.py:317-319) and the Ix/Iy/Iz receiver
 outputs (:417-418); both are CPU-only in the reference and are supported by this core.  The input commands are parsed by
-the reference's own `process_multicmds`; it merely does not see `G.gpu` while it parses.
+the reference's own `process_multicmds`; it merely does not see `G.gpu` while it parses.  Finally the per-edge ID build
+(`build_electric_components` / `build_magnetic_components`, model_build_run.py:216-218) runs on all host cores with an identical
+result (gprmax_b200/yee_build.py; GPRMAX_B200_REF_BUILD=1 keeps the reference's single-threaded loop).
 """
 import os
 import sys
@@ -60,6 +62,20 @@ def install():
         finally:
             G.gpu = gpu
     mbr.process_multicmds = process_multicmds
+
+    # per-edge material IDs on all host cores (yee_build.py; identical G.ID and G.materials, tests/test_yee_build.py).  The
+    # reference calls the electric and the magnetic build back to back (model_build_run.py:216-218): the first call does both.
+    if os.environ.get('GPRMAX_B200_REF_BUILD') != '1':
+        from . import yee_build
+        from gprMax.yee_cell_build_ext import create_electric_average, create_magnetic_average
+
+        def build_electric_components(solid, rigidE, ID, G):
+            yee_build.build_components(G, create_electric_average, create_magnetic_average)
+
+        def build_magnetic_components(solid, rigidH, ID, G):
+            pass
+        mbr.build_electric_components = build_electric_components
+        mbr.build_magnetic_components = build_magnetic_components
     _installed = True
     return top, mbr
 

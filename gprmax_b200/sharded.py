@@ -237,6 +237,9 @@ def solve_gpu_sharded(G, iterations=None, overlap=True, ID_local=None, timing=No
     seconds_host = float(seconds.item())
     torch.cuda.synchronize()
     dist.barrier()                                 # nobody unlinks while a neighbour may still push into its planes
+    if transport == 'p2p':
+        shard.solver.link()                        # drop my mappings of the neighbours' arrays ...
+        dist.barrier()                             # ... before anybody frees them
     if timing is not None:
         timing['launches'] = shard.solver.kernel_launches
         timing['mem'] = shard.solver.mem_used

@@ -204,8 +204,9 @@ typedef struct gpb_link_t {
     int32_t x_start, nx_planes, ny, nz;
     uint64_t plane_elems, array_elems; /* elements per (padded) plane / per component array incl. the two ghost planes */
     uint64_t fields_ptr, flags_ptr;    /* device addresses, valid inside the owner process */
-    unsigned char fields_ipc[64];      /* cudaIpcMemHandle_t of the field allocation */
-    unsigned char flags_ipc[64];       /* cudaIpcMemHandle_t of the flag words */
+    unsigned char fields_ipc[64];      /* cudaIpcMemHandle_t of the driver allocation that holds the field arrays ... */
+    unsigned char flags_ipc[64];       /* ... and of the one that holds the flag words (small allocations share a block) */
+    uint64_t fields_ipc_offset, flags_ipc_offset;   /* byte offsets of the arrays inside those allocations */
 } gpb_link_t;
 int gpb_link_info(gpb_handle h, gpb_link_t *out);
 int gpb_link(gpb_handle h, const gpb_link_t *left, const gpb_link_t *right);
@@ -227,6 +228,24 @@ int gpb_set_field(gpb_handle h, int component, const void *in, size_t in_bytes);
  * B-scan creates one solver per trace; the reference pays a fresh CUDA context and allocations per model run,
  * model_build_run.py:492-497, 713-714).  gpb_release_cached returns it to the driver; GPB_NO_POOL=1 disables the cache. */
 int gpb_release_cached(void);
+
+/* ---- host-side build of the per-edge ID array (yee_cell_build_ext.pyx:110-257), all host cores ----
+ * Arrays in the reference's layout: solid uint32[nx][ny][nz], rigidE int8[12][nx][ny][nz], rigidH int8[6][nx][ny][nz]
+ * (grid.py:157-169), ID uint32[6][nx+1][ny+1][nz+1] in/out (edges marked rigid keep what the geometry commands wrote).
+ * gpb_ids_scan writes every non-rigid edge of the planes [x0, x1) whose surrounding cells agree and returns the DISTINCT
+ * disagreeing combinations of cell materials, each with the first edge that shows it, sorted in the reference's scan order
+ * (component, i, j, k).  The caller resolves them in that order with create_electric_average / create_magnetic_average
+ * (:31-107) -- which is what fixes the numbering of the averaged materials -- and gpb_ids_apply writes the result on every
+ * disagreeing edge.  Return: 0 ok, 1 bad argument, 2 more than max_combos combinations (*ncombos = the number needed),
+ * 3 a combination met in gpb_ids_apply was not in the table. */
+typedef struct gpb_idcombo_t {
+    uint32_t id[4];                    /* numID1..4 as the reference passes them (magnetic components: 2 used) */
+    int32_t comp, i, j, k;             /* component (0 Ex .. 5 Hz) and first edge in scan order */
+} gpb_idcombo_t;
+int gpb_ids_scan(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
+                 gpb_idcombo_t *combos, int max_combos, int *ncombos);
+int gpb_ids_apply(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
+                  const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos);
 
 const char *gpb_last_error(void);
 const char *gpb_version(void);
