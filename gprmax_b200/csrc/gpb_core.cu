@@ -256,21 +256,33 @@ struct IpcMappings {
         if (e == cudaSuccess) open[key] = {*base, 1};
         return e;
     }
+    // A mapping whose last user is gone stays open: the owner's device-memory cache hands the same allocation to its next
+    // solver (the next trace, the next benchmark repetition), and mapping / unmapping a multi-GB allocation costs tenths of a
+    // second.  gpb_release_cached() closes the idle ones.
     void release(void *base)
     {
         std::lock_guard<std::mutex> g(mu);
-        for (auto it = open.begin(); it != open.end(); ++it)
-            if (it->second.first == base) {
-                if (--it->second.second == 0) {
-                    cudaError_t e = cudaIpcCloseMemHandle(base);
-                    if (e != cudaSuccess) {
-                        if (getenv("GPB_DEBUG")) fprintf(stderr, "[gpb] cudaIpcCloseMemHandle: %s\n", cudaGetErrorString(e));
-                        cudaGetLastError();
-                    }
-                    open.erase(it);
-                }
+        for (auto &kv : open)
+            if (kv.second.first == base) {
+                if (kv.second.second > 0) --kv.second.second;
                 return;
             }
+    }
+    void close_idle()
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto it = open.begin(); it != open.end();) {
+            if (it->second.second == 0) {
+                cudaError_t e = cudaIpcCloseMemHandle(it->second.first);
+                if (e != cudaSuccess) {
+                    if (getenv("GPB_DEBUG")) fprintf(stderr, "[gpb] cudaIpcCloseMemHandle: %s\n", cudaGetErrorString(e));
+                    cudaGetLastError();
+                }
+                it = open.erase(it);
+            } else {
+                ++it;
+            }
+        }
     }
 };
 IpcMappings g_ipc;
@@ -1866,6 +1878,7 @@ extern "C" {
 
 int gpb_release_cached(void)
 {
+    g_ipc.close_idle();
     g_pool.release_all();
     return 0;
 }
