@@ -336,7 +336,15 @@ struct Solver : SolverBase {
     int sm_count = 148;
     TmaMaps4 maps_e, maps_h;
     int setup_tma();
-    int launch_tma(int phase, int p0, int p1);
+    int launch_tma(int phase, int p0, int p1, bool concurrent = false);
+    // H and E half-steps of an iteration as two concurrent kernels coupled by per-chunk progress counters (see PhaseParams)
+    bool overlap_he = false;
+    cudaStream_t stream_e = nullptr;
+    cudaEvent_t evo[2] = {nullptr, nullptr};
+    unsigned *d_progress = nullptr;   // [chunks + 1]: finished H warps per chunk, [chunks] = time-out flag
+    int *d_sched_e = nullptr;
+    int n_he_chunks = 0;
+    int enqueue_overlapped_updates();
     unsigned zslabs_e = 0, zslabs_h = 0;  // z slabs (bit per slab) handled by k_pml_slabs on the v4 path
     uint64_t graph_launches = 0;
     size_t smem_bytes;
@@ -349,6 +357,7 @@ struct Solver : SolverBase {
     Cplx<R> *T[3] = {0, 0, 0};   // treal: the allocation holds R[maxpoles][narr] instead
     Cplx<R> *dcoef = 0;          // treal: R[nmat][maxpoles][3]
     bool treal = false;          // all dispersive coefficients real (Debye media): real-valued T
+    int xblock = 0;              // > 0: planes per block of the x-blocked H/E launch order (GPB_XBLOCK)
     bool tma_disp = false;       // dispersive E half-step on the TMA kernels
     int tma_tpf = 2;
     int *d_iter = 0;  // [0] current, [1] next
@@ -360,6 +369,7 @@ struct Solver : SolverBase {
     SrcDev<R> *d_srcs = 0;
     TLDev<R> *d_tls = 0;
     std::vector<TLDev<R>> h_tls;
+    std::vector<int> h_src_plane, h_src_phase;   // plane and phase (0: magnetic dipole, 1: voltage source / Hertzian dipole) of every point source
     std::vector<std::vector<R>> tl_v0, tl_c0;
     std::vector<R> tl_abc0;
     bool has_hsrc = false, has_esrc = false;
@@ -386,7 +396,8 @@ struct Solver : SolverBase {
     cudaEvent_t evl[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long link_timeout_ns = 20000000000ull;
     bool snap_needs_right = false;
-    bool snap_unlinked_ok = true;    // every snapshot cell of this slab averages planes of this slab only   // some snapshot cell of this shard reads planes of the right neighbour
+    bool snap_unlinked_ok = true;    // every snapshot cell of this slab averages planes of this slab only
+    bool no_overlap_now = false;     // profile(): time the two half-step kernels one after the other   // some snapshot cell of this shard reads planes of the right neighbour
     int begin_run(int n);
     int enqueue_iterations(int n);
     int end_run();
@@ -411,6 +422,9 @@ struct Solver : SolverBase {
             if (e) cudaEventDestroy(e);
         if (stream2) cudaStreamDestroy(stream2);
         if (d_flags) cudaFree(d_flags);
+        for (auto &e : evo)
+            if (e) cudaEventDestroy(e);
+        if (stream_e) cudaStreamDestroy(stream_e);
         for (void *p : allocs) g_pool.free(p);
         if (stream) cudaStreamDestroy(stream);
         cudaError_t e = cudaGetLastError();   // nothing of the tear-down may linger as the "last error" of the next call
@@ -733,6 +747,8 @@ int Solver<R>::setup_points(const gpb_model_t &m)
     if (dalloc(&d_rxs, (size_t)GPB_NRXOUT * iterations * std::max(nrx, 1))) return 1;
     nsrc = m.nsources;
     std::vector<SrcDev<R>> hs(nsrc);
+    h_src_plane.clear();
+    h_src_phase.clear();
     const double dd[3] = {m.dx, m.dy, m.dz};
     for (int s = 0; s < nsrc; ++s) {
         const gpb_source_t &g = m.sources[s];
@@ -740,6 +756,8 @@ int Solver<R>::setup_points(const gpb_model_t &m)
         if (g.kind < 0 || g.kind > 2 || g.polarisation < 0 || g.polarisation > 2) return fail("source %d: bad kind/polarisation", s);
         if (g.i < 0 || g.i > nx || g.j < 0 || g.j > ny || g.k < 0 || g.k > nz) return fail("source %d outside the grid", s);
         d.kind = g.kind; d.i = g.i; d.j = g.j; d.k = g.k; d.pol = g.polarisation;
+        h_src_plane.push_back(g.i);
+        h_src_phase.push_back(g.kind == GPB_SRC_MAGNETIC ? 0 : 1);
         d.it_first = g.it_first; d.it_last = g.it_last; d.hard = 0; d.f1 = 0; d.f2 = 0;
         R *w = nullptr;
         if (upload(&w, (const R *)g.waveform, (size_t)iterations)) return 1;
@@ -932,6 +950,18 @@ int Solver<R>::build(const gpb_model_t &m)
     tma_disp = use_tma && maxpoles > 0 && tma_ty == 14 && tma_tz == 64 && tma_stages == 3 && tma_pw == 1 && !getenv("GPB_DISP_V4") &&
                (size_t)nmat * maxpoles * 3 * (treal ? 1 : 2) * sizeof(R) <= 24 * 1024;
     tma_tpf = getenv("GPB_TMA_TPF") ? std::max(0, atoi(getenv("GPB_TMA_TPF"))) : 2;
+    xblock = getenv("GPB_XBLOCK") ? atoi(getenv("GPB_XBLOCK")) : 0;
+    // concurrent H / E kernels: float32 (two CTAs of the pair per SM), default tile with the producer warp, whole-domain handle
+    // (a shard's halo protocol orders the half-steps itself), nothing that acts on H between the two half-steps (magnetic
+    // dipoles, transmission lines), E half-step on the TMA kernels
+    overlap_he = use_tma && sizeof(R) == 4 && tma_ty == 14 && tma_tz == 64 && tma_stages == 3 && tma_pw == 1 && tma_persist && nplanes == nx + 1 &&
+                 (!maxpoles || tma_disp) && !getenv("GPB_NO_OVERLAP");
+    if (overlap_he) {
+        n_he_chunks = (nplanes + tma_xchunk - 1) / tma_xchunk;
+        if (dalloc(&d_progress, (size_t)n_he_chunks + 1) || dalloc(&d_sched_e, 2)) return 1;
+        CK(cudaStreamCreateWithFlags(&stream_e, cudaStreamNonBlocking));
+        for (auto &e : evo) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     tick("tensor maps");
     if (use_v4) {
         for (int s = 0; s < ph_e.nslabs; ++s)
@@ -1013,7 +1043,7 @@ int Solver<R>::setup_tma()
 
 // E or H half-step of planes [p0, p1) on the TMA-staged kernels (gpb_tma_inst.cu)
 template <typename R>
-int Solver<R>::launch_tma(int phase, int p0, int p1)
+int Solver<R>::launch_tma(int phase, int p0, int p1, bool concurrent)
 {
     TmaLaunch<R> a;
     PhaseParams<R> &p = a.p;
@@ -1039,8 +1069,12 @@ int Solver<R>::launch_tma(int phase, int p0, int p1)
     a.disp = (phase == 1 && maxpoles) ? (treal ? 2 : 1) : 0;
     a.t_max = tma_tpf;
     a.sm_count = sm_count;
-    a.sched = d_sched;
-    a.stream = stream;
+    a.sched = (concurrent && phase == 1) ? d_sched_e : d_sched;
+    a.stream = (concurrent && phase == 1) ? stream_e : stream;
+    a.concurrent = concurrent ? 1 : 0;
+    p.progress = concurrent ? d_progress : nullptr;
+    p.prog_flags = d_progress ? d_progress + n_he_chunks : nullptr;
+    p.prog_timeout_ns = 5000000000ull;
     std::string err;
     const int pv = 2 * form + order - 1;
     int rc;
@@ -1169,8 +1203,12 @@ int Solver<R>::launch_sources(int phase, int p0, int p1, int t0, int t1)
     // point sources on the owned planes [p0, p1) and transmission lines on the owned planes [t0, t1) (local indices)
     if (phase == 0 ? !has_hsrc : !has_esrc) return 0;
     const int i_lo = x_start + p0, i_hi = x_start + p1, tl_lo = x_start + t0, tl_hi = x_start + t1;
-    const bool tl_any = ntl && tl_hi > tl_lo;
-    if ((i_hi <= i_lo || !nsrc) && !tl_any) return 0;
+    // (host copy of the source planes: no launch when nothing of this phase lies in the ranges)
+    bool tl_any = false, src_any = false;
+    for (int t = 0; t < ntl; ++t) tl_any = tl_any || (h_tls[t].i >= tl_lo && h_tls[t].i < tl_hi);
+    for (size_t q = 0; q < h_src_plane.size(); ++q)
+        src_any = src_any || (h_src_phase[q] == phase && h_src_plane[q] >= i_lo && h_src_plane[q] < i_hi);
+    if (!src_any && !tl_any) return 0;
     const int ntl_ = tl_any ? ntl : 0;
     if (idbytes == 1) k_sources<R, uint8_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi);
     else if (idbytes == 2) k_sources<R, uint16_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi);
@@ -1209,10 +1247,41 @@ int Solver<R>::enqueue_step(bool with_snap)
     // model_build_run.py:590-696 in order
     if (launch_begin()) return 1;
     if (with_snap && launch_snapshots()) return 1;
+    if (xblock > 0 && xblock < nplanes) {
+        // x-blocked order: the E half-step of a block of planes right after its H half-step, while the block's fields are
+        // still in L2.  Valid because E(i) needs H(i-1), H(i) (done) and the next block's H update only reads E planes the
+        // E update of this block does not write.
+        for (int a = 0; a < nplanes; a += xblock) {
+            const int b = std::min(a + xblock, nplanes);
+            if (launch_phase(0, a, b) || launch_sources(0, a, b, a, b)) return 1;
+            if (launch_phase(1, a, b) || launch_sources(1, a, b, a, b)) return 1;
+        }
+        return 0;
+    }
+    if (overlap_he && !has_hsrc && !no_overlap_now) {
+        if (enqueue_overlapped_updates()) return 1;
+        return launch_sources(1, 0, nplanes, 0, nplanes);
+    }
     if (launch_phase(0, 0, nplanes)) return 1;
     if (launch_sources(0, 0, nplanes, 0, nplanes)) return 1;
     if (launch_phase(1, 0, nplanes)) return 1;
     if (launch_sources(1, 0, nplanes, 0, nplanes)) return 1;
+    return 0;
+}
+
+// H and E half-steps side by side (one CTA of each kernel per SM).  The E kernel's producer follows the H kernel chunk by chunk
+// through the progress counters, so the E half-step finds the H planes it needs -- and the E planes the H kernel has just read
+// -- in L2: the step moves ~25 % fewer bytes through HBM than two kernels one after the other.
+template <typename R>
+int Solver<R>::enqueue_overlapped_updates()
+{
+    CK(cudaMemsetAsync(d_progress, 0, (size_t)n_he_chunks * sizeof(unsigned), stream));
+    CK(cudaEventRecord(evo[0], stream));
+    CK(cudaStreamWaitEvent(stream_e, evo[0], 0));
+    if (launch_tma(0, 0, nplanes, true)) return 1;
+    if (launch_tma(1, 0, nplanes, true)) return 1;
+    CK(cudaEventRecord(evo[1], stream_e));
+    CK(cudaStreamWaitEvent(stream, evo[1], 0));
     return 0;
 }
 
@@ -1491,6 +1560,11 @@ int Solver<R>::finish_run()
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
     elapsed += ms * 1e-3;
     CK(cudaGetLastError());
+    if (overlap_he) {
+        unsigned t = 0;
+        CK(cudaMemcpy(&t, d_progress + n_he_chunks, sizeof t, cudaMemcpyDeviceToHost));
+        if (t) return fail("concurrent H / E kernels: the E kernel waited more than 5 s for the H kernel's progress (GPB_NO_OVERLAP=1 runs them one after the other)");
+    }
     return check_link_timeout();
 }
 
@@ -1501,10 +1575,10 @@ std::string Solver<R>::kernel_path() const
     auto name = [&](int phase) -> std::string {
         const char *dn = treal ? "DISP=real" : "DISP=complex";
         if (use_tma && !(phase == 1 && maxpoles && !tma_disp)) {
-            char b[96];
+            char b[128];
             if (phase == 1 && maxpoles) snprintf(b, sizeof b, "k_update_tma<%dx%d,PHASE=1,%s>", tma_ty, tma_tz, dn);
             else snprintf(b, sizeof b, "k_update_tma<%dx%d,PHASE=%d>", tma_ty, tma_tz, phase);
-            return b;
+            return std::string(b) + ((overlap_he && !has_hsrc) ? (phase == 0 ? "||" : "(concurrent)") : "");
         }
         if (use_v4) return phase == 0 ? "k_update_h4" : (maxpoles ? std::string("k_update_e4<") + dn + ">" : "k_update_e4");
         return phase == 0 ? "k_update_h" : (maxpoles ? std::string("k_update_e<") + dn + ">" : "k_update_e");
@@ -1523,6 +1597,7 @@ int Solver<R>::profile(int n, double *ms4)
     if (linked) return fail("gpb_profile works on unlinked handles only");
     cudaEvent_t ev[6];
     for (auto &e : ev) CK(cudaEventCreate(&e));
+    // (profile() always times the half-step kernels one after the other; gpb_profile_step times the iteration as gpb_run runs it)
     for (int q = 0; q < 4; ++q) ms4[q] = 0;
     for (int s = 0; s < n; ++s) {
         CK(cudaEventRecord(ev[0], stream));

@@ -99,6 +99,14 @@ struct PhaseParams {
     int pf_depth;             // TMA kernels: Phi prefetch distance in planes (cp.async ring per thread), 0 = direct loads
     int persist;              // TMA kernels: persistent CTAs pulling (tile, x-chunk) items from an atomic counter
     int t_depth;              // TMA kernels, dispersive E half-step: T prefetch distance in planes (cp.async ring per thread), 0 = direct loads
+    // TMA kernels, H and E half-steps of one iteration running CONCURRENTLY (Solver::overlap_he): both hand their x chunks out
+    // in increasing x; the H kernel counts finished (tile, chunk) items per chunk in progress[], the E kernel's producer loads a
+    // chunk only when the H items of that chunk and of the one before it are complete -- so E reads H (and re-reads E) out of L2
+    int monotone;
+    unsigned *progress;       // [nchunks] finished H warps per chunk (null: kernels run one after the other)
+    unsigned prog_need;       // tiles * consumer warps
+    unsigned *prog_flags;     // [0] |= 1 when a wait timed out
+    unsigned long long prog_timeout_ns;
 };
 
 // ------------------------------------------------------------------------------------------

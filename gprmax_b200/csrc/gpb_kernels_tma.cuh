@@ -182,11 +182,13 @@ __device__ __forceinline__ int chunk_of(int q, int nchunks)
 }
 // Plane range [l0, l1) of hand-out slot v.  The last `nsplit` chunks of the hand-out order (about one wave of items) are
 // handed out as two halves each, so that the SMs run dry within half an item of each other at the end of the kernel.
-__device__ __forceinline__ void chunk_range(int v, int nchunks, int nsplit, int xc, int p0, int p1, int &l0, int &l1)
+__device__ __forceinline__ void chunk_range(int v, int nchunks, int nsplit, int xc, int p0, int p1, int &l0, int &l1, int monotone = 0)
 {
     const int nbig = nchunks - nsplit;
     int c, lo = 0, len = xc;
-    if (v < nbig) {
+    if (monotone) {
+        c = v;   // increasing x (concurrent H / E kernels)
+    } else if (v < nbig) {
         c = chunk_of(v, nchunks);
     } else {
         const int u = v - nbig;
@@ -346,7 +348,26 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
             const int tile = p_item & 0xfffff, chunk = p_item >> 20;
             p_k0 = (tile % tiles_k) * TZ;
             p_j0 = (tile / tiles_k) * TY;
-            chunk_range(chunk, nchunks, nsplit, p.xchunk, p.p0, p.p1, p_l0, p_l1);
+            chunk_range(chunk, nchunks, nsplit, p.xchunk, p.p0, p.p1, p_l0, p_l1, p.monotone);
+            if (PHASE == 1 && p.progress) {
+                // concurrent H kernel: the H fields of this chunk's planes and of the plane in front of them must be final.
+                // The finished items were published with fence + atomic by the H kernel's warps; acquire here, then order the
+                // TMA (async proxy) loads that follow behind what was acquired.
+                unsigned long long t0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for (int cc = chunk > 0 ? chunk - 1 : chunk; cc <= chunk; ++cc) {
+                    unsigned v;
+                    for (;;) {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.progress + cc) : "memory");
+                        if (v >= p.prog_need) break;
+                        __nanosleep(100);
+                        unsigned long long t1;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > p.prog_timeout_ns) { atomicOr(p.prog_flags, 1u); break; }
+                    }
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
         }
         p_n = -1;
     };
@@ -422,7 +443,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     const int k0 = (tile % tiles_k) * TZ, j0 = (tile / tiles_k) * TY;
     const int j = j0 + r, k = k0 + c;
     int l0, l1;
-    chunk_range(chunkid, nchunks, nsplit, p.xchunk, p.p0, p.p1, l0, l1);
+    chunk_range(chunkid, nchunks, nsplit, p.xchunk, p.p0, p.p1, l0, l1, p.monotone);
     const int nl = l1 - l0;
     V4<R> qb, qc;   // register queue: operand B / C of the x-neighbour plane at my cells
     {
@@ -863,6 +884,11 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         }
         qb = b_c;
         qc = c_c;
+    }
+    if (PHASE == 0 && p.progress) {   // this warp's part of the item is in memory: publish (see the E kernel's producer)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.progress + chunkid, 1u);
     }
     }   // items
 

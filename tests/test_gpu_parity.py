@@ -229,7 +229,7 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
     G.ID = rng.integers(2, G.updatecoeffsE.shape[0], size=G.ID.shape, dtype=np.uint32)
 
     def run(env):
-        for k in ('GPB_NO_TMA', 'GPB_TMA_NOPERSIST', 'GPB_TMA_PW', 'GPB_TMA_ZSPLIT', 'GPB_TMA_ZNOCOOP'):
+        for k in ('GPB_NO_TMA', 'GPB_TMA_NOPERSIST', 'GPB_TMA_PW', 'GPB_TMA_ZSPLIT', 'GPB_TMA_ZNOCOOP', 'GPB_NO_OVERLAP'):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -242,7 +242,8 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
     # the field has reached the x0 / ymax / z0 corner region of the PML (all three slabs overlap there)
     for c in range(6):
         assert np.abs(ref[c][1:9, ny - 9:ny - 1, 1:9]).max() > 0, c
-    for env in ({}, {}, {'GPB_TMA_NOPERSIST': '1'}, {'GPB_TMA_PW': '0'}, {'GPB_TMA_ZSPLIT': '1'}, {'GPB_TMA_ZNOCOOP': '1'}):
+    # {} = the default: H and E kernels of an iteration running concurrently, coupled by progress counters
+    for env in ({}, {}, {'GPB_NO_OVERLAP': '1'}, {'GPB_TMA_NOPERSIST': '1'}, {'GPB_TMA_PW': '0'}, {'GPB_TMA_ZSPLIT': '1'}, {'GPB_TMA_ZNOCOOP': '1'}):
         out = run(env)
         for c, (a, b) in enumerate(zip(out, ref)):
             assert np.array_equal(a, b), (env, c, int((a != b).sum()))
@@ -276,6 +277,36 @@ def test_dispersive_families_and_real_T_bit_identical(monkeypatch):
         path, out = run(env)
         for c, (a, b) in enumerate(zip(out, ref)):
             assert np.array_equal(a, b), (env, path, c, int((a != b).sum()))
+
+
+@pytest.mark.parametrize('name', ['pml_HORIPML_2', 'pml_MRIPML_1', 'hertzian_dipole_dispersive', 'heterogeneous_soil_small', 'bench_100', 'snapshots', 'sources_mixed'])
+def test_f32_concurrent_half_step_kernels_bit_identical(name, monkeypatch):
+    """float32 on the TMA kernels: by default the H and the E kernel of an iteration run side by side (the E kernel's producer
+    follows the H kernel through per-chunk progress counters and reads the fresh H planes out of L2).  Same bits as the two
+    kernels one after the other and as the register-vectorised kernels, three runs in a row (a race would show as jitter)."""
+    from gprmax_b200 import Solver
+    from gprmax_b200.model_io import load_model
+    G, _ = load_model(golden_path(name, 'f32'))
+
+    def run(env):
+        for k in ('GPB_FORCE_TMA', 'GPB_NO_TMA', 'GPB_NO_OVERLAP'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Solver(G, device_id=0) as sv:
+            path = sv.kernel_path
+            sv.run()
+            return path, [sv.get_field(c) for c in range(6)] + [sv.receivers()]
+
+    _, ref = run({'GPB_NO_TMA': '1'})
+    pseq, seq = run({'GPB_FORCE_TMA': '1', 'GPB_NO_OVERLAP': '1'})
+    assert 'k_update_tma' in pseq and 'concurrent' not in pseq
+    for rep in range(3):
+        pcon, con = run({'GPB_FORCE_TMA': '1'})
+        if name != 'sources_mixed':   # a magnetic dipole acts between the half-steps: those models keep the kernels in sequence
+            assert 'concurrent' in pcon, pcon
+        for c, (a, b, d) in enumerate(zip(con, seq, ref)):
+            assert np.array_equal(a, b) and np.array_equal(a, d), (name, rep, c)
 
 
 def test_device_memory_cache_reuse_and_release():
