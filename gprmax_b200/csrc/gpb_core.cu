@@ -336,15 +336,14 @@ struct Solver : SolverBase {
     int sm_count = 148;
     TmaMaps4 maps_e, maps_h;
     int setup_tma();
-    int launch_tma(int phase, int p0, int p1, bool concurrent = false);
-    // H and E half-steps of an iteration as two concurrent kernels coupled by per-chunk progress counters (see PhaseParams)
-    bool overlap_he = false;
-    cudaStream_t stream_e = nullptr;
-    cudaEvent_t evo[2] = {nullptr, nullptr};
+    int launch_tma(int phase, int p0, int p1);
+    // H and E half-steps of an iteration in ONE launch (gpb_kernels_pair.cuh): items of both phases from one queue, the E items
+    // of a chunk about two chunks behind its H items, so E finds its operands in L2
+    bool pair_he = false;
+    int pair_xchunk = 4;
     unsigned *d_progress = nullptr;   // [chunks + 1]: finished H warps per chunk, [chunks] = time-out flag
-    int *d_sched_e = nullptr;
     int n_he_chunks = 0;
-    int enqueue_overlapped_updates();
+    int launch_pair();
     unsigned zslabs_e = 0, zslabs_h = 0;  // z slabs (bit per slab) handled by k_pml_slabs on the v4 path
     uint64_t graph_launches = 0;
     size_t smem_bytes;
@@ -422,9 +421,6 @@ struct Solver : SolverBase {
             if (e) cudaEventDestroy(e);
         if (stream2) cudaStreamDestroy(stream2);
         if (d_flags) cudaFree(d_flags);
-        for (auto &e : evo)
-            if (e) cudaEventDestroy(e);
-        if (stream_e) cudaStreamDestroy(stream_e);
         for (void *p : allocs) g_pool.free(p);
         if (stream) cudaStreamDestroy(stream);
         cudaError_t e = cudaGetLastError();   // nothing of the tear-down may linger as the "last error" of the next call
@@ -951,17 +947,17 @@ int Solver<R>::build(const gpb_model_t &m)
                (size_t)nmat * maxpoles * 3 * (treal ? 1 : 2) * sizeof(R) <= 24 * 1024;
     tma_tpf = getenv("GPB_TMA_TPF") ? std::max(0, atoi(getenv("GPB_TMA_TPF"))) : 2;
     xblock = getenv("GPB_XBLOCK") ? atoi(getenv("GPB_XBLOCK")) : 0;
-    // concurrent H / E kernels: float32 (two CTAs of the pair per SM), default tile with the producer warp, whole-domain handle
-    // (a shard's halo protocol orders the half-steps itself), nothing that acts on H between the two half-steps (magnetic
-    // dipoles, transmission lines), E half-step on the TMA kernels
-    overlap_he = use_tma && sizeof(R) == 4 && tma_ty == 14 && tma_tz == 64 && tma_stages == 3 && tma_pw == 1 && tma_persist && nplanes == nx + 1 &&
-                 (!maxpoles || tma_disp) && !getenv("GPB_NO_OVERLAP");
-    if (overlap_he) {
-        n_he_chunks = (nplanes + tma_xchunk - 1) / tma_xchunk;
-        if (dalloc(&d_progress, (size_t)n_he_chunks + 1) || dalloc(&d_sched_e, 2)) return 1;
-        CK(cudaStreamCreateWithFlags(&stream_e, cudaStreamNonBlocking));
-        for (auto &e : evo) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // both half-steps in one launch: default tile with the producer warp, whole-domain handle (a shard's halo protocol orders
+    // the half-steps itself), E half-step on the TMA kernels; models with something that acts on H between the two half-steps
+    // (magnetic dipoles, transmission lines) keep the two launches (checked per step: has_hsrc)
+    pair_he = use_tma && tma_ty == 14 && tma_tz == 64 && tma_stages == 3 && tma_pw == 1 && tma_persist && nplanes == nx + 1 &&
+              (!maxpoles || tma_disp) && !getenv("GPB_NO_PAIR");
+    if (pair_he) {
+        pair_xchunk = getenv("GPB_PAIR_XCHUNK") ? std::max(1, atoi(getenv("GPB_PAIR_XCHUNK"))) : 4;
+        n_he_chunks = (nplanes + pair_xchunk - 1) / pair_xchunk;
+        if (n_he_chunks >= (1 << 11)) pair_he = false;
     }
+    if (pair_he && dalloc(&d_progress, (size_t)n_he_chunks + 1)) return 1;
     tick("tensor maps");
     if (use_v4) {
         for (int s = 0; s < ph_e.nslabs; ++s)
@@ -1037,13 +1033,13 @@ int Solver<R>::setup_tma()
     if (tiles * ((nplanes + 7) / 8) < 2ll * 2 * sm_count) tma_xchunk = 4;
     if (getenv("GPB_TMA_XCHUNK")) tma_xchunk = std::max(1, atoi(getenv("GPB_TMA_XCHUNK")));
     // work items travel as tile | chunk << 20 through the kernels' item ring
-    if (tiles >= (1ll << 20) || (nplanes + tma_xchunk - 1) / tma_xchunk >= (1 << 11)) use_tma = false;
+    if (tiles >= (1ll << 19) || (nplanes + tma_xchunk - 1) / tma_xchunk >= (1 << 11)) use_tma = false;
     return 0;
 }
 
 // E or H half-step of planes [p0, p1) on the TMA-staged kernels (gpb_tma_inst.cu)
 template <typename R>
-int Solver<R>::launch_tma(int phase, int p0, int p1, bool concurrent)
+int Solver<R>::launch_tma(int phase, int p0, int p1)
 {
     TmaLaunch<R> a;
     PhaseParams<R> &p = a.p;
@@ -1069,12 +1065,10 @@ int Solver<R>::launch_tma(int phase, int p0, int p1, bool concurrent)
     a.disp = (phase == 1 && maxpoles) ? (treal ? 2 : 1) : 0;
     a.t_max = tma_tpf;
     a.sm_count = sm_count;
-    a.sched = (concurrent && phase == 1) ? d_sched_e : d_sched;
-    a.stream = (concurrent && phase == 1) ? stream_e : stream;
-    a.concurrent = concurrent ? 1 : 0;
-    p.progress = concurrent ? d_progress : nullptr;
-    p.prog_flags = d_progress ? d_progress + n_he_chunks : nullptr;
-    p.prog_timeout_ns = 5000000000ull;
+    a.sched = d_sched;
+    a.stream = stream;
+    a.concurrent = 0;
+    p.progress = nullptr;
     std::string err;
     const int pv = 2 * form + order - 1;
     int rc;
@@ -1258,8 +1252,8 @@ int Solver<R>::enqueue_step(bool with_snap)
         }
         return 0;
     }
-    if (overlap_he && !has_hsrc && !no_overlap_now) {
-        if (enqueue_overlapped_updates()) return 1;
+    if (pair_he && !has_hsrc) {
+        if (launch_pair()) return 1;
         return launch_sources(1, 0, nplanes, 0, nplanes);
     }
     if (launch_phase(0, 0, nplanes)) return 1;
@@ -1269,19 +1263,45 @@ int Solver<R>::enqueue_step(bool with_snap)
     return 0;
 }
 
-// H and E half-steps side by side (one CTA of each kernel per SM).  The E kernel's producer follows the H kernel chunk by chunk
-// through the progress counters, so the E half-step finds the H planes it needs -- and the E planes the H kernel has just read
-// -- in L2: the step moves ~25 % fewer bytes through HBM than two kernels one after the other.
+// H and E half-steps of the whole grid in one launch of k_update_pair
 template <typename R>
-int Solver<R>::enqueue_overlapped_updates()
+int Solver<R>::launch_pair()
 {
     CK(cudaMemsetAsync(d_progress, 0, (size_t)n_he_chunks * sizeof(unsigned), stream));
-    CK(cudaEventRecord(evo[0], stream));
-    CK(cudaStreamWaitEvent(stream_e, evo[0], 0));
-    if (launch_tma(0, 0, nplanes, true)) return 1;
-    if (launch_tma(1, 0, nplanes, true)) return 1;
-    CK(cudaEventRecord(evo[1], stream_e));
-    CK(cudaStreamWaitEvent(stream, evo[1], 0));
+    TmaLaunchPair<R> a;
+    for (int phase = 0; phase < 2; ++phase) {
+        PhaseParams<R> &p = phase == 0 ? a.ph : a.pe;
+        p = phase == 0 ? ph_h : ph_e;
+        p.p0 = 0; p.p1 = nplanes; p.xchunk = pair_xchunk; p.persist = 1;
+        p.fast_i0 = std::max(p.box[0].lo[0], std::max(p.box[1].lo[0], p.box[2].lo[0]));
+        p.fast_i1 = std::min(p.box[0].hi[0], std::min(p.box[1].hi[0], p.box[2].hi[0]));
+        for (int s = 0; s < p.nslabs; ++s)
+            if (p.slab[s].axis == 0) {
+                if (p.slab[s].minus) p.fast_i0 = std::max(p.fast_i0, p.slab[s].hi[0]);
+                else p.fast_i1 = std::min(p.fast_i1, p.slab[s].lo[0]);
+            }
+        if (tma_nofast) p.fast_i1 = p.fast_i0;
+        p.zfused = 1;
+        p.znocoop = tma_znocoop ? 1 : 0;
+        p.progress = d_progress;
+        p.prog_flags = d_progress + n_he_chunks;
+        p.prog_timeout_ns = 5000000000ull;
+    }
+    a.maps_h = &maps_h; a.maps_e = &maps_e;
+    a.idbytes = idbytes; a.pf_max = tma_pf; a.t_max = tma_tpf;
+    a.disp = maxpoles ? (treal ? 2 : 1) : 0;
+    a.sm_count = sm_count; a.sched = d_sched; a.stream = stream;
+    std::string err;
+    const int pv = 2 * form + order - 1;
+    int rc;
+    switch (pv) {
+    case 0: rc = tma_launch_pair<R, 0>(a, &err); break;
+    case 1: rc = tma_launch_pair<R, 1>(a, &err); break;
+    case 2: rc = tma_launch_pair<R, 2>(a, &err); break;
+    default: rc = tma_launch_pair<R, 3>(a, &err); break;
+    }
+    if (rc) return fail("%s", err.c_str());
+    ++launches;
     return 0;
 }
 
@@ -1560,10 +1580,10 @@ int Solver<R>::finish_run()
     CK(cudaEventElapsedTime(&ms, ev0, ev1));
     elapsed += ms * 1e-3;
     CK(cudaGetLastError());
-    if (overlap_he) {
+    if (pair_he) {
         unsigned t = 0;
         CK(cudaMemcpy(&t, d_progress + n_he_chunks, sizeof t, cudaMemcpyDeviceToHost));
-        if (t) return fail("concurrent H / E kernels: the E kernel waited more than 5 s for the H kernel's progress (GPB_NO_OVERLAP=1 runs them one after the other)");
+        if (t) return fail("k_update_pair: an E item waited more than 5 s for the H items it depends on (GPB_NO_PAIR=1 runs the half-steps as two launches)");
     }
     return check_link_timeout();
 }
@@ -1578,7 +1598,7 @@ std::string Solver<R>::kernel_path() const
             char b[128];
             if (phase == 1 && maxpoles) snprintf(b, sizeof b, "k_update_tma<%dx%d,PHASE=1,%s>", tma_ty, tma_tz, dn);
             else snprintf(b, sizeof b, "k_update_tma<%dx%d,PHASE=%d>", tma_ty, tma_tz, phase);
-            return std::string(b) + ((overlap_he && !has_hsrc) ? (phase == 0 ? "||" : "(concurrent)") : "");
+            return std::string(b) + ((pair_he && !has_hsrc) ? " [one launch: k_update_pair]" : "");
         }
         if (use_v4) return phase == 0 ? "k_update_h4" : (maxpoles ? std::string("k_update_e4<") + dn + ">" : "k_update_e4");
         return phase == 0 ? "k_update_h" : (maxpoles ? std::string("k_update_e<") + dn + ">" : "k_update_e");

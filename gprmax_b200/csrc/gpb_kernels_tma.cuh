@@ -277,7 +277,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     // DISP (electric half-step only): 0 no dispersive media, 1 complex T, 2 real T (Debye media) -- the polarisation arrays are
     // read and written once per step by the thread that owns the cells, prefetched like Phi (per-thread cp.async, p.t_depth)
     static_assert(DISP == 0 || PHASE == 1, "dispersive update belongs to the electric half-step");
-    constexpr int TW = DISP == 1 ? 2 : 1;   // V4 vectors per 4 cells of T
+    constexpr int KTW = DISP == 1 ? 2 : 1;   // V4 vectors per 4 cells of T
     using L = StageLayout<R, IDT, TY, TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);   // [kStages] TMA bytes landed
@@ -292,9 +292,9 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     const int pf_bytes = p.pf_depth * 2 * PORDER * kTmaThreads * (int)sizeof(V4<R>);
     // dispersive: coefficient triples [nmat][poles][3] (R or complex) and the T prefetch slots [t_depth][3 comps][poles][TW][threads]
     R *sdc = reinterpret_cast<R *>(smem_raw + 128 + coef_bytes + tab_bytes + pf_bytes);
-    const int dc_bytes = DISP ? (int)((p.nmat * p.maxpoles * 3 * TW * sizeof(R) + 127) / 128 * 128) : 0;
+    const int dc_bytes = DISP ? (int)((p.nmat * p.maxpoles * 3 * KTW * sizeof(R) + 127) / 128 * 128) : 0;
     V4<R> *stf = reinterpret_cast<V4<R> *>(smem_raw + 128 + coef_bytes + tab_bytes + pf_bytes + dc_bytes);
-    const int tslot = DISP ? 3 * p.maxpoles * TW * kTmaThreads : 0;   // V4 vectors per plane of T slots
+    const int tslot = DISP ? 3 * p.maxpoles * KTW * kTmaThreads : 0;   // V4 vectors per plane of T slots
     const int tf_bytes = DISP ? p.t_depth * tslot * (int)sizeof(V4<R>) : 0;
     unsigned char *stages = smem_raw + 128 + coef_bytes + tab_bytes + pf_bytes + dc_bytes + tf_bytes;
 
@@ -320,7 +320,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     }
     if (DISP) {
         const R *src = reinterpret_cast<const R *>(p.dcoef);
-        for (int m = tid; m < p.nmat * p.maxpoles * 3 * TW; m += kTmaThreads + 32 * PW) sdc[m] = src[m];
+        for (int m = tid; m < p.nmat * p.maxpoles * 3 * KTW; m += kTmaThreads + 32 * PW) sdc[m] = src[m];
     }
     for (int s = 0; s < p.nslabs; ++s) {
         const SlabDev<R> &sl = p.slab[s];
@@ -345,7 +345,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         // 7 % of the SM cycles are idle at the end -- broke that locality: 57.5 -> 53.8 Gcells/s at 300^3, 75.2 -> 66.8 at 500^3.)
         p_item = w < W ? ((w % tiles) | ((w / tiles) << 20)) : -1;
         if (p_item >= 0) {
-            const int tile = p_item & 0xfffff, chunk = p_item >> 20;
+            const int tile = p_item & 0x7ffff, chunk = p_item >> 20;
             p_k0 = (tile % tiles_k) * TZ;
             p_j0 = (tile / tiles_k) * TY;
             chunk_range(chunk, nchunks, nsplit, p.xchunk, p.p0, p.p1, p_l0, p_l1, p.monotone);
@@ -423,15 +423,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
 
     // ---------------- consumers
     const int r = tid / (TZ / 4), c = (tid % (TZ / 4)) * 4;
-    // element offsets of my 4 cells inside the operand / own tiles
-    const int eo = PHASE == 1 ? ((r + 1) * L::PA + c + 4) : (r * L::PA + c);   // centre
-    const int eoj = PHASE == 1 ? (eo - L::PA) : (eo + L::PA);                    // j-1 (E) / j+1 (H)
     const int e = r * TZ + c;
-
-    // fields this phase writes (the operand arrays are read-only in this phase)
-    R *__restrict__ F0 = PHASE == 1 ? p.Ex : p.Hx;
-    R *__restrict__ F1 = PHASE == 1 ? p.Ey : p.Hy;
-    R *__restrict__ F2 = PHASE == 1 ? p.Ez : p.Hz;
 
     int g = 0;   // consumer position in the slot sequence
     for (int q = 0;; ++q) {
@@ -439,457 +431,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     mbar_wait(full + (g % kStages), (uint32_t)((g / kStages) & 1));
     const int item = ring[q & 3];
     if (item < 0) break;
-    const int tile = item & 0xfffff, chunkid = item >> 20;
-    const int k0 = (tile % tiles_k) * TZ, j0 = (tile / tiles_k) * TY;
-    const int j = j0 + r, k = k0 + c;
-    int l0, l1;
-    chunk_range(chunkid, nchunks, nsplit, p.xchunk, p.p0, p.p1, l0, l1, p.monotone);
-    const int nl = l1 - l0;
-    V4<R> qb, qc;   // register queue: operand B / C of the x-neighbour plane at my cells
-    {
-        const R *sX = reinterpret_cast<const R *>(stages + (size_t)(g % kStages) * L::bytes + L::oOwn);
-        qb = ld4(sX + eo);
-        qc = ld4(sX + L::CS + eo);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + (g % kStages));
-        if (!PW && tid == 0 && !p_done) produce();
-        ++g;
-    }
-
-    const bool valid = j <= p.ny && k <= p.nz;
-    const JK4 bx = jk4_of(p.box[0].lo, p.box[0].hi, j, k), by = jk4_of(p.box[1].lo, p.box[1].hi, j, k), bz = jk4_of(p.box[2].lo, p.box[2].hi, j, k);
-    unsigned smask = 0;
-#pragma unroll
-    for (int s = 0; s < kMaxSlabs; ++s)
-        // (slabs that do not meet this tile in (j, k) at all are skipped with a CTA-uniform test)
-        if (s < p.nslabs && (p.zfused || p.slab[s].axis != 2) && valid && p.slab[s].lo[1] < j0 + TY && p.slab[s].hi[1] > j0 && p.slab[s].lo[2] < k0 + TZ &&
-            p.slab[s].hi[2] > k0)
-            smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
-    const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u);
-    // fast cells: all 4 inside all three update boxes and outside every y- and z-slab footprint; on the planes between the x
-    // slabs (p.fast_i0 <= i < p.fast_i1) such a thread needs no masks and no slab logic
-    unsigned yfoot = 0;
-#pragma unroll
-    for (int s = 0; s < kMaxSlabs; ++s)
-        if (s < p.nslabs && p.slab[s].axis != 0) yfoot |= (smask >> (4 * s)) & 0xfu;
-    const bool fast_jk = valid && bx.kmask == 0xfu && by.kmask == 0xfu && bz.kmask == 0xfu && yfoot == 0u;
-    const long long eoff = valid ? ((long long)j * p.pitch + k) : 0;
-
-    // Phi prefetch: the lowest-numbered slab that touches my cells on a plane is fetched one plane ahead (pf_depth 2) or at the
-    // top of the same iteration (pf_depth 1) with per-thread cp.async into a private shared-memory slot, so the DRAM latency of
-    // Phi hides behind the TMA wait and the base update; any further slab on the same cells (edges, corners) loads directly
-    unsigned smask6 = 0;   // bit s: slab s touches at least one of my cells
-#pragma unroll
-    for (int s = 0; s < kMaxSlabs; ++s)
-        if ((smask >> (4 * s)) & 0xfu) smask6 |= 1u << s;
-    // Cooperative z-slab corrections.  A z slab covers ~10 cells at one end of every z row: handled per thread, 3 of the 16
-    // threads of a row would run the whole correction for their 4 cells while the other 13 idle (r1k: the z corrections were the
-    // largest PML cost, executed by 40 % of all warps on 6 of 32 lanes).  Instead lane c of a row takes ONE cell (column zkq0 + c
-    // of its own row) and both components, and hands the correction to the owner of the cell by warp shuffle.  Needs a single z
-    // slab in the tile with at most TZ/4 columns here; otherwise that slab stays on the per-thread path.
-    constexpr int LPR = TZ / 4;   // lanes per tile row
-    int zs = -1;
-    if (p.zfused && !p.znocoop) {
-#pragma unroll
-        for (int s = 0; s < kMaxSlabs; ++s)
-            if (s < p.nslabs && p.slab[s].axis == 2 && min(k0 + TZ, p.slab[s].hi[2]) > max(k0, p.slab[s].lo[2])) zs = zs == -1 ? s : -2;
-    }
-    int zkq0 = 0;
-    if (zs >= 0) {
-        zkq0 = max(p.slab[zs].ko, k0);
-        if (LPR > 32 || min(p.slab[zs].hi[2], k0 + TZ) - zkq0 > LPR) zs = -1;
-    }
-    const bool zcoop = zs >= 0;
-    const int zc = zcoop ? zs : 0;                      // index used for parameter reads (any valid slab when unused)
-    const int zk = zkq0 + (tid % LPR);                  // my cooperative cell: own row j, column zk
-    const bool zok = zcoop && j <= p.ny && j >= p.slab[zc].lo[1] && j < p.slab[zc].hi[1] && zk >= p.slab[zc].lo[2] && zk < p.slab[zc].hi[2];
-    const int zdepth = p.slab[zc].minus ? (p.slab[zc].dref - zk) : (zk - p.slab[zc].dref);
-    const long long zphi_off = zok ? ((long long)(j - p.slab[zc].lo[1]) * p.slab[zc].n2 + (zk - p.slab[zc].ko)) : 0;
-    const unsigned zm = zcoop ? ((smask >> (4 * zc)) & 0xfu) : 0u;   // cells of my own quad inside that slab
-    if (zcoop) {   // the per-thread machinery (prefetch, slab loop) no longer sees the slab
-        smask6 &= ~(1u << zc);
-    }
-    const bool pf = smask6 != 0u && p.pf_depth > 0;
-    auto i_of = [&](int n) { return p.x_start + (PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1)) - 1; };
-    // Order of the slab corrections on a cell: x and y slabs in G.pmls order, then the z slabs -- the same order in every
-    // kernel family (the register-vectorised path applies its z slabs in a second kernel, k_pml_slabs), so that edge and
-    // corner cells, which take two or three corrections, get the same bits whichever family a grid or a shard runs on.
-    unsigned zbits = 0;
-#pragma unroll
-    for (int s = 0; s < kMaxSlabs; ++s)
-        if (s < p.nslabs && p.slab[s].axis == 2) zbits |= 1u << s;
-    auto first_of = [&](unsigned m) { return __ffs((m & ~zbits) ? (m & ~zbits) : m) - 1; };
-    auto prefetch = [&](V4<R> *slot, unsigned pmn, int ii) {   // Phi of the first slab (in application order) of pmn at plane ii -> my slot
-        const SlabDev<R> &sl = p.slab[first_of(pmn)];
-        const R *phi = sl.phi + ((long long)(ii - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
-        for (int q = 0; q < 2 * PORDER; ++q) cp_async_v4<R>(slot + q * kTmaThreads, phi + q * sl.ostride);
-    };
-    // slabs on a plane (CTA-uniform): the same set on every plane of the item unless the item straddles the edge of an x slab
-    unsigned act_all = 0, act_some = 0;
-    {
-        const int ilo = min(i_of(0), i_of(nl - 1)), ihi = max(i_of(0), i_of(nl - 1));
-#pragma unroll
-        for (int s = 0; s < kMaxSlabs; ++s)
-            if (s < p.nslabs) {
-                if (ilo >= p.slab[s].lo[0] && ihi < p.slab[s].hi[0]) act_all |= 1u << s;
-                if (ihi >= p.slab[s].lo[0] && ilo < p.slab[s].hi[0]) act_some |= 1u << s;
-            }
-    }
-    const bool act_same = act_all == act_some;
-    auto act_of = [&](int n) { return act_same ? act_all : slabs_on_plane(p, i_of(n)); };
-    // T prefetch (dispersive): every thread with cells on the grid fetches its 4 cells of every pole and component
-    const bool tpf = DISP && p.t_depth > 0 && any;
-    auto tprefetch = [&](V4<R> *slot, int n) {   // T of plane n of this item -> my slots [comp][pole][TW]
-        const long long off = (long long)(PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1)) * p.plane + eoff;
-        for (int cq = 0; cq < 3 * p.maxpoles; ++cq) {
-            const R *g = reinterpret_cast<const R *>(p.T[cq / p.maxpoles]) + ((long long)(cq % p.maxpoles) * p.tstride + off) * TW;
-            for (int w = 0; w < TW; ++w) cp_async_v4<R>(slot + (cq * TW + w) * kTmaThreads, g + 4 * w);
-        }
-    };
-    // One cp.async group per plane, committed at the top of the loop body, holds whatever is fetched then: Phi and / or T of
-    // this plane (distance 1) or of the next one (distance 2).  Data of distance 2 is complete after wait_group 1, of distance 1
-    // after wait_group 0.  A distance-2 user needs one group in front of the loop for plane 0.
-    const bool pf2 = pf && p.pf_depth == 2, tpf2 = tpf && p.t_depth == 2;
-    // (the commits are uniform per thread; whether a thread has anything in the group does not matter)
-    const bool grouped = (p.pf_depth > 0 && p.nslabs > 0) || (DISP && p.t_depth > 0);
-    const bool lead_group = (p.pf_depth == 2 && p.nslabs > 0) || (DISP && p.t_depth == 2);
-    if (lead_group) {
-        if (pf2 && (act_of(0) & smask6)) prefetch(spf + tid, act_of(0) & smask6, i_of(0));
-        if (tpf2) tprefetch(stf + tid, 0);
-        cp_async_commit();
-    }
-
-    // dispersive sum of one component on my 4 cells (all poles): T from my prefetch slot or from global memory, advanced and
-    // written back; u = base update - srce * phi on the cells inside the component's update box
-    auto disp_apply = [&](int comp, const IdQ<IDT> &idq, unsigned m, const V4<R> &eold, V4<R> &u, int n, int pl) {
-        if (!m) return;
-        float ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0;
-        const unsigned i0 = idq.at(0);
-        unsigned i1 = i0, i2 = i0, i3 = i0;
-        if (!idq.uniform()) { i1 = idq.at(1); i2 = idq.at(2); i3 = idq.at(3); }
-        const int P = p.maxpoles;
-        R *Tg = reinterpret_cast<R *>(p.T[comp]) + ((long long)pl * p.plane + eoff) * TW;
-        const V4<R> *slot = tpf ? stf + (size_t)(n % p.t_depth) * tslot + (size_t)comp * P * TW * kTmaThreads + tid : nullptr;
-        for (int q = 0; q < P; ++q) {
-            R *Tq = Tg + (long long)q * p.tstride * TW;
-            if (DISP == 2) {
-                V4<R> t = slot ? slot[(size_t)q * kTmaThreads] : ld4(Tq);
-                if (m & 1u) disp_cell_r(sdc + ((size_t)i0 * P + q) * 3, eold.x, t.x, ph0);
-                if (m & 2u) disp_cell_r(sdc + ((size_t)i1 * P + q) * 3, eold.y, t.y, ph1);
-                if (m & 4u) disp_cell_r(sdc + ((size_t)i2 * P + q) * 3, eold.z, t.z, ph2);
-                if (m & 8u) disp_cell_r(sdc + ((size_t)i3 * P + q) * 3, eold.w, t.w, ph3);
-                st4(Tq, t);
-            } else {
-                const Cplx<R> *dc = reinterpret_cast<const Cplx<R> *>(sdc);
-                V4<R> t01 = slot ? slot[(size_t)(2 * q) * kTmaThreads] : ld4(Tq), t23 = slot ? slot[(size_t)(2 * q + 1) * kTmaThreads] : ld4(Tq + 4);
-                if (m & 1u) disp_cell_c(dc + ((size_t)i0 * P + q) * 3, eold.x, t01.x, t01.y, ph0);
-                if (m & 2u) disp_cell_c(dc + ((size_t)i1 * P + q) * 3, eold.y, t01.z, t01.w, ph1);
-                if (m & 4u) disp_cell_c(dc + ((size_t)i2 * P + q) * 3, eold.z, t23.x, t23.y, ph2);
-                if (m & 8u) disp_cell_c(dc + ((size_t)i3 * P + q) * 3, eold.w, t23.z, t23.w, ph3);
-                st4(Tq, t01);
-                st4(Tq + 4, t23);
-            }
-        }
-        u.x = disp_sub(u.x, ssrc[i0], ph0);
-        u.y = disp_sub(u.y, ssrc[i1], ph1);
-        u.z = disp_sub(u.z, ssrc[i2], ph2);
-        u.w = disp_sub(u.w, ssrc[i3], ph3);
-    };
-
-    for (int n = 0; n < nl; ++n, ++g) {
-        const unsigned act = act_of(n);
-        if (grouped) {
-            if (pf) {
-                const int np = n + p.pf_depth - 1;   // plane fetched now
-                const unsigned pmn = (p.pf_depth == 2 ? (n + 1 < nl ? act_of(n + 1) : 0u) : act) & smask6;
-                if (pmn) prefetch(spf + (size_t)(np % p.pf_depth) * 2 * PORDER * kTmaThreads + tid, pmn, i_of(np));
-            }
-            if (tpf) {
-                const int np = n + p.t_depth - 1;
-                if (np < nl) tprefetch(stf + (size_t)(np % p.t_depth) * tslot + tid, np);
-            }
-            cp_async_commit();
-        }
-        const int pl = PHASE == 1 ? (l0 + n + 1) : (l1 - 1 - n + 1);
-        const int i = p.x_start + pl - 1;
-        // cooperative z slab: my cell's Phi (both components) straight into registers, before the wait for the plane
-        const bool zact = zcoop && i >= p.slab[zc].lo[0] && i < p.slab[zc].hi[0];   // CTA-uniform
-        R *zphi = nullptr;
-        R zP[2 * PORDER];
-        if (zact && zok) {
-            zphi = p.slab[zc].phi + (long long)(i - p.slab[zc].lo[0]) * p.slab[zc].n1 * p.slab[zc].n2 + zphi_off;
-#pragma unroll
-            for (int q = 0; q < 2 * PORDER; ++q) zP[q] = zphi[q * p.slab[zc].ostride];
-        }
-        const unsigned char *st = stages + (size_t)(g % kStages) * L::bytes;
-        mbar_wait(full + (g % kStages), (uint32_t)((g / kStages) & 1));
-        const R *sOp = reinterpret_cast<const R *>(st + L::oOp);
-        const R *sOwn = reinterpret_cast<const R *>(st + L::oOwn);
-        // E phase: A = Hx (needs j-1, k-1), B = Hy (k-1), C = Hz (j-1) ; H phase: A = Ex (j+1, k+1), B = Ey (k+1), C = Ez (j+1)
-        const V4<R> a_c = ld4(sOp + eo), a_j = ld4(sOp + eoj);
-        const V4<R> b_c = ld4(sOp + L::CS + eo);
-        const V4<R> c_c = ld4(sOp + 2 * L::CS + eo), c_j = ld4(sOp + 2 * L::CS + eoj);
-        R a_k, b_k;
-        if (PHASE == 1) {
-            a_k = __shfl_up_sync(0xffffffffu, a_c.w, 1);
-            b_k = __shfl_up_sync(0xffffffffu, b_c.w, 1);
-            if (c == 0 || lane == 0) {
-                a_k = sOp[eo - 1];
-                b_k = sOp[L::CS + eo - 1];
-            }
-        } else {
-            a_k = __shfl_down_sync(0xffffffffu, a_c.x, 1);
-            b_k = __shfl_down_sync(0xffffffffu, b_c.x, 1);
-            if (c == TZ - 4 || lane == 31) {
-                a_k = sOp[eo + 4];
-                b_k = sOp[L::CS + eo + 4];
-            }
-        }
-        V4<R> f0 = ld4(sOwn + e), f1 = ld4(sOwn + L::OS + e), f2 = ld4(sOwn + 2 * L::OS + e);
-        const unsigned pm = act & smask6;   // slabs on my cells on this plane; 0 for fast threads by construction
-        // A warp without slab cells on this plane has now taken what it needs from the stage and hands it back to the producer.
-        // A warp with slab cells keeps it until its PML corrections are done: they re-read their operands and IDs from the stage
-        // instead of keeping them in registers (which spilled the straight-line update of every thread).
-        // (the IDs are read here, before the release: the stage is refilled as soon as the last warp has arrived)
-        const IdQ<IDT> id0 = IdQ<IDT>::load(st + L::oId, e), id1 = IdQ<IDT>::load(st + L::oId, L::OS + e), id2 = IdQ<IDT>::load(st + L::oId, 2 * L::OS + e);
-        const bool wpml = __any_sync(0xffffffffu, pm != 0u) || zact;
-        if (!wpml) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + (g % kStages));
-            if (!PW && tid == 0 && !p_done) produce();
-        }
-
-        bool w0 = false, w1 = false, w2 = false;
-        if (any) {
-            // one straight-line update for every thread; threads with cells outside an update box (domain faces, the
-            // two x-slab plane ranges) put the old value back per cell afterwards
-            const bool fast = fast_jk && i >= p.fast_i0 && i < p.fast_i1;
-            unsigned m0 = 0xfu, m1 = 0xfu, m2 = 0xfu;
-            if (!fast) {
-                m0 = (i >= p.box[0].lo[0] && i < p.box[0].hi[0]) ? bx.kmask : 0u;
-                m1 = (i >= p.box[1].lo[0] && i < p.box[1].hi[0]) ? by.kmask : 0u;
-                m2 = (i >= p.box[2].lo[0] && i < p.box[2].hi[0]) ? bz.kmask : 0u;
-            }
-            // E phase: backward differences (c - neighbour); H phase: forward (neighbour - c)
-            // E phase: Ex = CA Ex + CBy dHz/dy - CBz dHy/dz ; Ey = CA Ey + CBz dHx/dz - CBx dHz/dx ; Ez = CA Ez + CBx dHy/dx - CBy dHx/dy
-            // H phase: Hx = DA Hx - DBy dEz/dy + DBz dEy/dz ; Hy = DA Hy - DBz dEx/dz + DBx dEz/dx ; Hz = DA Hz - DBx dEy/dx + DBy dEx/dy
-            {
-                V4<R> dC_dy, dB_dz;
-                if (PHASE == 1) {
-                    dB_dz = {b_c.x - b_k, b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z};       // dHy/dz
-                    dC_dy = {c_c.x - c_j.x, c_c.y - c_j.y, c_c.z - c_j.z, c_c.w - c_j.w};     // dHz/dy
-                } else {
-                    dB_dz = {b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z, b_k - b_c.w};       // dEy/dz
-                    dC_dy = {c_j.x - c_c.x, c_j.y - c_c.y, c_j.z - c_c.z, c_j.w - c_c.w};     // dEz/dy
-                }
-                Coef4<R> q0, q1, q2, q3;
-                coef4q(scoef, id0, q0, q1, q2, q3);
-                V4<R> u;
-                if (PHASE == 1) {
-                    u.x = upd3(q0.a, f0.x, q0.by, dC_dy.x, -q0.bz, dB_dz.x);
-                    u.y = upd3(q1.a, f0.y, q1.by, dC_dy.y, -q1.bz, dB_dz.y);
-                    u.z = upd3(q2.a, f0.z, q2.by, dC_dy.z, -q2.bz, dB_dz.z);
-                    u.w = upd3(q3.a, f0.w, q3.by, dC_dy.w, -q3.bz, dB_dz.w);
-                } else {
-                    u.x = upd3(q0.a, f0.x, -q0.by, dC_dy.x, q0.bz, dB_dz.x);
-                    u.y = upd3(q1.a, f0.y, -q1.by, dC_dy.y, q1.bz, dB_dz.y);
-                    u.z = upd3(q2.a, f0.z, -q2.by, dC_dy.z, q2.bz, dB_dz.z);
-                    u.w = upd3(q3.a, f0.w, -q3.by, dC_dy.w, q3.bz, dB_dz.w);
-                }
-                if (DISP) {
-                    if (tpf) { if (p.t_depth == 2) cp_async_wait1(); else cp_async_wait0(); }
-                    disp_apply(0, id0, m0, f0, u, n, pl);
-                }
-                if (!fast) { u.x = sel(m0, 0, u.x, f0.x); u.y = sel(m0, 1, u.y, f0.y); u.z = sel(m0, 2, u.z, f0.z); u.w = sel(m0, 3, u.w, f0.w); }
-                f0 = u;
-            }
-            {
-                V4<R> dA_dz, dC_dx;
-                if (PHASE == 1) {
-                    dA_dz = {a_c.x - a_k, a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z};       // dHx/dz
-                    dC_dx = {c_c.x - qc.x, c_c.y - qc.y, c_c.z - qc.z, c_c.w - qc.w};         // dHz/dx
-                } else {
-                    dA_dz = {a_c.y - a_c.x, a_c.z - a_c.y, a_c.w - a_c.z, a_k - a_c.w};       // dEx/dz
-                    dC_dx = {qc.x - c_c.x, qc.y - c_c.y, qc.z - c_c.z, qc.w - c_c.w};         // dEz/dx
-                }
-                Coef4<R> q0, q1, q2, q3;
-                coef4q(scoef, id1, q0, q1, q2, q3);
-                V4<R> u;
-                if (PHASE == 1) {
-                    u.x = upd3(q0.a, f1.x, q0.bz, dA_dz.x, -q0.bx, dC_dx.x);
-                    u.y = upd3(q1.a, f1.y, q1.bz, dA_dz.y, -q1.bx, dC_dx.y);
-                    u.z = upd3(q2.a, f1.z, q2.bz, dA_dz.z, -q2.bx, dC_dx.z);
-                    u.w = upd3(q3.a, f1.w, q3.bz, dA_dz.w, -q3.bx, dC_dx.w);
-                } else {
-                    u.x = upd3(q0.a, f1.x, -q0.bz, dA_dz.x, q0.bx, dC_dx.x);
-                    u.y = upd3(q1.a, f1.y, -q1.bz, dA_dz.y, q1.bx, dC_dx.y);
-                    u.z = upd3(q2.a, f1.z, -q2.bz, dA_dz.z, q2.bx, dC_dx.z);
-                    u.w = upd3(q3.a, f1.w, -q3.bz, dA_dz.w, q3.bx, dC_dx.w);
-                }
-                if (DISP) disp_apply(1, id1, m1, f1, u, n, pl);
-                if (!fast) { u.x = sel(m1, 0, u.x, f1.x); u.y = sel(m1, 1, u.y, f1.y); u.z = sel(m1, 2, u.z, f1.z); u.w = sel(m1, 3, u.w, f1.w); }
-                f1 = u;
-            }
-            {
-                V4<R> dB_dx, dA_dy;
-                if (PHASE == 1) {
-                    dA_dy = {a_c.x - a_j.x, a_c.y - a_j.y, a_c.z - a_j.z, a_c.w - a_j.w};     // dHx/dy
-                    dB_dx = {b_c.x - qb.x, b_c.y - qb.y, b_c.z - qb.z, b_c.w - qb.w};         // dHy/dx
-                } else {
-                    dA_dy = {a_j.x - a_c.x, a_j.y - a_c.y, a_j.z - a_c.z, a_j.w - a_c.w};     // dEx/dy
-                    dB_dx = {qb.x - b_c.x, qb.y - b_c.y, qb.z - b_c.z, qb.w - b_c.w};         // dEy/dx
-                }
-                Coef4<R> q0, q1, q2, q3;
-                coef4q(scoef, id2, q0, q1, q2, q3);
-                V4<R> u;
-                if (PHASE == 1) {
-                    u.x = upd3(q0.a, f2.x, q0.bx, dB_dx.x, -q0.by, dA_dy.x);
-                    u.y = upd3(q1.a, f2.y, q1.bx, dB_dx.y, -q1.by, dA_dy.y);
-                    u.z = upd3(q2.a, f2.z, q2.bx, dB_dx.z, -q2.by, dA_dy.z);
-                    u.w = upd3(q3.a, f2.w, q3.bx, dB_dx.w, -q3.by, dA_dy.w);
-                } else {
-                    u.x = upd3(q0.a, f2.x, -q0.bx, dB_dx.x, q0.by, dA_dy.x);
-                    u.y = upd3(q1.a, f2.y, -q1.bx, dB_dx.y, q1.by, dA_dy.y);
-                    u.z = upd3(q2.a, f2.z, -q2.bx, dB_dx.z, q2.by, dA_dy.z);
-                    u.w = upd3(q3.a, f2.w, -q3.bx, dB_dx.w, q3.by, dA_dy.w);
-                }
-                if (DISP) disp_apply(2, id2, m2, f2, u, n, pl);
-                if (!fast) { u.x = sel(m2, 0, u.x, f2.x); u.y = sel(m2, 1, u.y, f2.y); u.z = sel(m2, 2, u.z, f2.z); u.w = sel(m2, 3, u.w, f2.w); }
-                f2 = u;
-            }
-            w0 = m0 != 0u; w1 = m1 != 0u; w2 = m2 != 0u;
-        }
-        if (wpml) {   // warp-uniform
-            {
-                const V4<R> *slot = nullptr;
-                if (pf && pm) {
-                    if (p.pf_depth == 2) cp_async_wait1();
-                    else cp_async_wait0();
-                    slot = spf + (size_t)(n % p.pf_depth) * 2 * PORDER * kTmaThreads + tid;
-                }
-                // slabs any lane of this warp has to apply on this plane: x / y slabs in G.pmls order, then the z slabs
-                // (warp-uniform: the cooperative z step needs every lane)
-                const unsigned wtodo = __reduce_or_sync(0xffffffffu, pm) | (zact ? 1u << zs : 0u);
-                for (int zpass = 0; zpass < 2; ++zpass)
-                for (unsigned todo = wtodo & (zpass ? zbits : ~zbits); todo; todo &= todo - 1) {
-                    const int s = __ffs(todo) - 1;
-                    if (zact && s == zs) {
-                        // ---- cooperative z slab: one cell per lane, both components
-                        const SlabDev<R> &sl = p.slab[s];
-                        R corr_a = 0, corr_b = 0;
-                        if (zok) {
-                            const PmlCo<R> co = pml_load_s(PFORM, PORDER, stab + (size_t)s * 4 * PORDER * p.tmax, p.tmax, zdepth);
-                            const int zkk = zk - k0;
-                            const int o = PHASE == 1 ? ((r + 1) * L::PA + zkk + 4) : (r * L::PA + zkk);
-                            R dB, dA;   // d(operand B)/dz for the first component, d(operand A)/dz for the second, as in the quad path
-                            if (PHASE == 1) { dB = sOp[L::CS + o] - sOp[L::CS + o - 1]; dA = sOp[o] - sOp[o - 1]; }
-                            else { dB = sOp[L::CS + o + 1] - sOp[L::CS + o]; dA = sOp[o + 1] - sOp[o]; }
-                            const IDT *sid = reinterpret_cast<const IDT *>(st + L::oId);
-                            const unsigned ida = sid[r * TZ + zkk], idb = sid[L::OS + r * TZ + zkk];
-                            R Pa0 = zP[0], Pb0 = zP[1], Pa1 = PORDER == 2 ? zP[2 * (PORDER - 1)] : Pa0, Pb1 = PORDER == 2 ? zP[2 * (PORDER - 1) + 1] : Pb0;
-                            corr_a = mul_(ssrc[ida], pml_apply(PFORM, PORDER, co, mul_(dB, sl.inv_d), Pa0, Pa1));
-                            corr_b = mul_(ssrc[idb], pml_apply(PFORM, PORDER, co, mul_(dA, sl.inv_d), Pb0, Pb1));
-                            zphi[0] = Pa0;
-                            zphi[sl.ostride] = Pb0;
-                            if (PORDER == 2) { zphi[2 * sl.ostride] = Pa1; zphi[3 * sl.ostride] = Pb1; }
-                        }
-                        // to the owners: cell e of my quad was computed by lane (row base) + (k - zkq0) + e
-                        const int src0 = (lane & ~(LPR - 1)) + (k - zkq0);
-                        const R sa = PHASE == 1 ? (R)-1 : (R)1;   // E: Ex -= , Ey += ; H: Hx += , Hy -=
-                        const R ca0 = __shfl_sync(0xffffffffu, corr_a, src0 & 31), ca1 = __shfl_sync(0xffffffffu, corr_a, (src0 + 1) & 31);
-                        const R ca2 = __shfl_sync(0xffffffffu, corr_a, (src0 + 2) & 31), ca3 = __shfl_sync(0xffffffffu, corr_a, (src0 + 3) & 31);
-                        const R cb0 = __shfl_sync(0xffffffffu, corr_b, src0 & 31), cb1 = __shfl_sync(0xffffffffu, corr_b, (src0 + 1) & 31);
-                        const R cb2 = __shfl_sync(0xffffffffu, corr_b, (src0 + 2) & 31), cb3 = __shfl_sync(0xffffffffu, corr_b, (src0 + 3) & 31);
-                        if (zm & 1u) { f0.x = fma_(sa, ca0, f0.x); f1.x = fma_(-sa, cb0, f1.x); }
-                        if (zm & 2u) { f0.y = fma_(sa, ca1, f0.y); f1.y = fma_(-sa, cb1, f1.y); }
-                        if (zm & 4u) { f0.z = fma_(sa, ca2, f0.z); f1.z = fma_(-sa, cb2, f1.z); }
-                        if (zm & 8u) { f0.w = fma_(sa, ca3, f0.w); f1.w = fma_(-sa, cb3, f1.w); }
-                        if (zm) w0 = w1 = true;
-                        continue;
-                    }
-                    if (!((pm >> s) & 1u)) continue;
-                    const SlabDev<R> &sl = p.slab[s];
-                    const unsigned m = (smask >> (4 * s)) & 0xfu;
-                    const R *tb = stab + (size_t)s * 4 * PORDER * p.tmax;
-                    R *phi = sl.phi + ((long long)(i - sl.lo[0]) * sl.n1 + (j - sl.lo[1])) * sl.n2 + (k - sl.ko);
-                    const V4<R> *slb = slot ? slot + kTmaThreads : nullptr;
-                    // Component / derivative / sign table of SURVEY.md section 8a (identical in all 48 reference kernels):
-                    //   E phase  x: Ey -= dHz/dx, Ez += dHy/dx   y: Ex += dHz/dy, Ez -= dHx/dy   z: Ex -= dHy/dz, Ey += dHx/dz
-                    //   H phase  x: Hy += dEz/dx, Hz -= dEy/dx   y: Hx -= dEz/dy, Hz += dEx/dy   z: Hx += dEy/dz, Hy -= dEx/dz
-                    // The derivatives are formed again from the stage (same operands, same expression as above).
-                    if (sl.axis == 0) {
-                        const int depth = sl.minus ? (sl.dref - i) : (i - sl.dref);
-                        V4<R> dF;
-                        if (PHASE == 1) dF = {c_c.x - qc.x, c_c.y - qc.y, c_c.z - qc.z, c_c.w - qc.w};
-                        else dF = {qc.x - c_c.x, qc.y - c_c.y, qc.z - c_c.z, qc.w - c_c.w};
-                        pml_comp<R, 0>(PFORM, PORDER, tb, p.tmax, depth, 0, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, L::OS + e), ssrc, PHASE == 1 ? (R)-1 : (R)1, dF, f1, phi,
-                                       2 * sl.ostride, slot, 2 * kTmaThreads);
-                        if (PHASE == 1) dF = {b_c.x - qb.x, b_c.y - qb.y, b_c.z - qb.z, b_c.w - qb.w};
-                        else dF = {qb.x - b_c.x, qb.y - b_c.y, qb.z - b_c.z, qb.w - b_c.w};
-                        pml_comp<R, 0>(PFORM, PORDER, tb, p.tmax, depth, 0, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, 2 * L::OS + e), ssrc, PHASE == 1 ? (R)1 : (R)-1, dF, f2,
-                                       phi + sl.ostride, 2 * sl.ostride, slb, 2 * kTmaThreads);
-                        w1 = w2 = true;
-                    } else if (sl.axis == 1) {
-                        const int depth = sl.minus ? (sl.dref - j) : (j - sl.dref);
-                        V4<R> dF;
-                        {
-                            const V4<R> cj = ld4(sOp + 2 * L::CS + eoj);
-                            if (PHASE == 1) dF = {c_c.x - cj.x, c_c.y - cj.y, c_c.z - cj.z, c_c.w - cj.w};
-                            else dF = {cj.x - c_c.x, cj.y - c_c.y, cj.z - c_c.z, cj.w - c_c.w};
-                        }
-                        pml_comp<R, 0>(PFORM, PORDER, tb, p.tmax, depth, 0, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, e), ssrc, PHASE == 1 ? (R)1 : (R)-1, dF, f0, phi,
-                                       2 * sl.ostride, slot, 2 * kTmaThreads);
-                        {
-                            const V4<R> ac = ld4(sOp + eo), aj = ld4(sOp + eoj);
-                            if (PHASE == 1) dF = {ac.x - aj.x, ac.y - aj.y, ac.z - aj.z, ac.w - aj.w};
-                            else dF = {aj.x - ac.x, aj.y - ac.y, aj.z - ac.z, aj.w - ac.w};
-                        }
-                        pml_comp<R, 0>(PFORM, PORDER, tb, p.tmax, depth, 0, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, 2 * L::OS + e), ssrc, PHASE == 1 ? (R)-1 : (R)1, dF, f2,
-                                       phi + sl.ostride, 2 * sl.ostride, slb, 2 * kTmaThreads);
-                        w0 = w2 = true;
-                    } else {
-                        const int depth = sl.minus ? (sl.dref - k) : (k - sl.dref), ds = sl.minus ? -1 : 1;
-                        V4<R> dF;
-                        {
-                            const R bk = sOp[L::CS + eo + (PHASE == 1 ? -1 : 4)];
-                            if (PHASE == 1) dF = {b_c.x - bk, b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z};
-                            else dF = {b_c.y - b_c.x, b_c.z - b_c.y, b_c.w - b_c.z, bk - b_c.w};
-                        }
-                        pml_comp<R, 1>(PFORM, PORDER, tb, p.tmax, depth, ds, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, e), ssrc, PHASE == 1 ? (R)-1 : (R)1, dF, f0, phi,
-                                       2 * sl.ostride, slot, 2 * kTmaThreads);
-                        {
-                            const V4<R> ac = ld4(sOp + eo);
-                            const R ak = sOp[eo + (PHASE == 1 ? -1 : 4)];
-                            if (PHASE == 1) dF = {ac.x - ak, ac.y - ac.x, ac.z - ac.y, ac.w - ac.z};
-                            else dF = {ac.y - ac.x, ac.z - ac.y, ac.w - ac.z, ak - ac.w};
-                        }
-                        pml_comp<R, 1>(PFORM, PORDER, tb, p.tmax, depth, ds, sl.inv_d, m, lds_ids4<IDT>(st + L::oId, L::OS + e), ssrc, PHASE == 1 ? (R)1 : (R)-1, dF, f1,
-                                       phi + sl.ostride, 2 * sl.ostride, slb, 2 * kTmaThreads);
-                        w0 = w1 = true;
-                    }
-                    slot = nullptr;   // only the first slab was prefetched
-                }
-            }
-        }
-        if (any) {
-            const long long off = (long long)pl * p.plane + eoff;
-            if (w0) st4(F0 + off, f0);
-            if (w1) st4(F1 + off, f1);
-            if (w2) st4(F2 + off, f2);
-        }
-        if (wpml) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + (g % kStages));
-            if (!PW && tid == 0 && !p_done) produce();
-        }
-        qb = b_c;
-        qc = c_c;
-    }
-    if (PHASE == 0 && p.progress) {   // this warp's part of the item is in memory: publish (see the E kernel's producer)
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(p.progress + chunkid, 1u);
-    }
+#include "gpb_tma_item.inc"
     }   // items
 
     // the last CTA to finish re-arms the scheduler for the next launch

@@ -40,4 +40,18 @@ struct TmaLaunch {
 template <typename R, int PV>
 int tma_launch(const TmaLaunch<R> &a, std::string *err);
 
+// Both half-steps of one iteration in one launch (gpb_kernels_pair.cuh): default 14 x 64 tile with the producer warp only.
+template <typename R>
+struct TmaLaunchPair {
+    PhaseParams<R> ph, pe;    // magnetic / electric phase parameters (p0/p1/xchunk/fast_i*/zfused/znocoop/progress set by the caller)
+    const TmaMaps4 *maps_h, *maps_e;
+    int idbytes, pf_max, t_max;
+    int disp;                 // 0 none, 1 complex T, 2 real T
+    int sm_count;
+    int *sched;
+    cudaStream_t stream;
+};
+template <typename R, int PV>
+int tma_launch_pair(const TmaLaunchPair<R> &a, std::string *err);
+
 }  // namespace gpb

@@ -5,7 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "gpb_kernels_tma.cuh"
+#include "gpb_kernels_pair.cuh"
 
 #ifndef GPB_TMA_R
 #define GPB_TMA_R float
@@ -115,6 +115,74 @@ int tma_launch(const TmaLaunch<R> &a, std::string *err)
     return tma_launch_idt<R, PV, uint32_t>(a, err);
 }
 
+template <typename R, int PV, typename IDT, int DISP>
+static int tma_launch_pair_cfg(const TmaLaunchPair<R> &a, std::string *err)
+{
+    constexpr int TY = 14, TZ = 64, S = 3;
+    using L = StageLayout<R, IDT, TY, TZ>;
+    constexpr int order = (PV & 1) + 1;
+    constexpr int threads = TY * TZ / 4;
+    PhaseParams<R> ph = a.ph, pe = a.pe;
+    const int tiles_k = (ph.pitch + TZ - 1) / TZ, tiles_j = (ph.ny + 1 + TY - 1) / TY;
+    ph.tmax = pe.tmax = 1;
+    for (int s = 0; s < ph.nslabs; ++s) ph.tmax = std::max(ph.tmax, ph.slab[s].t);
+    for (int s = 0; s < pe.nslabs; ++s) pe.tmax = std::max(pe.tmax, pe.slab[s].t);
+    auto a128 = [](size_t x) { return (x + 127) / 128 * 128; };
+    const size_t fixed = 128 + 2 * a128(ph.nmat * (sizeof(Coef4<R>) + sizeof(R))) + a128(ph.nslabs * 4 * order * ph.tmax * sizeof(R)) +
+                         a128(pe.nslabs * 4 * order * pe.tmax * sizeof(R)) + (size_t)S * L::bytes;
+    const size_t pf_unit = (size_t)2 * order * threads * 4 * sizeof(R);
+    const size_t smem_cap = (sizeof(R) == 4 ? (size_t)(227 * 1024) / GPB_TMA_CTAS : (size_t)227 * 1024) - 1024;
+    size_t disp_fixed = 0, t_unit = 0;
+    ph.t_depth = pe.t_depth = 0;
+    if (DISP) {
+        const int tw = DISP == 1 ? 2 : 1;
+        disp_fixed = a128(pe.nmat * pe.maxpoles * 3 * tw * sizeof(R));
+        t_unit = (size_t)3 * pe.maxpoles * tw * threads * 4 * sizeof(R);
+        if (fixed + disp_fixed > smem_cap) {
+            if (err) *err = "dispersive coefficient table does not fit the shared memory of the TMA kernels";
+            return 1;
+        }
+        pe.t_depth = fixed + disp_fixed + 2 * t_unit <= smem_cap ? 2 : (fixed + disp_fixed + t_unit <= smem_cap ? 1 : 0);
+        pe.t_depth = std::min(pe.t_depth, a.t_max);
+    }
+    const size_t fixed2 = fixed + disp_fixed + pe.t_depth * t_unit;
+    const int nslabs = std::max(ph.nslabs, pe.nslabs);
+    int pfd = nslabs == 0 ? 0 : (fixed2 + 2 * pf_unit <= smem_cap ? 2 : (fixed2 + pf_unit <= smem_cap ? 1 : 0));
+    pfd = std::min(pfd, a.pf_max);
+    ph.pf_depth = ph.nslabs ? pfd : 0;
+    pe.pf_depth = pe.nslabs ? pfd : 0;
+    const size_t smem = fixed2 + pfd * pf_unit;
+    const int tiles = tiles_k * tiles_j, nchunks = (ph.p1 - ph.p0 + ph.xchunk - 1) / ph.xchunk;
+    ph.monotone = pe.monotone = 1;
+    ph.persist = pe.persist = 1;
+    ph.prog_need = pe.prog_need = (unsigned)(tiles * (threads / 32));
+    const int resident = (sizeof(R) == 4 ? GPB_TMA_CTAS : 1) * a.sm_count;
+    const long long W = 2ll * nchunks * tiles;
+    const dim3 grid((unsigned)std::min<long long>(W, resident));
+    auto kern = k_update_pair<R, IDT, TY, TZ, S, PV, DISP>;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return tma_fail(err, "cudaFuncSetAttribute", e);
+    kern<<<grid, threads + 32, smem, a.stream>>>(ph, pe, *a.maps_h, *a.maps_e, tiles_k, tiles, nchunks, a.sched);
+    if ((e = cudaGetLastError()) != cudaSuccess) return tma_fail(err, "k_update_pair launch", e);
+    return 0;
+}
+
+template <typename R, int PV>
+int tma_launch_pair(const TmaLaunchPair<R> &a, std::string *err)
+{
+#define GPB_PAIR_IDT(IDT)                                                      \
+    do {                                                                       \
+        if (a.disp == 0) return tma_launch_pair_cfg<R, PV, IDT, 0>(a, err);    \
+        if (a.disp == 1) return tma_launch_pair_cfg<R, PV, IDT, 1>(a, err);    \
+        return tma_launch_pair_cfg<R, PV, IDT, 2>(a, err);                     \
+    } while (0)
+    if (a.idbytes == 1) GPB_PAIR_IDT(uint8_t);
+    if (a.idbytes == 2) GPB_PAIR_IDT(uint16_t);
+    GPB_PAIR_IDT(uint32_t);
+#undef GPB_PAIR_IDT
+}
+
 template int tma_launch<GPB_TMA_R, GPB_TMA_PV>(const TmaLaunch<GPB_TMA_R> &, std::string *);
+template int tma_launch_pair<GPB_TMA_R, GPB_TMA_PV>(const TmaLaunchPair<GPB_TMA_R> &, std::string *);
 
 }  // namespace gpb
