@@ -340,7 +340,7 @@ struct Solver : SolverBase {
     // H and E half-steps of an iteration in ONE launch (gpb_kernels_pair.cuh): items of both phases from one queue, the E items
     // of a chunk about two chunks behind its H items, so E finds its operands in L2
     bool pair_he = false;
-    int pair_xchunk = 4;
+    int pair_xchunk = 4, pair_lag = 1;
     unsigned *d_progress = nullptr;   // [chunks + 1]: finished H warps per chunk, [chunks] = time-out flag
     int n_he_chunks = 0;
     int launch_pair();
@@ -947,13 +947,17 @@ int Solver<R>::build(const gpb_model_t &m)
                (size_t)nmat * maxpoles * 3 * (treal ? 1 : 2) * sizeof(R) <= 24 * 1024;
     tma_tpf = getenv("GPB_TMA_TPF") ? std::max(0, atoi(getenv("GPB_TMA_TPF"))) : 2;
     xblock = getenv("GPB_XBLOCK") ? atoi(getenv("GPB_XBLOCK")) : 0;
-    // both half-steps in one launch: default tile with the producer warp, whole-domain handle (a shard's halo protocol orders
-    // the half-steps itself), E half-step on the TMA kernels; models with something that acts on H between the two half-steps
-    // (magnetic dipoles, transmission lines) keep the two launches (checked per step: has_hsrc)
+    // both half-steps in one launch (opt-in, GPB_PAIR=1): default tile with the producer warp, whole-domain handle (a shard's halo
+    // protocol orders the half-steps itself), E half-step on the TMA kernels; models with something that acts on H between the two
+    // half-steps (magnetic dipoles, transmission lines) keep the two launches (checked per step: has_hsrc).
+    // Measured at 300^3 (profiles/README.md, r2 pair): DRAM traffic per iteration 2.36 -> 1.68 GB (E finds its operands in L2),
+    // but 0.51 - 0.66 ms per iteration against 0.43 ms for two launches: the E items wait for H items that are still in flight
+    // (close coupling) or lose the L2 reuse (loose coupling) -- 296 resident CTAs hold about as much data in flight as L2 keeps.
     pair_he = use_tma && tma_ty == 14 && tma_tz == 64 && tma_stages == 3 && tma_pw == 1 && tma_persist && nplanes == nx + 1 &&
-              (!maxpoles || tma_disp) && !getenv("GPB_NO_PAIR");
+              (!maxpoles || tma_disp) && getenv("GPB_PAIR") && !getenv("GPB_NO_PAIR");
     if (pair_he) {
         pair_xchunk = getenv("GPB_PAIR_XCHUNK") ? std::max(1, atoi(getenv("GPB_PAIR_XCHUNK"))) : 4;
+        pair_lag = getenv("GPB_PAIR_LAG") ? std::max(0, atoi(getenv("GPB_PAIR_LAG"))) : 1;
         n_he_chunks = (nplanes + pair_xchunk - 1) / pair_xchunk;
         if (n_he_chunks >= (1 << 11)) pair_he = false;
     }
@@ -1284,6 +1288,7 @@ int Solver<R>::launch_pair()
         p.zfused = 1;
         p.znocoop = tma_znocoop ? 1 : 0;
         p.progress = d_progress;
+        p.pair_lag = pair_lag;
         p.prog_flags = d_progress + n_he_chunks;
         p.prog_timeout_ns = 5000000000ull;
     }

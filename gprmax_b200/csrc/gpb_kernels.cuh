@@ -103,6 +103,7 @@ struct PhaseParams {
     // in increasing x; the H kernel counts finished (tile, chunk) items per chunk in progress[], the E kernel's producer loads a
     // chunk only when the H items of that chunk and of the one before it are complete -- so E reads H (and re-reads E) out of L2
     int monotone;
+    int pair_lag;             // k_update_pair: the E items of chunk c follow the H items of chunk c + pair_lag in the queue
     unsigned *progress;       // [nchunks] finished H warps per chunk (null: kernels run one after the other)
     unsigned prog_need;       // tiles * consumer warps
     unsigned *prog_flags;     // [0] |= 1 when a wait timed out

@@ -5,7 +5,7 @@
 // operands.  Here the persistent CTAs of k_update_tma pull work items of BOTH half-steps from one queue, ordered so that the E
 // items of an x chunk follow the H items of the chunk behind it by about two chunks of planes:
 //
-//      H(0)  H(1)  E(0)  H(2)  E(1)  H(3)  E(2)  ...  H(C-1)  E(C-2)  E(C-1)          (each group = all tiles of one chunk)
+//      H(0) .. H(L)  E(0)  H(L+1)  E(1)  H(L+2)  E(2)  ...  H(C-1)  E(C-1-L) .. E(C-1)     (each group = all tiles of one chunk)
 //
 // so an E item finds its H operands and its own E planes in the 126 MB L2 (written / read a few tens of MB ago).  It is valid
 // because E(i) needs H(i-1), H(i), and the H update of later chunks only reads E planes the E update of this chunk does not
@@ -22,13 +22,20 @@
 
 namespace gpb {
 
-// group g of the unified queue -> (phase, chunk); C = number of x chunks, 2 C groups
-__device__ __forceinline__ void pair_group(int g, int C, int &phase, int &chunk)
+// group g of the unified queue -> (phase, chunk); C = number of x chunks (2 C groups), L = lag: E(c) directly follows H(c + L)
+//      H(0) .. H(L)  E(0)  H(L+1)  E(1)  ...  H(C-1)  E(C-1-L)  E(C-L) .. E(C-1)
+__device__ __forceinline__ void pair_group(int g, int C, int L, int &phase, int &chunk)
 {
-    if (g == 0) { phase = 0; chunk = 0; }
-    else if (g == 2 * C - 1) { phase = 1; chunk = C - 1; }
-    else if (g & 1) { phase = 0; chunk = (g + 1) >> 1; }
-    else { phase = 1; chunk = (g >> 1) - 1; }
+    L = min(L, C - 1);
+    if (g <= L) { phase = 0; chunk = g; return; }
+    const int t = g - (L + 1), rem = C - 1 - L;
+    if (t < 2 * rem) {
+        phase = (t & 1) ? 0 : 1;
+        chunk = (t & 1) ? L + 1 + (t >> 1) : (t >> 1);
+    } else {
+        phase = 1;
+        chunk = rem + (t - 2 * rem);
+    }
 }
 
 template <typename R, typename IDT, int TY, int TZ, int kStages, int PV, int DISP>
@@ -114,7 +121,7 @@ k_update_pair(const __grid_constant__ PhaseParams<R> ph, const __grid_constant__
         p_item = -1;
         if (w < W) {
             int chunk;
-            pair_group(w / tiles, nchunks, p_phase, chunk);
+            pair_group(w / tiles, nchunks, ph.pair_lag, p_phase, chunk);
             const int tile = w % tiles;
             p_item = tile | (p_phase << 19) | (chunk << 20);
             p_k0 = (tile % tiles_k) * TZ;

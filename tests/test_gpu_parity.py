@@ -161,7 +161,7 @@ TMA_FIXTURES = ['pml_HORIPML_1', 'pml_HORIPML_2', 'pml_MRIPML_1', 'pml_MRIPML_2'
 
 
 @pytest.mark.parametrize('name', TMA_FIXTURES)
-@pytest.mark.parametrize('mode', ['tma', 'tma_nopair', 'tma_nopersist', 'tma_pw0', 'tma_tile8x128', 'tma_zsplit', 'tma_znocoop', 'tma_ids16', 'tma_ids32', 'v4_ids16', 'scalar',
+@pytest.mark.parametrize('mode', ['tma', 'tma_pair', 'tma_nopersist', 'tma_pw0', 'tma_tile8x128', 'tma_zsplit', 'tma_znocoop', 'tma_ids16', 'tma_ids32', 'v4_ids16', 'scalar',
                                   'tma_tpf1', 'tma_tpf0', 'tma_disp_v4', 'tma_disp_complex', 'v4_disp_complex'])
 def test_f64_every_kernel_path(name, mode, monkeypatch):
     """The small fixtures normally run on the register-vectorised kernels (the TMA kernels are only selected above
@@ -171,8 +171,8 @@ def test_f64_every_kernel_path(name, mode, monkeypatch):
     from gprmax_b200.model_io import load_model
     if mode.startswith('tma'):
         monkeypatch.setenv('GPB_FORCE_TMA', '1')
-    if mode == 'tma_nopair':
-        monkeypatch.setenv('GPB_NO_PAIR', '1')
+    if mode == 'tma_pair':
+        monkeypatch.setenv('GPB_PAIR', '1')
     if mode == 'tma_nopersist':
         monkeypatch.setenv('GPB_TMA_NOPERSIST', '1')
     if mode == 'tma_pw0':
@@ -231,7 +231,7 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
     G.ID = rng.integers(2, G.updatecoeffsE.shape[0], size=G.ID.shape, dtype=np.uint32)
 
     def run(env):
-        for k in ('GPB_NO_TMA', 'GPB_TMA_NOPERSIST', 'GPB_TMA_PW', 'GPB_TMA_ZSPLIT', 'GPB_TMA_ZNOCOOP', 'GPB_NO_PAIR'):
+        for k in ('GPB_NO_TMA', 'GPB_TMA_NOPERSIST', 'GPB_TMA_PW', 'GPB_TMA_ZSPLIT', 'GPB_TMA_ZNOCOOP', 'GPB_PAIR'):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -244,8 +244,8 @@ def test_kernel_families_bit_identical_on_heterogeneous_grid(monkeypatch):
     # the field has reached the x0 / ymax / z0 corner region of the PML (all three slabs overlap there)
     for c in range(6):
         assert np.abs(ref[c][1:9, ny - 9:ny - 1, 1:9]).max() > 0, c
-    # {} = the default: both half-steps of an iteration in one launch (k_update_pair); GPB_NO_PAIR: two launches
-    for env in ({}, {}, {'GPB_NO_PAIR': '1'}, {'GPB_TMA_NOPERSIST': '1'}, {'GPB_TMA_PW': '0'}, {'GPB_TMA_ZSPLIT': '1'}, {'GPB_TMA_ZNOCOOP': '1'}):
+    # GPB_PAIR: both half-steps of an iteration in one launch (k_update_pair)
+    for env in ({}, {}, {'GPB_PAIR': '1'}, {'GPB_TMA_NOPERSIST': '1'}, {'GPB_TMA_PW': '0'}, {'GPB_TMA_ZSPLIT': '1'}, {'GPB_TMA_ZNOCOOP': '1'}):
         out = run(env)
         for c, (a, b) in enumerate(zip(out, ref)):
             assert np.array_equal(a, b), (env, c, int((a != b).sum()))
@@ -283,7 +283,7 @@ def test_dispersive_families_and_real_T_bit_identical(monkeypatch):
 
 @pytest.mark.parametrize('name', ['pml_HORIPML_2', 'pml_MRIPML_1', 'hertzian_dipole_dispersive', 'heterogeneous_soil_small', 'bench_100', 'snapshots', 'sources_mixed'])
 def test_pair_kernel_bit_identical(name, monkeypatch):
-    """TMA kernels: by default both half-steps of an iteration run in ONE launch (k_update_pair: H and E work items from one
+    """TMA kernels, opt-in GPB_PAIR=1: both half-steps of an iteration run in ONE launch (k_update_pair: H and E work items from one
     queue, an E item loaded only after the H items it depends on were published through per-chunk progress counters, so that
     E finds its operands in L2).  Same bits as one launch per half-step and as the register-vectorised kernels, three runs in a
     row (a missed dependency would show as run-to-run jitter)."""
@@ -302,12 +302,12 @@ def test_pair_kernel_bit_identical(name, monkeypatch):
             return path, [sv.get_field(c) for c in range(6)] + [sv.receivers()]
 
     _, ref = run({'GPB_NO_TMA': '1'})
-    pseq, seq = run({'GPB_FORCE_TMA': '1', 'GPB_NO_PAIR': '1'})
-    assert 'k_update_tma' in pseq and 'concurrent' not in pseq
+    pseq, seq = run({'GPB_FORCE_TMA': '1'})
+    assert 'k_update_tma' in pseq and 'k_update_pair' not in pseq
     for rep in range(3):
         pcon, con = run({'GPB_FORCE_TMA': '1'})
         if name != 'sources_mixed':   # a magnetic dipole acts between the half-steps: those models keep the kernels in sequence
-            assert 'concurrent' in pcon, pcon
+            assert 'k_update_pair' in pcon, pcon
         for c, (a, b, d) in enumerate(zip(con, seq, ref)):
             assert np.array_equal(a, b) and np.array_equal(a, d), (name, rep, c)
 
