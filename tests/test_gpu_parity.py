@@ -292,7 +292,7 @@ def test_pair_kernel_bit_identical(name, monkeypatch):
     G, _ = load_model(golden_path(name, 'f32'))
 
     def run(env):
-        for k in ('GPB_FORCE_TMA', 'GPB_NO_TMA', 'GPB_NO_PAIR'):
+        for k in ('GPB_FORCE_TMA', 'GPB_NO_TMA', 'GPB_PAIR', 'GPB_PAIR_XCHUNK', 'GPB_PAIR_LAG'):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -305,8 +305,9 @@ def test_pair_kernel_bit_identical(name, monkeypatch):
     pseq, seq = run({'GPB_FORCE_TMA': '1'})
     assert 'k_update_tma' in pseq and 'k_update_pair' not in pseq
     for rep in range(3):
-        pcon, con = run({'GPB_FORCE_TMA': '1'})
-        if name != 'sources_mixed':   # a magnetic dipole acts between the half-steps: those models keep the kernels in sequence
+        pcon, con = run({'GPB_FORCE_TMA': '1', 'GPB_PAIR': '1', 'GPB_PAIR_XCHUNK': ('4', '2', '8')[rep], 'GPB_PAIR_LAG': ('1', '0', '3')[rep]})
+        # (a magnetic dipole acts between the half-steps, other tile shapes have no pair kernel: those keep two launches)
+        if name not in ('sources_mixed', 'heterogeneous_soil_small'):
             assert 'k_update_pair' in pcon, pcon
         for c, (a, b, d) in enumerate(zip(con, seq, ref)):
             assert np.array_equal(a, b) and np.array_equal(a, d), (name, rep, c)
