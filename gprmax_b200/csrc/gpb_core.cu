@@ -7,6 +7,7 @@
 #include "../../include/gprmax_b200.h"
 #include "gpb_kernels.cuh"
 #include "gpb_kernels_v4.cuh"
+#include "gpb_kernels_coop.cuh"
 #include "gpb_tma.h"
 
 #include <algorithm>
@@ -357,6 +358,13 @@ struct Solver : SolverBase {
     Cplx<R> *dcoef = 0;          // treal: R[nmat][maxpoles][3]
     bool treal = false;          // all dispersive coefficients real (Debye media): real-valued T
     int xblock = 0;              // > 0: planes per block of the x-blocked H/E launch order (GPB_XBLOCK)
+    // small grids: n iterations in ONE cooperative launch (gpb_kernels_coop.cuh)
+    bool coop = false;
+    int coop_grid = 0, coop_xchunk = 1, coop_gx = 0, coop_gy = 0;
+    size_t coop_smem = 0;
+    const void *coop_kernel() const;
+    int setup_coop();
+    int launch_coop(int n);
     bool tma_disp = false;       // dispersive E half-step on the TMA kernels
     int tma_tpf = 2;
     int *d_iter = 0;  // [0] current, [1] next
@@ -391,8 +399,6 @@ struct Solver : SolverBase {
     Peer left, right;
     bool linked = false;
     unsigned *d_flags = nullptr;   // [GPB_NFLAGS] written by the neighbours (peer stores) and by this shard's own kernels
-    cudaStream_t stream2 = nullptr;   // halo pushes run beside the interior update
-    cudaEvent_t evl[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long link_timeout_ns = 20000000000ull;
     bool snap_needs_right = false;
     bool snap_unlinked_ok = true;    // every snapshot cell of this slab averages planes of this slab only
@@ -417,9 +423,6 @@ struct Solver : SolverBase {
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamSynchronize(stream);   // cached blocks are handed to the next solver, which runs on another stream
         unlink();
-        for (auto &e : evl)
-            if (e) cudaEventDestroy(e);
-        if (stream2) cudaStreamDestroy(stream2);
         if (d_flags) cudaFree(d_flags);
         for (void *p : allocs) g_pool.free(p);
         if (stream) cudaStreamDestroy(stream);
@@ -970,6 +973,8 @@ int Solver<R>::build(const gpb_model_t &m)
             if (ph_h.slab[s].axis == 2) zslabs_h |= 1u << s;
     }
 
+    if (setup_coop()) return 1;
+
     memset(&pp, 0, sizeof pp);
     pp.x_start = x_start; pp.nplanes = nplanes; pp.ny = ny; pp.nz = nz; pp.pitch = pitch; pp.plane = plane;
     for (int c = 0; c < 6; ++c) { pp.F[c] = F[c]; pp.ID[c] = ID[c]; }
@@ -1311,7 +1316,7 @@ int Solver<R>::launch_pair()
 }
 
 // One iteration of a LINKED shard (gpb_link): same kernels on the same operands as enqueue_step, boundary plane first, with the
-// halo planes pushed into the neighbours' ghost planes by k_halo_push on a second stream while the interior runs, and
+// halo planes pushed into the neighbours' ghost planes by k_halo_push between the boundary and the interior launch, and
 // one-thread flag waits where a phase needs the neighbour's plane.  Flag protocol (values = iteration + 1, monotonic):
 //   my H_READY  <- left neighbour:  its Hy,Hz of this iteration are in my ghost plane x_start-1     (before my E half-step)
 //   my E_READY  <- right neighbour: its Ey,Ez of the previous iteration are in my ghost plane x_end (before my H half-step)
@@ -1337,19 +1342,19 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
         if (right.present) { k_flag_signal<<<1, 1, 0, stream>>>(right.flags + GPB_FLAG_SNAP_DONE, it, 1); ++launches; }
         if (left.present) { k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_SNAP_DONE, it, 1, d_flags, GPB_FLAG_SNAP_DONE, link_timeout_ns); ++launches; }
     }
-    // ---- H half-step: last owned plane first (its Hy,Hz feed the right neighbour)
+    // ---- H half-step: last owned plane first (its Hy,Hz feed the right neighbour).  The push runs IN the stream, before the
+    // interior kernel: the persistent interior kernel fills every SM (2 CTAs x 256 threads x 128 registers = the whole
+    // register file), so a push on a second stream only got SM slots when the interior was over and the neighbour stalled on
+    // the halo (4 GPUs: 282 k instead of 293 k Mcells/s).  In the stream it costs ~30 us of a 3.7 ms half-step.
     if (right.present) {
         k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_E_READY, it, 0, d_flags, GPB_FLAG_E_READY, link_timeout_ns);
         ++launches;
         if (launch_phase(0, n - 1, n) || launch_sources(0, n - 1, n, 0, 0)) return 1;
-        CK(cudaEventRecord(evl[0], stream));
-        CK(cudaStreamWaitEvent(stream2, evl[0], 0));
-        k_flag_wait<<<1, 1, 0, stream2>>>(d_flags + GPB_FLAG_H_FREE, it, 0, d_flags, GPB_FLAG_H_FREE, link_timeout_ns);
-        k_halo_push<R><<<64, 256, 0, stream2>>>(F[4] + plane * n, F[5] + plane * n, right.F + 4 * right.narr, right.F + 5 * right.narr, plane,
-                                                right.flags + GPB_FLAG_H_READY, it, 1, d_flags + GPB_FLAG_PUSH_COUNT);
+        k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_H_FREE, it, 0, d_flags, GPB_FLAG_H_FREE, link_timeout_ns);
+        k_halo_push<R><<<128, 256, 0, stream>>>(F[4] + plane * n, F[5] + plane * n, right.F + 4 * right.narr, right.F + 5 * right.narr, plane,
+                                                 right.flags + GPB_FLAG_H_READY, it, 1, d_flags + GPB_FLAG_PUSH_COUNT);
         CK(cudaGetLastError());
         launches += 2;
-        CK(cudaEventRecord(evl[1], stream2));
         if (launch_phase(0, 0, n - 1) || launch_sources(0, 0, n - 1, 0, 0)) return 1;
     } else {
         if (launch_phase(0, 0, n) || launch_sources(0, 0, n, 0, 0)) return 1;
@@ -1363,21 +1368,15 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
     if (ntl && launch_sources(0, 0, 0, 0, n)) return 1;
     if (left.present) {
         if (launch_phase(1, 0, 1) || launch_sources(1, 0, 1, 0, 1)) return 1;
-        CK(cudaEventRecord(evl[2], stream));
-        CK(cudaStreamWaitEvent(stream2, evl[2], 0));
-        k_halo_push<R><<<64, 256, 0, stream2>>>(F[1] + plane, F[2] + plane, left.F + 1 * left.narr + plane * (left.nplanes + 1),
-                                                left.F + 2 * left.narr + plane * (left.nplanes + 1), plane, left.flags + GPB_FLAG_E_READY, it, 1,
-                                                d_flags + GPB_FLAG_PUSH_COUNT + 1);
+        k_halo_push<R><<<128, 256, 0, stream>>>(F[1] + plane, F[2] + plane, left.F + 1 * left.narr + plane * (left.nplanes + 1),
+                                                 left.F + 2 * left.narr + plane * (left.nplanes + 1), plane, left.flags + GPB_FLAG_E_READY, it, 1,
+                                                 d_flags + GPB_FLAG_PUSH_COUNT + 1);
         CK(cudaGetLastError());
         ++launches;
-        CK(cudaEventRecord(evl[3], stream2));
         if (launch_phase(1, 1, n) || launch_sources(1, 1, n, 1, n)) return 1;
     } else {
         if (launch_phase(1, 0, n) || launch_sources(1, 0, n, 0, n)) return 1;
     }
-    // join: the next iteration may change the planes the pushes read
-    if (right.present) CK(cudaStreamWaitEvent(stream, evl[1], 0));
-    if (left.present) CK(cudaStreamWaitEvent(stream, evl[3], 0));
     CK(cudaGetLastError());
     return 0;
 }
@@ -1421,7 +1420,6 @@ int Solver<R>::unlink()
     if (!linked) return 0;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    if (stream2) cudaStreamSynchronize(stream2);
     for (Peer *p : {&left, &right}) {
         if (p->ipc_F) g_ipc.release(p->ipc_F);
         if (p->ipc_flags) g_ipc.release(p->ipc_flags);
@@ -1440,9 +1438,6 @@ int Solver<R>::link(const gpb_link_t *l, const gpb_link_t *r)
     unlink();
     if (!l && !r) return 0;
     if (const char *e = getenv("GPB_LINK_TIMEOUT_MS")) link_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
-    if (!stream2) CK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
-    for (auto &e : evl)
-        if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const uint64_t me = (uint64_t)getpid();
     for (int side = 0; side < 2; ++side) {
         const gpb_link_t *q = side == 0 ? l : r;
@@ -1521,6 +1516,65 @@ int Solver<R>::set_smem_attributes()
 }
 
 template <typename R>
+const void *Solver<R>::coop_kernel() const
+{
+    if (idbytes == 1) return maxpoles ? (const void *)k_run_coop<R, uint8_t, true> : (const void *)k_run_coop<R, uint8_t, false>;
+    if (idbytes == 2) return maxpoles ? (const void *)k_run_coop<R, uint16_t, true> : (const void *)k_run_coop<R, uint16_t, false>;
+    return maxpoles ? (const void *)k_run_coop<R, uint32_t, true> : (const void *)k_run_coop<R, uint32_t, false>;
+}
+
+// Grids that are launch-bound on the kernel-per-half-step path (everything the register-vectorised kernels serve: 2-D models
+// and 3-D grids below the TMA threshold) run n iterations in one cooperative launch, provided the whole domain is on this
+// handle (a shard's half-steps are ordered by the halo protocol) and the device can keep enough CTAs resident.
+template <typename R>
+int Solver<R>::setup_coop()
+{
+    coop = false;
+    if (!use_v4 || use_tma || nplanes != nx + 1 || getenv("GPB_NO_COOP")) return 0;
+    int can = 0;
+    CK(cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, device));
+    if (!can) return 0;
+    coop_smem = (size_t)nmat * 2 * (sizeof(Coef4<R>) + sizeof(R));
+    if (coop_smem > 96 * 1024) return 0;
+    const void *kern = coop_kernel();
+    if (coop_smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreadsV4, coop_smem));
+    CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (per_sm < 1) return 0;
+    coop_gx = (int)((plane / 4 + kThreadsV4 - 1) / kThreadsV4);
+    const int resident = per_sm * sm_count;
+    // planes per item: as long as possible (the x-neighbour plane rides in registers) while every resident CTA still gets a
+    // few items per half-step
+    coop_xchunk = 16;
+    while (coop_xchunk > 1 && (long long)coop_gx * ((nplanes + coop_xchunk - 1) / coop_xchunk) < 3ll * resident) coop_xchunk /= 2;
+    if (getenv("GPB_COOP_XCHUNK")) coop_xchunk = std::max(1, atoi(getenv("GPB_COOP_XCHUNK")));
+    coop_gy = (nplanes + coop_xchunk - 1) / coop_xchunk;
+    coop_grid = (int)std::min<long long>((long long)coop_gx * coop_gy, resident);
+    coop = true;
+    return 0;
+}
+
+template <typename R>
+int Solver<R>::launch_coop(int n)
+{
+    CoopParams<R> cp;
+    cp.ph = ph_h; cp.pe = ph_e;
+    for (PhaseParams<R> *p : {&cp.ph, &cp.pe}) { p->p0 = 0; p->p1 = nplanes; p->xchunk = coop_xchunk; }
+    cp.pp = pp;
+    cp.nrx = nrx; cp.rxc = d_rxc; cp.rxs = d_rxs;
+    cp.nsrc = nsrc; cp.srcs = d_srcs;
+    cp.zs_h = zslabs_h; cp.zs_e = zslabs_e;
+    cp.gx = coop_gx; cp.gy = coop_gy;
+    cp.it0 = iteration; cp.n_iters = n;
+    cp.d_iter = d_iter;
+    void *args[] = {&cp};
+    CK(cudaLaunchCooperativeKernel(coop_kernel(), dim3((unsigned)coop_grid), dim3(kThreadsV4), args, coop_smem, stream));
+    ++launches;
+    return 0;
+}
+
+template <typename R>
 int Solver<R>::run(int n)
 {
     if (begin_run(n) || enqueue_iterations(n) || end_run()) return 1;
@@ -1533,7 +1587,7 @@ int Solver<R>::begin_run(int n)
 {
     CK(cudaSetDevice(device));
     if (n < 0 || iteration + n > iterations) return fail("cannot run %d iterations from %d: model has %d", n, iteration, iterations);
-    if (use_graph && !graph && n > 1) {
+    if (use_graph && !graph && n > 1 && !(coop && !ntl && !linked)) {
         // the step is identical every iteration (the iteration index lives on the device), so it is
         // captured once and replayed: one graph launch per time step instead of 4-6 kernel launches
         cudaGraph_t g = nullptr;
@@ -1556,6 +1610,24 @@ template <typename R>
 int Solver<R>::enqueue_iterations(int n)
 {
     CK(cudaSetDevice(device));
+    if (coop && !ntl && !linked) {
+        // cooperative whole-run kernel, split around the iterations that take a snapshot (those run as a plain step)
+        while (n > 0) {
+            if (snapshot_due(iteration)) {
+                if (enqueue_step(true)) return 1;
+                ++iteration;
+                --n;
+                continue;
+            }
+            int k = n;
+            for (auto &sn : snaps)
+                if (sn.time - 1 > iteration) k = std::min(k, sn.time - 1 - iteration);
+            if (launch_coop(k)) return 1;
+            iteration += k;
+            n -= k;
+        }
+        return 0;
+    }
     for (int s = 0; s < n; ++s) {
         if (graph && !snapshot_due(iteration)) {
             CK(cudaGraphLaunch(graph, stream));
@@ -1597,6 +1669,8 @@ int Solver<R>::finish_run()
 template <typename R>
 std::string Solver<R>::kernel_path() const
 {
+    if (coop && !ntl && !linked)
+        return std::string("H+E:k_run_coop (whole run in one cooperative launch; ") + (maxpoles ? (treal ? "h4_body / e4_body<DISP=real>" : "h4_body / e4_body<DISP=complex>") : "h4_body / e4_body") + ")";
     auto name = [&](int phase) -> std::string {
         const char *dn = treal ? "DISP=real" : "DISP=complex";
         if (use_tma && !(phase == 1 && maxpoles && !tma_disp)) {

@@ -29,6 +29,16 @@ namespace gpb {
 constexpr int kThreadsV4 = GPB_V4_THREADS;
 constexpr int kV4Unroll = GPB_V4_UNROLL;
 
+// T * or T *__restrict__
+template <bool RESTRICT, typename T>
+struct MaybeRestrict {
+    typedef T *type;
+};
+template <typename T>
+struct MaybeRestrict<true, T> {
+    typedef T *__restrict__ type;
+};
+
 template <typename R>
 struct alignas(4 * sizeof(R)) V4 {
     R x, y, z, w;
@@ -130,27 +140,20 @@ __device__ __forceinline__ void coef4(const Coef4<R> *coef, const Ids4 &id, Coef
 // Magnetic half-step, 4 z cells per thread.  Arithmetic: fields_updates_ext.pyx:352-412 and
 // pml_updates_magnetic_*_ext.pyx (x and y slabs).
 // ------------------------------------------------------------------------------------------
-template <typename R, typename IDT, bool TABSMEM>
-__global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(const PhaseParams<R> p)
+// (blk, chunk) = block of 4-cell vectors within a plane / x chunk; NC: the operand fields are read-only for the whole kernel, so
+// their pointers may be restrict-qualified (loads hoisted above stores, non-coherent path).  The cooperative whole-run kernel
+// (gpb_kernels_coop.cuh) runs both half-steps in one launch and instantiates NC = false.
+template <typename R, typename IDT, bool NC>
+__device__ __forceinline__ void h4_body(const PhaseParams<R> &p, const Coef4<R> *coef, const R *srcm, int blk, int chunk, int tid)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Coef4<R> *coef = p.coef;
-    const R *srcm = p.src;
-    if (TABSMEM) {
-        Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw);
-        R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
-        stage_coefs(p, scoef, ssrc);
-        coef = scoef;
-        srcm = ssrc;
-    }
-    const long long idx4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx4 = (long long)blk * kThreadsV4 + tid;
     const long long e0 = idx4 * 4;
     const bool valid = e0 < p.plane;
     const long long eoff = valid ? e0 : 0;
     const int j = (int)(eoff / p.pitch);
     const int k = (int)(eoff - (long long)j * p.pitch);
-    const int lane = threadIdx.x & 31;
-    const int l0 = p.p0 + blockIdx.y * p.xchunk;
+    const int lane = tid & 31;
+    const int l0 = p.p0 + chunk * p.xchunk;
     const int l1 = min(l0 + p.xchunk, p.p1);
     if (l0 >= l1) return;
     const JK4 bx = jk4_of(p.box[0].lo, p.box[0].hi, j, k), by = jk4_of(p.box[1].lo, p.box[1].hi, j, k), bz = jk4_of(p.box[2].lo, p.box[2].hi, j, k);
@@ -163,12 +166,8 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(cons
 
     // E is read-only in this phase and never aliases H: tell the compiler so that the loads of the
     // next plane can be hoisted above the stores of this one
-    const R *__restrict__ Ex = p.Ex;
-    const R *__restrict__ Ey = p.Ey;
-    const R *__restrict__ Ez = p.Ez;
-    R *__restrict__ Hx = p.Hx;
-    R *__restrict__ Hy = p.Hy;
-    R *__restrict__ Hz = p.Hz;
+    typename MaybeRestrict<NC, const R>::type Ex = p.Ex, Ey = p.Ey, Ez = p.Ez;
+    typename MaybeRestrict<NC, R>::type Hx = p.Hx, Hy = p.Hy, Hz = p.Hz;
     long long off = (long long)(l0 + 1) * p.plane + eoff;
     V4<R> ey_c = ld4(Ey + off), ez_c = ld4(Ez + off);
 #pragma unroll kV4Unroll
@@ -266,6 +265,22 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(cons
     }
 }
 
+template <typename R, typename IDT, bool TABSMEM>
+__global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(const PhaseParams<R> p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Coef4<R> *coef = p.coef;
+    const R *srcm = p.src;
+    if (TABSMEM) {
+        Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw);
+        R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
+        stage_coefs(p, scoef, ssrc);
+        coef = scoef;
+        srcm = ssrc;
+    }
+    h4_body<R, IDT, true>(p, coef, srcm, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
+}
+
 // Dispersive sum for 4 cells of one component: part B of the previous step folded into part A of this one, the per-cell
 // arithmetic of gpb_kernels.cuh (disp_cell_c / disp_cell_r).  Complex T: complex[pole][cells], 4 cells = two 128-bit (fp32)
 // accesses; real T (Debye media, p.treal): R[pole][cells], one access.  Cells outside the update box keep their T.
@@ -302,27 +317,17 @@ __device__ __forceinline__ void disp4(const PhaseParams<R> &p, int comp, const I
 // Electric half-step, 4 z cells per thread.  Arithmetic: fields_updates_ext.pyx:30-107 and
 // pml_updates_electric_*_ext.pyx (x and y slabs).
 // ------------------------------------------------------------------------------------------
-template <typename R, typename IDT, bool TABSMEM, bool DISP>
-__global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(const PhaseParams<R> p)
+template <typename R, typename IDT, bool DISP, bool NC>
+__device__ __forceinline__ void e4_body(const PhaseParams<R> &p, const Coef4<R> *coef, const R *srce, int blk, int chunk, int tid)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Coef4<R> *coef = p.coef;
-    const R *srce = p.src;
-    if (TABSMEM) {
-        Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw);
-        R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
-        stage_coefs(p, scoef, ssrc);
-        coef = scoef;
-        srce = ssrc;
-    }
-    const long long idx4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx4 = (long long)blk * kThreadsV4 + tid;
     const long long e0 = idx4 * 4;
     const bool valid = e0 < p.plane;
     const long long eoff = valid ? e0 : 4;  // 4: keeps the k-1 load of lane 0 inside the allocation
     const int j = (int)(eoff / p.pitch);
     const int k = (int)(eoff - (long long)j * p.pitch);
-    const int lane = threadIdx.x & 31;
-    const int l0 = p.p0 + blockIdx.y * p.xchunk;
+    const int lane = tid & 31;
+    const int l0 = p.p0 + chunk * p.xchunk;
     const int l1 = min(l0 + p.xchunk, p.p1);
     if (l0 >= l1) return;
     const JK4 bx = jk4_of(p.box[0].lo, p.box[0].hi, j, k), by = jk4_of(p.box[1].lo, p.box[1].hi, j, k), bz = jk4_of(p.box[2].lo, p.box[2].hi, j, k);
@@ -332,12 +337,8 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
         if (s < p.nslabs && p.slab[s].axis != 2 && valid) smask |= jk4_of(p.slab[s].lo, p.slab[s].hi, j, k).kmask << (4 * s);
     const bool any = valid && ((bx.kmask | by.kmask | bz.kmask) != 0u || smask != 0u);
 
-    const R *__restrict__ Hx = p.Hx;
-    const R *__restrict__ Hy = p.Hy;
-    const R *__restrict__ Hz = p.Hz;
-    R *__restrict__ Ex = p.Ex;
-    R *__restrict__ Ey = p.Ey;
-    R *__restrict__ Ez = p.Ez;
+    typename MaybeRestrict<NC, const R>::type Hx = p.Hx, Hy = p.Hy, Hz = p.Hz;
+    typename MaybeRestrict<NC, R>::type Ex = p.Ex, Ey = p.Ey, Ez = p.Ez;
     long long off = (long long)(l0 + 1) * p.plane + eoff;
     V4<R> hy_p = ld4(Hy + off - p.plane), hz_p = ld4(Hz + off - p.plane);
 #pragma unroll kV4Unroll
@@ -459,6 +460,22 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
         hy_p = hy_c;
         hz_p = hz_c;
     }
+}
+
+template <typename R, typename IDT, bool TABSMEM, bool DISP>
+__global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(const PhaseParams<R> p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Coef4<R> *coef = p.coef;
+    const R *srce = p.src;
+    if (TABSMEM) {
+        Coef4<R> *scoef = reinterpret_cast<Coef4<R> *>(smem_raw);
+        R *ssrc = reinterpret_cast<R *>(scoef + p.nmat);
+        stage_coefs(p, scoef, ssrc);
+        coef = scoef;
+        srce = ssrc;
+    }
+    e4_body<R, IDT, DISP, true>(p, coef, srce, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------

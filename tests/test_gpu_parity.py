@@ -313,6 +313,40 @@ def test_pair_kernel_bit_identical(name, monkeypatch):
             assert np.array_equal(a, b) and np.array_equal(a, d), (name, rep, c)
 
 
+@pytest.mark.parametrize('name,variant', [('cylinder_Ascan_2D', 'f32'), ('2D_ExHyHz', 'f64'), ('pml_HORIPML_2', 'f32'), ('pml_MRIPML_2', 'f64'), ('sources_mixed', 'f32'),
+                                          ('snapshots', 'f32'), ('hertzian_dipole_dispersive', 'f32'), ('dispersive_multipole', 'f64'),
+                                          ('heterogeneous_soil_small', 'f32'), ('bench_100', 'f32')])
+def test_cooperative_whole_run_kernel_bit_identical(name, variant, monkeypatch):
+    """Small grids run n iterations in ONE cooperative launch (k_run_coop: grid-wide barrier between the half-steps; z-slab PML,
+    point sources and receiver samples done by the block that owns the cells).  Same bits as the kernel-per-half-step graph
+    path -- receivers (all nine rows), snapshots, final fields -- also when the run is cut into uneven pieces."""
+    from gprmax_b200 import Solver
+    from gprmax_b200.model_io import load_model
+    G, _ = load_model(golden_path(name, variant))
+
+    def run(env, pieces=None):
+        for k in ('GPB_NO_COOP', 'GPB_COOP_XCHUNK'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Solver(G, device_id=0) as sv:
+            path = sv.kernel_path
+            for n in (pieces or [G.iterations]):
+                sv.run(n)
+            assert sv.iteration == G.iterations
+            return path, [sv.get_field(c) for c in range(6)] + [sv.receivers()] + [a for k in range(len(G.snapshots)) for a in sv.snapshot(k)]
+
+    pref, ref = run({'GPB_NO_COOP': '1'})
+    assert 'k_run_coop' not in pref
+    assert np.abs(ref[6]).max() > 0
+    its = G.iterations
+    for env, pieces in (({}, None), ({}, [1, 2, 37, its - 40]), ({'GPB_COOP_XCHUNK': '1'}, None), ({'GPB_COOP_XCHUNK': '16'}, [its // 2, its - its // 2])):
+        path, out = run(env, pieces)
+        assert 'k_run_coop' in path, path
+        for c, (a, b) in enumerate(zip(out, ref)):
+            assert np.array_equal(a, b), (name, env, pieces, c, int((a != b).sum()))
+
+
 def test_device_memory_cache_reuse_and_release():
     """gpb_destroy keeps the device blocks for the next gpb_create of the same size (a B-scan creates one solver per trace):
     a second solver built from stale cached blocks must give the same bits as the first, and gpb_release_cached must work."""
