@@ -1530,7 +1530,11 @@ template <typename R>
 int Solver<R>::setup_coop()
 {
     coop = false;
-    if (!use_v4 || use_tma || nplanes != nx + 1 || getenv("GPB_NO_COOP")) return 0;
+    // Opt-in (GPB_COOP=1).  Measured on B200 (profiles/README.md, r2 coop): bit-identical, but slower than the graph of small
+    // kernels -- cylinder_Ascan_2D 30 us per iteration against 18 us, 100^3 168 us against 52 us: a grid-wide barrier over ~600
+    // resident CTAs costs more than the two kernel boundaries it replaces, and the half-step bodies, called as functions with
+    // coherent loads, spill.
+    if (!use_v4 || use_tma || nplanes != nx + 1 || !getenv("GPB_COOP") || getenv("GPB_NO_COOP")) return 0;
     int can = 0;
     CK(cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, device));
     if (!can) return 0;

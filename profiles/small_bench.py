@@ -1,5 +1,5 @@
-"""Small and mid-size grids: device loop time per iteration with the default kernels and with the cooperative whole-run kernel
-switched off (GPB_NO_COOP=1).   python profiles/small_bench.py"""
+"""Small and mid-size grids: device loop time per iteration with the default kernels and with the opt-in cooperative whole-run kernel
+(GPB_COOP=1).   python profiles/small_bench.py"""
 import json, os, subprocess, sys
 sys.path.insert(0, ".")
 CODE = r'''
@@ -20,7 +20,7 @@ cells = G.nx * G.ny * G.nz
 print(json.dumps({'model': spec, 'cells': cells, 'iterations': G.iterations, 'us_per_iteration': t / G.iterations * 1e6, 'mcells_per_s': cells * G.iterations / t / 1e6, 'kernels': path}))
 '''
 for spec in ('cylinder_Ascan_2D_f32', 'bench:100', 'bench:120', 'bench:150', 'heterogeneous_soil_full_f32', 'bscan_gssi_trace1_f32'):
-    for env in ({}, {'GPB_NO_COOP': '1'}):
+    for env in ({}, {'GPB_COOP': '1'}):
         r = subprocess.run([sys.executable, '-c', CODE, spec], stdout=subprocess.PIPE, stderr=subprocess.PIPE, universal_newlines=True, env=dict(os.environ, **env))
         line = (r.stdout.strip().splitlines() or ['{}'])[-1]
         try:

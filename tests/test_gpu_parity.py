@@ -317,7 +317,7 @@ def test_pair_kernel_bit_identical(name, monkeypatch):
                                           ('snapshots', 'f32'), ('hertzian_dipole_dispersive', 'f32'), ('dispersive_multipole', 'f64'),
                                           ('heterogeneous_soil_small', 'f32'), ('bench_100', 'f32')])
 def test_cooperative_whole_run_kernel_bit_identical(name, variant, monkeypatch):
-    """Small grids run n iterations in ONE cooperative launch (k_run_coop: grid-wide barrier between the half-steps; z-slab PML,
+    """Opt-in GPB_COOP=1: small grids run n iterations in ONE cooperative launch (k_run_coop: grid-wide barrier between the half-steps; z-slab PML,
     point sources and receiver samples done by the block that owns the cells).  Same bits as the kernel-per-half-step graph
     path -- receivers (all nine rows), snapshots, final fields -- also when the run is cut into uneven pieces."""
     from gprmax_b200 import Solver
@@ -325,7 +325,7 @@ def test_cooperative_whole_run_kernel_bit_identical(name, variant, monkeypatch):
     G, _ = load_model(golden_path(name, variant))
 
     def run(env, pieces=None):
-        for k in ('GPB_NO_COOP', 'GPB_COOP_XCHUNK'):
+        for k in ('GPB_COOP', 'GPB_COOP_XCHUNK'):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -336,11 +336,12 @@ def test_cooperative_whole_run_kernel_bit_identical(name, variant, monkeypatch):
             assert sv.iteration == G.iterations
             return path, [sv.get_field(c) for c in range(6)] + [sv.receivers()] + [a for k in range(len(G.snapshots)) for a in sv.snapshot(k)]
 
-    pref, ref = run({'GPB_NO_COOP': '1'})
+    pref, ref = run({})
     assert 'k_run_coop' not in pref
     assert np.abs(ref[6]).max() > 0
     its = G.iterations
-    for env, pieces in (({}, None), ({}, [1, 2, 37, its - 40]), ({'GPB_COOP_XCHUNK': '1'}, None), ({'GPB_COOP_XCHUNK': '16'}, [its // 2, its - its // 2])):
+    for env, pieces in (({'GPB_COOP': '1'}, None), ({'GPB_COOP': '1'}, [1, 2, 37, its - 40]), ({'GPB_COOP': '1', 'GPB_COOP_XCHUNK': '1'}, None),
+                        ({'GPB_COOP': '1', 'GPB_COOP_XCHUNK': '16'}, [its // 2, its - its // 2])):
         path, out = run(env, pieces)
         assert 'k_run_coop' in path, path
         for c, (a, b) in enumerate(zip(out, ref)):
