@@ -76,6 +76,9 @@ def install():
             pass
         mbr.build_electric_components = build_electric_components
         mbr.build_magnetic_components = build_magnetic_components
+        # PML face averages without the per-cell Python search through the material list (pml_build.py; identical tables)
+        from .pml_build import build_pmls
+        mbr.build_pmls = build_pmls
     _installed = True
     return top, mbr
 

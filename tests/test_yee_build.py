@@ -1,4 +1,5 @@
-"""Multi-threaded ID build (gprmax_b200/yee_build.py + csrc/gpb_idbuild.cpp) against the reference's own
+"""Host-side build steps next to the hot path: the multi-threaded ID build (gprmax_b200/yee_build.py +
+csrc/gpb_idbuild.cpp) and the vectorised PML build (gprmax_b200/pml_build.py: every R table bit-identical) against the reference's own
 build_electric_components / build_magnetic_components (yee_cell_build_ext.pyx:110-257) on real models: the ID array and the
 list of dielectric-smoothed materials (names, numbering, averaged properties) must be IDENTICAL.
 
@@ -63,6 +64,28 @@ def electric(solid, rigidE, ID, G):
     res['same_id_slabs'] = bool(np.array_equal(G.ID, ID_ref))
     raise Done()
 
+from gprmax_b200 import pml_build
+ref_build_pmls = mbr.build_pmls
+def pmls(G, pbar):
+    class Quiet(object):
+        def update(self, *a):
+            pass
+    t0 = time.perf_counter()
+    ref_build_pmls(G, Quiet())
+    res['t_pml_ref'] = time.perf_counter() - t0
+    names = ('ERA', 'ERB', 'ERE', 'ERF', 'HRA', 'HRB', 'HRE', 'HRF')
+    tabs_ref = [[getattr(p, n).copy() for n in names] + [p.direction, p.xs, p.xf, p.ys, p.yf, p.zs, p.zf, p.thickness] for p in G.pmls]
+    cfs_ref = [float(c.sigma.max) for c in G.cfs]
+    del G.pmls[:]
+    t0 = time.perf_counter()
+    pml_build.build_pmls(G, pbar)
+    res['t_pml_new'] = time.perf_counter() - t0
+    tabs_new = [[getattr(p, n).copy() for n in names] + [p.direction, p.xs, p.xf, p.ys, p.yf, p.zs, p.zf, p.thickness] for p in G.pmls]
+    same = len(tabs_ref) == len(tabs_new)
+    for a, b in zip(tabs_ref, tabs_new):
+        same = same and all(np.array_equal(x, y) for x, y in zip(a[:8], b[:8])) and a[8:] == b[8:]
+    res['same_pml'] = bool(same) and cfs_ref == [float(c.sigma.max) for c in G.cfs]
+mbr.build_pmls = pmls
 mbr.build_electric_components = electric
 work = tempfile.mkdtemp()
 text = open(os.path.join(baseline.REF_DIR, {rel!r})).read()
@@ -78,7 +101,7 @@ try:
 except Done:
     pass
 print('RESULT', res)
-assert res['same_id'] and res['same_mats'] and res['same_id_slabs'], res
+assert res['same_id'] and res['same_mats'] and res['same_id_slabs'] and res['same_pml'], res
 print('YEE_OK')
 '''
 
