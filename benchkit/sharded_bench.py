@@ -163,9 +163,11 @@ def bench_sharded(args):
     shard = None
 
     # ---- 3. end-to-end leg: the public sharded call from HOST arrays on every rank, per-cell material IDs included.
+    # One call = one job: 500 iterations (the N = 1 benchmark's job is its model's own 1559 iterations; a run that lets a wave
+    # cross this 2-metre domain would take ~3500), so that the one-off upload is weighed against a run, not against 20 steps.
     # Two dielectrics in 16-plane layers along z (IDs 2 and 3): every rank holds its slab of the uint32 ID array
     # [6][planes][ny+1][nz+1] (12.9 GB per rank at the default size) and the library uploads it plane by plane.
-    e2e_iters = int(os.environ.get('GPB_E2E_ITERS', '100'))
+    e2e_iters = int(os.environ.get('GPB_E2E_ITERS', '500'))
     slab_id_bytes = 6 * nplanes * (ny + 1) * (nz + 1) * 4
     try:
         import psutil

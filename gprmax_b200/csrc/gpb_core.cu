@@ -202,6 +202,39 @@ void parallel_copy(char *dst, const char *src, size_t bytes, int nthreads)
     }
     for (auto &t : th) t.join();
 }
+// uint32 -> IDT on the host, split over threads like parallel_copy; returns the largest value seen.  Narrowing before the
+// transfer quarters the PCIe bytes and the pinned-buffer writes: the host side of the upload is memory-bound (a 12.9 GB slab
+// per rank of a sharded run went through at 13 GB/s per rank with four ranks on one host)
+template <typename IDT>
+uint32_t parallel_narrow(IDT *dst, const uint32_t *src, size_t n, int nthreads)
+{
+    auto body = [](IDT *d, const uint32_t *s, size_t cnt) {
+        uint32_t mx = 0;
+        for (size_t q = 0; q < cnt; ++q) {
+            const uint32_t v = s[q];
+            mx = v > mx ? v : mx;
+            d[q] = (IDT)v;
+        }
+        return mx;
+    };
+    if (nthreads <= 1 || n < (1u << 20)) return body(dst, src, n);
+    std::vector<std::thread> th;
+    std::vector<uint32_t> mx(nthreads, 0);
+    const size_t part = (n / nthreads + 4095) & ~(size_t)4095;
+    for (int t = 0; t < nthreads; ++t) {
+        const size_t o = (size_t)t * part;
+        if (o >= n) break;
+        th.emplace_back([=, &mx] {
+            cpu_set_t all;   // see parallel_copy
+            CPU_ZERO(&all);
+            for (int c = 0; c < CPU_SETSIZE; ++c) CPU_SET(c, &all);
+            pthread_setaffinity_np(pthread_self(), sizeof all, &all);
+            mx[t] = body(dst + o, src + o, std::min(part, n - o));
+        });
+    }
+    for (auto &t : th) t.join();
+    return *std::max_element(mx.begin(), mx.end());
+}
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------
@@ -551,21 +584,24 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
         CK(cudaStreamSynchronize(stream));
         return 0;
     }
-    // uint32 rows -> pinned bounce buffer (several host threads) -> device stage -> narrowed on the device, double-buffered:
-    // the host copy of chunk q+1 overlaps the PCIe transfer and the narrowing kernel of chunk q (a plain cudaMemcpy from
-    // the pageable NumPy array ran at 11 GB/s: 59 ms of the 300^3 model's 62 ms set-up)
+    // uint32 rows -> narrowed by several host threads into a pinned bounce buffer -> device stage -> placed into the pitched
+    // layout, double-buffered: the host pass over chunk q+1 overlaps the PCIe transfer and the placement kernel of chunk q
+    // (a plain cudaMemcpy from the pageable NumPy array ran at 11 GB/s: 59 ms of the 300^3 model's 62 ms set-up).  Models
+    // with more than 65536 materials keep 32-bit IDs: copied as they are and "narrowed" (32 -> 32) on the device.
     const long long rows_per_plane = ny + 1;
     const long long total_rows = rows_per_plane * nplanes;
-    const size_t row_bytes = (size_t)(nz + 1) * 4;
-    const long long chunk_rows = std::max<long long>(1, (long long)(kBounceBytes / row_bytes));
+    const size_t row_elems = (size_t)(nz + 1);
+    const bool host_narrow = idbytes < 4 && !getenv("GPB_DEVICE_NARROW");
+    const size_t xfer_elem = host_narrow ? (size_t)idbytes : 4;   // bytes per ID that cross PCIe
+    const long long chunk_rows = std::max<long long>(1, (long long)(kBounceBytes / (row_elems * xfer_elem)));
     // a shard may point into the caller's global ID array (component stride of the whole grid): no second host copy of the slab
     const size_t comp_stride = m.id_comp_stride > 0 ? (size_t)m.id_comp_stride : (size_t)total_rows * (nz + 1);
-    uint32_t *stage[2] = {nullptr, nullptr};
+    void *stage[2] = {nullptr, nullptr};
     unsigned *d_max = nullptr;
     void *bounce[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     for (int b = 0; b < 2; ++b) {
-        CK(g_pool.alloc((void **)&stage[b], kBounceBytes, device));
+        CK(g_pool.alloc(&stage[b], kBounceBytes, device));
         CK(g_pool.alloc_pinned(&bounce[b], kBounceBytes));
         CK(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
     }
@@ -579,6 +615,7 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
     // (configured CPUs, not std::thread::hardware_concurrency(): that one follows the calling thread's affinity mask, which is a
     //  single core once the OpenMP runtime has pinned the main thread)
     const int nthreads = (int)std::max(1l, std::min(8l, sysconf(_SC_NPROCESSORS_CONF) / 2));
+    uint32_t host_max = 0;
     long long q = 0;
     for (int c = 0; c < 6; ++c) {
         void *dst = (char *)idbase + (size_t)c * narr * idbytes;
@@ -586,18 +623,25 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
         for (long long r0 = 0; r0 < total_rows; r0 += chunk_rows, ++q) {
             const int b = (int)(q & 1);
             const long long rows = std::min(chunk_rows, total_rows - r0);
-            const size_t bytes = (size_t)rows * row_bytes;
-            const char *src = (const char *)(m.ID + (size_t)c * comp_stride + (size_t)r0 * (nz + 1));
+            const size_t n = (size_t)rows * row_elems;
+            const uint32_t *src = m.ID + (size_t)c * comp_stride + (size_t)r0 * row_elems;
             if (q >= 2) CK(cudaEventSynchronize(ev[b]));   // the transfer out of this bounce buffer two chunks ago
-            parallel_copy((char *)bounce[b], src, bytes, nthreads);
-            CK(cudaMemcpyAsync(stage[b], bounce[b], bytes, cudaMemcpyHostToDevice, stream));
+            if (host_narrow) {
+                const uint32_t mx = idbytes == 1 ? parallel_narrow((uint8_t *)bounce[b], src, n, nthreads) : parallel_narrow((uint16_t *)bounce[b], src, n, nthreads);
+                host_max = std::max(host_max, mx);
+            } else {
+                parallel_copy((char *)bounce[b], (const char *)src, n * 4, nthreads);
+            }
+            CK(cudaMemcpyAsync(stage[b], bounce[b], n * xfer_elem, cudaMemcpyHostToDevice, stream));
             CK(cudaEventRecord(ev[b], stream));
-            const long long n = rows * (nz + 1);
-            const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+            const int blocks = (int)std::min<long long>(((long long)n + 255) / 256, 148 * 16);
             char *d = (char *)dst + ((size_t)plane + (size_t)r0 * pitch) * idbytes;   // plane 0 of the array is the ghost plane
-            if (idbytes == 1) k_narrow_ids<uint8_t><<<blocks, 256, 0, stream>>>(stage[b], (uint8_t *)d, rows, nz + 1, pitch, d_max);
-            else if (idbytes == 2) k_narrow_ids<uint16_t><<<blocks, 256, 0, stream>>>(stage[b], (uint16_t *)d, rows, nz + 1, pitch, d_max);
-            else k_narrow_ids<uint32_t><<<blocks, 256, 0, stream>>>(stage[b], (uint32_t *)d, rows, nz + 1, pitch, d_max);
+            if (host_narrow) {
+                if (idbytes == 1) k_place_ids<uint8_t><<<blocks, 256, 0, stream>>>((const uint8_t *)stage[b], (uint8_t *)d, rows, nz + 1, pitch);
+                else k_place_ids<uint16_t><<<blocks, 256, 0, stream>>>((const uint16_t *)stage[b], (uint16_t *)d, rows, nz + 1, pitch);
+            } else if (idbytes == 1) k_narrow_ids<uint8_t><<<blocks, 256, 0, stream>>>((const uint32_t *)stage[b], (uint8_t *)d, rows, nz + 1, pitch, d_max);
+            else if (idbytes == 2) k_narrow_ids<uint16_t><<<blocks, 256, 0, stream>>>((const uint32_t *)stage[b], (uint16_t *)d, rows, nz + 1, pitch, d_max);
+            else k_narrow_ids<uint32_t><<<blocks, 256, 0, stream>>>((const uint32_t *)stage[b], (uint32_t *)d, rows, nz + 1, pitch, d_max);
             CK(cudaGetLastError());
         }
     }
@@ -610,6 +654,7 @@ int Solver<R>::upload_ids(const gpb_model_t &m)
     unsigned mx = 0;
     CK(cudaMemcpy(&mx, d_max, sizeof mx, cudaMemcpyDeviceToHost));
     g_pool.free(d_max);
+    mx = std::max(mx, host_max);
     if ((int)mx >= nmat) return fail("ID array references material %u but only %d materials were given", mx, nmat);
     return 0;
 }

@@ -824,6 +824,17 @@ __global__ void k_narrow_ids(const uint32_t *src, IDT *dst, long long rows, int 
     if (mx) atomicMax(maxid, mx);
 }
 
+// IDs narrowed on the host (dense rows of nzp1 elements) -> device layout with z pitch
+template <typename IDT>
+__global__ void k_place_ids(const IDT *src, IDT *dst, long long rows, int nzp1, int pitch)
+{
+    const long long n = rows * nzp1;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const long long row = q / nzp1;
+        dst[row * pitch + (int)(q - row * nzp1)] = src[q];
+    }
+}
+
 template <typename IDT>
 __global__ void k_fill_ids(IDT *dst, long long n, IDT v)
 {
