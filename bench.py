@@ -43,47 +43,7 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-
-    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-
-    def __init__(self, index=0):
-        self.index = index
-        self.rows = []
-        self.stop = threading.Event()
-        self.th = None
-
-    def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(',')])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
-
-    def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
-        return self
-
-    def __exit__(self, *a):
-        self.stop.set()
-        self.th.join(timeout=6)
-
-    def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(self.rows)}
+from benchkit.clocks import ClockSampler  # noqa: E402
 
 
 def _usable_cores():
@@ -141,11 +101,14 @@ def slab_model(n, iterations, x_range=None, build_id=False):
                              x_range=x_range, build_id=build_id)
 
 
-def bench_grid(N, iterations=None):
+def bench_grid(N, iterations=None, dtype='f32'):
     """tests/benchmarking/bench_NxNxN.in as the drop-in receives it.  Built by the unmodified reference front end when
     baseline/_ref is present (parse + geometry / material / PML build, stopped at the solve_gpu seam), otherwise by the
     closed-form builder benchkit/synthetic.py (pinned bit-exactly against the reference's build in tests/test_synthetic.py)."""
     from benchkit import refmodel
+    if dtype == 'f64':   # the vendored reference is the float32 build (constants.py:36-49 is a source-level switch)
+        from benchkit.synthetic import bench_model
+        return bench_model(N, real=np.float64, iterations=iterations), 'benchkit.synthetic (closed-form tables), float64'
     if iterations is None and os.environ.get('GPB_BENCH_MODEL', 'reference') == 'reference' and refmodel.reference_available():
         try:
             G = refmodel.build_with_reference(refmodel.reference_input('tests/benchmarking/bench_{0}x{0}x{0}.in'.format(N)))
@@ -260,21 +223,23 @@ def run_single_gpu(args):
     from gprmax_b200 import GPU, Solver, solve_gpu
 
     N = args.size
-    G, model_source = bench_grid(N, iterations=args.iters)
+    G, model_source = bench_grid(N, iterations=args.iters, dtype=args.dtype)
+    f64 = args.dtype == 'f64'
+    rbytes = 8 if f64 else 4
     G.gpu = GPU(0)
     G.gpu.get_gpu_info()
     cells = G.nx * G.ny * G.nz
     its = G.iterations
     S = sum(p.thickness * {'x': G.ny * G.nz, 'y': G.nx * G.nz, 'z': G.nx * G.ny}[p.direction[0]] for p in G.pmls)
-    b_pml = 32.0 * len(G.cfs) * S / cells
-    b_alg = B_ALG_FP32 + b_pml  # + PML Phi read+write
+    b_pml = 8.0 * rbytes * len(G.cfs) * S / cells
+    b_alg = 18.0 * rbytes + 24.0 + b_pml  # fields + uint32 IDs + PML Phi read+write (96 B fp32, 168 B fp64)
     peak, peak_src = measured_peaks()
 
     # ---- device-resident leg: handle created once, K timed full runs
     sv = Solver(G, device_id=0)
     kpath = sv.kernel_path
     idbytes = 1 if G.updatecoeffsE.shape[0] <= 256 else (2 if G.updatecoeffsE.shape[0] <= 65536 else 4)
-    b_moved = 72.0 + 6.0 * idbytes + b_pml   # what the kernels have to move with the narrowed device IDs
+    b_moved = 18.0 * rbytes + 6.0 * idbytes + b_pml   # what the kernels have to move with the narrowed device IDs
     times = []
     launches = 0
     rx_gpu = None
@@ -307,7 +272,7 @@ def run_single_gpu(args):
         alg_bytes = cells * b_alg / 2.0  # one half-step
         achieved = alg_bytes / t_launch / 1e9
         share = prof[dom] / max(sum(prof.values()), 1e-30)
-        traffic, traffic_src = committed_traffic(N)
+        traffic, traffic_src = committed_traffic(N) if not f64 else (None, 'no capture of the float64 kernels')
         kname = [k for k in kpath.split() if k.startswith('E:' if dom == 'update_e' else 'H:')][0][2:]
         roof = {'bound': 'hbm', 'kernel': '{} ({}: base update + PML slabs of one half-step)'.format(kname, dom),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
@@ -348,13 +313,13 @@ def run_single_gpu(args):
                'sample': 'first {} of {} iterations of the same {}^3 model, {} OpenMP threads, {:.1f} s'.format(sample, its, N, cores, t)}
         parity['prefix'] = trace_parity(rx_gpu, G, ref_out, sample, 'the reference CPU kernels ({}) run here on the same grid, first {} iterations'.format(kind, sample))
     # the complete trace against the committed golden of the unmodified reference (tests/golden/make_golden.py: bench_300_trace)
-    gold = os.path.join(ROOT, 'tests', 'golden', 'bench_{}_trace_f32.npz'.format(N))
+    gold = os.path.join(ROOT, 'tests', 'golden', 'bench_{}_trace_{}.npz'.format(N, args.dtype))
     if os.path.exists(gold) and args.iters is None:
         z = np.load(gold)
         g32 = {k[len('golden_'):]: z[k] for k in z.files}
-        parity['full'] = trace_parity(rx_gpu, G, g32, its, 'tests/golden/bench_{}_trace_f32.npz: all {} iterations, unmodified reference CPU solver'.format(N, its))
+        parity['full'] = trace_parity(rx_gpu, G, g32, its, 'tests/golden/bench_{}_trace_{}.npz: all {} iterations, unmodified reference CPU solver'.format(N, args.dtype, its))
         t64 = gold.replace('_f32.npz', '_f64.npz')
-        if os.path.exists(t64):
+        if os.path.exists(t64) and not f64:
             # criterion (b) of tests/parity.py, per component: against the reference's own float64 run, the GPU's float32 trace is
             # as close as the reference's float32 trace is (x3: two realisations of the same rounding noise)
             z64 = np.load(t64)
@@ -365,7 +330,7 @@ def run_single_gpu(args):
                                   ref32_vs_ref64={k: float('{:.3e}'.format(v)) for k, v in e_ref.items()})
         # the end-to-end call must give the same bits as the device-resident run
         parity['e2e_equals_resident'] = bool(all(np.array_equal(rx_e2e[k], rx_gpu[_row(k), :, int(k[2:k.index('_')])]) for k in rx_e2e))
-    tol = 1e-4
+    tol = 1e-10 if f64 else 1e-4   # north_star: float32 1e-4 of trace peak, float64 1e-10
     verdicts = {}
     for k, v in parity.get('prefix', {}).get('per_component', {}).items():
         verdicts['prefix:' + k] = 'a' if v <= tol else 'FAIL'
@@ -373,7 +338,7 @@ def run_single_gpu(args):
         b_ok = 'gpu32_vs_ref64' in parity['full'] and parity['full']['gpu32_vs_ref64'].get(k, 1e9) <= 3 * parity['full']['ref32_vs_ref64'].get(k, 0.0) + 1e-5
         verdicts['full:' + k] = 'a' if v <= tol else ('b' if b_ok else 'FAIL')
     parity['per_component_criterion'] = verdicts
-    parity['criterion'] = ('a = max|gpu32 - ref32| <= 1e-4 of trace peak (north_star); b = |gpu32 - ref64| <= 3 |ref32 - ref64| + 1e-5: as close to the '
+    parity['criterion'] = ('float64: max|gpu64 - ref64| <= 1e-10 of trace peak (north_star)' if f64 else 'a = max|gpu32 - ref32| <= 1e-4 of trace peak (north_star); b = |gpu32 - ref64| <= 3 |ref32 - ref64| + 1e-5: as close to the '
                            "reference's float64 result as the reference's own float32 result is (tests/parity.py)")
     checks = list(verdicts.values())
     ok_a = ok_b = False
@@ -382,7 +347,7 @@ def run_single_gpu(args):
 
     # ---- weak-scaling baseline: the per-GPU slab of the sharded runs on this one GPU (so that v_N / (N v_1) is like for like)
     wsb = None
-    if not args.no_slab and args.iters is None:
+    if not args.no_slab and args.iters is None and not f64:
         try:
             Gs = slab_model(SLAB, 20 * 6)
             with Solver(Gs, device_id=0) as ss:
@@ -400,8 +365,8 @@ def run_single_gpu(args):
 
     line = {
         'metric': 'FDTD throughput', 'value': value, 'unit': 'Mcells/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'tests/benchmarking/bench_{0}x{0}x{0}.in: {0}^3 free space, Hertzian dipole, 1 rx, 10-cell HORIPML x6, float32'.format(N),
+        'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+        'config': {'workload': 'tests/benchmarking/bench_{0}x{0}x{0}.in: {0}^3 free space, Hertzian dipole, 1 rx, 10-cell HORIPML x6, {1}'.format(N, 'float64' if f64 else 'float32'),
                    'cells': cells, 'iterations_per_step': its, 'l2': 'working set {:.0f} MB >> 126 MB L2 (no flush needed)'.format(mem / 1e6),
                    'gpu': G.gpu.name, 'alg_bytes_per_cell_step': b_alg, 'model_built_by': model_source, 'kernels': kpath},
         'roofline': roof, 'cpu_baseline': cpu, 'parity': parity, 'weak_scaling_baseline': wsb,
@@ -430,6 +395,7 @@ def main():
     ap.add_argument('--size', type=int, default=300, help='cube side of the single-GPU benchmark model')
     ap.add_argument('--iters', type=int, default=None, help='iterations per step (default: the model\'s own 1559)')
     ap.add_argument('--cpu-iters', type=int, default=300, help='iterations of the CPU baseline sample (about 10 s on 32 threads at 300^3)')
+    ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'], help='N = 1 only: floating type of the run (the reference default and the headline is f32)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-slab', action='store_true', help='skip the weak-scaling baseline (the 256 x 2048 x 1024 slab on one GPU)')
     ap.add_argument('--workload', default='auto', choices=['auto', 'slab'], help="'slab' at N=1: run the sharded runs' per-GPU slab on one GPU")

@@ -119,6 +119,9 @@ def bench_sharded(args):
     plane_bytes = shard.solver.halo(0)[2]
     cells = nx * ny * nz
     times = []
+    from benchkit.clocks import ClockSampler
+    clocks = ClockSampler(local)
+    clocks.__enter__()
     if transport == 'p2p':
         if world > 1:
             link_neighbours(shard.solver, rank, world)
@@ -151,6 +154,11 @@ def bench_sharded(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 if s >= args.warmup:
                     times.append(float(t.item()))
+    clocks.__exit__()
+    clk = clocks.summary()
+    mhz = torch.tensor([clk['sm_mhz'] or 0.0], device=shard.device, dtype=torch.float64)
+    dist.all_reduce(mhz, op=dist.ReduceOp.MIN)
+    clk['sm_mhz_min_over_ranks'] = float(mhz.item())
     launches = torch.tensor([shard.solver.kernel_launches], device=shard.device, dtype=torch.int64)
     dist.all_reduce(launches)
     kpath = shard.solver.kernel_path
@@ -236,7 +244,7 @@ def bench_sharded(args):
                             'from host tables, {} run, traces gathered'.format(e2e_iters, 'per-cell ID upload (two dielectrics in 16-cell layers),' if hetero else
                                                                                  'homogeneous device-side ID fill (host RAM too small for the per-cell arrays),'),
                     'iterations_per_call': e2e_iters, 'seconds_per_call': [round(t_, 4) for t_ in e2e_t], 'statistic': 'median'},
-            'gpu_launches': int(launches.item()),
+            'gpu_launches': int(launches.item()), 'clocks': clk,
         }
         sys.stdout.flush()
         os.write(out_fd, (json.dumps(line) + '\n').encode())

@@ -370,7 +370,7 @@ struct Solver : SolverBase {
     int sm_count = 148;
     TmaMaps4 maps_e, maps_h;
     int setup_tma();
-    int launch_tma(int phase, int p0, int p1);
+    int launch_tma(int phase, int p0, int p1, bool peer_store = false);
     // H and E half-steps of an iteration in ONE launch (gpb_kernels_pair.cuh): items of both phases from one queue, the E items
     // of a chunk about two chunks behind its H items, so E finds its operands in L2
     bool pair_he = false;
@@ -1093,7 +1093,7 @@ int Solver<R>::setup_tma()
 
 // E or H half-step of planes [p0, p1) on the TMA-staged kernels (gpb_tma_inst.cu)
 template <typename R>
-int Solver<R>::launch_tma(int phase, int p0, int p1)
+int Solver<R>::launch_tma(int phase, int p0, int p1, bool peer_store)
 {
     TmaLaunch<R> a;
     PhaseParams<R> &p = a.p;
@@ -1123,6 +1123,17 @@ int Solver<R>::launch_tma(int phase, int p0, int p1)
     a.stream = stream;
     a.concurrent = 0;
     p.progress = nullptr;
+    p.peer1 = p.peer2 = nullptr;
+    p.peer_plane = -1;
+    if (peer_store && phase == 0 && right.present) {          // Hy,Hz of my last plane -> right neighbour's ghost plane x_start-1
+        p.peer1 = right.F + 4 * right.narr;
+        p.peer2 = right.F + 5 * right.narr;
+        p.peer_plane = nplanes;
+    } else if (peer_store && phase == 1 && left.present) {    // Ey,Ez of my first plane -> left neighbour's ghost plane x_end
+        p.peer1 = left.F + 1 * left.narr + plane * (left.nplanes + 1);
+        p.peer2 = left.F + 2 * left.narr + plane * (left.nplanes + 1);
+        p.peer_plane = 1;
+    }
     std::string err;
     const int pv = 2 * form + order - 1;
     int rc;
@@ -1338,6 +1349,8 @@ int Solver<R>::launch_pair()
         p.zfused = 1;
         p.znocoop = tma_znocoop ? 1 : 0;
         p.progress = d_progress;
+        p.peer1 = p.peer2 = nullptr;
+        p.peer_plane = -1;
         p.pair_lag = pair_lag;
         p.prog_flags = d_progress + n_he_chunks;
         p.prog_timeout_ns = 5000000000ull;
@@ -1387,40 +1400,61 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
         if (right.present) { k_flag_signal<<<1, 1, 0, stream>>>(right.flags + GPB_FLAG_SNAP_DONE, it, 1); ++launches; }
         if (left.present) { k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_SNAP_DONE, it, 1, d_flags, GPB_FLAG_SNAP_DONE, link_timeout_ns); ++launches; }
     }
-    // ---- H half-step: last owned plane first (its Hy,Hz feed the right neighbour).  The push runs IN the stream, before the
-    // interior kernel: the persistent interior kernel fills every SM (2 CTAs x 256 threads x 128 registers = the whole
-    // register file), so a push on a second stream only got SM slots when the interior was over and the neighbour stalled on
-    // the halo (4 GPUs: 282 k instead of 293 k Mcells/s).  In the stream it costs ~30 us of a 3.7 ms half-step.
+    // ---- H half-step in ONE launch.  On the TMA kernels the halo exchange is part of it: the threads that update the last
+    // owned plane store Hy,Hz into the right neighbour's ghost plane as well (PhaseParams::peer1/2).  Other kernel families (small
+    // shards, z slabs in their own kernel) and planes touched by a point source afterwards are pushed by k_halo_push.  The flag is
+    // published when the half-step is complete -- the neighbour needs the plane only at the start of ITS next half-step, which
+    // begins when mine ends.  (Round 1 and the first linked version split every half-step into a boundary and an interior launch
+    // to send early: at ~16 us of fill and tail per TMA launch the split cost more than the 30 us transfer it hid.)
+    auto src_on_plane = [&](int phase, int gi) {
+        for (size_t q = 0; q < h_src_plane.size(); ++q)
+            if (h_src_phase[q] == phase && h_src_plane[q] == gi) return true;
+        for (int t = 0; t < ntl; ++t)
+            if (phase == 1 && h_tls[t].i == gi) return true;
+        return false;
+    };
+    const bool fused = use_tma && !tma_zsplit && !getenv("GPB_NO_FUSED_PUSH");
+    const bool fused_e = fused && !(maxpoles && !tma_disp);   // (a dispersive E half-step on the register kernel has no peer stores)
     if (right.present) {
         k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_E_READY, it, 0, d_flags, GPB_FLAG_E_READY, link_timeout_ns);
-        ++launches;
-        if (launch_phase(0, n - 1, n) || launch_sources(0, n - 1, n, 0, 0)) return 1;
         k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_H_FREE, it, 0, d_flags, GPB_FLAG_H_FREE, link_timeout_ns);
-        k_halo_push<R><<<128, 256, 0, stream>>>(F[4] + plane * n, F[5] + plane * n, right.F + 4 * right.narr, right.F + 5 * right.narr, plane,
-                                                 right.flags + GPB_FLAG_H_READY, it, 1, d_flags + GPB_FLAG_PUSH_COUNT);
-        CK(cudaGetLastError());
         launches += 2;
-        if (launch_phase(0, 0, n - 1) || launch_sources(0, 0, n - 1, 0, 0)) return 1;
-    } else {
-        if (launch_phase(0, 0, n) || launch_sources(0, 0, n, 0, 0)) return 1;
     }
-    // ---- E half-step: first owned plane first (its Ey,Ez feed the left neighbour)
+    if (fused && right.present) {
+        if (launch_tma(0, 0, n, true)) return 1;
+    } else if (launch_phase(0, 0, n)) return 1;
+    if (launch_sources(0, 0, n, 0, 0)) return 1;
+    if (right.present) {
+        if (!fused || src_on_plane(0, x_start + n - 1)) {
+            k_halo_push<R><<<128, 256, 0, stream>>>(F[4] + plane * n, F[5] + plane * n, right.F + 4 * right.narr, right.F + 5 * right.narr, plane,
+                                                     right.flags + GPB_FLAG_H_READY, it, 1, d_flags + GPB_FLAG_PUSH_COUNT);
+        } else {
+            k_flag_signal<<<1, 1, 0, stream>>>(right.flags + GPB_FLAG_H_READY, it, 1);
+        }
+        CK(cudaGetLastError());
+        ++launches;
+    }
+    // ---- E half-step
     if (left.present) {
         k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_H_READY, it, 1, d_flags, GPB_FLAG_H_READY, link_timeout_ns);
         ++launches;
     }
     // transmission-line currents after the wait: a line on my first plane reads H of the ghost plane (sources.py:444-452)
     if (ntl && launch_sources(0, 0, 0, 0, n)) return 1;
+    if (fused_e && left.present) {
+        if (launch_tma(1, 0, n, true)) return 1;
+    } else if (launch_phase(1, 0, n)) return 1;
+    if (launch_sources(1, 0, n, 0, n)) return 1;
     if (left.present) {
-        if (launch_phase(1, 0, 1) || launch_sources(1, 0, 1, 0, 1)) return 1;
-        k_halo_push<R><<<128, 256, 0, stream>>>(F[1] + plane, F[2] + plane, left.F + 1 * left.narr + plane * (left.nplanes + 1),
-                                                 left.F + 2 * left.narr + plane * (left.nplanes + 1), plane, left.flags + GPB_FLAG_E_READY, it, 1,
-                                                 d_flags + GPB_FLAG_PUSH_COUNT + 1);
+        if (!fused_e || src_on_plane(1, x_start)) {
+            k_halo_push<R><<<128, 256, 0, stream>>>(F[1] + plane, F[2] + plane, left.F + 1 * left.narr + plane * (left.nplanes + 1),
+                                                     left.F + 2 * left.narr + plane * (left.nplanes + 1), plane, left.flags + GPB_FLAG_E_READY, it, 1,
+                                                     d_flags + GPB_FLAG_PUSH_COUNT + 1);
+        } else {
+            k_flag_signal<<<1, 1, 0, stream>>>(left.flags + GPB_FLAG_E_READY, it, 1);
+        }
         CK(cudaGetLastError());
         ++launches;
-        if (launch_phase(1, 1, n) || launch_sources(1, 1, n, 1, n)) return 1;
-    } else {
-        if (launch_phase(1, 0, n) || launch_sources(1, 0, n, 0, n)) return 1;
     }
     CK(cudaGetLastError());
     return 0;

@@ -102,6 +102,10 @@ struct PhaseParams {
     // TMA kernels, H and E half-steps of one iteration running CONCURRENTLY (Solver::overlap_he): both hand their x chunks out
     // in increasing x; the H kernel counts finished (tile, chunk) items per chunk in progress[], the E kernel's producer loads a
     // chunk only when the H items of that chunk and of the one before it are complete -- so E reads H (and re-reads E) out of L2
+    // TMA kernels, linked x-slab shards: results of array plane `peer_plane` (components 1 and 2 of the phase: Ey,Ez / Hy,Hz)
+    // are stored to the neighbour's ghost plane as well; peer1 / peer2 point at that plane in the neighbour's arrays
+    R *peer1, *peer2;
+    int peer_plane;
     int monotone;
     int pair_lag;             // k_update_pair: the E items of chunk c follow the H items of chunk c + pair_lag in the queue
     unsigned *progress;       // [nchunks] finished H warps per chunk (null: kernels run one after the other)
