@@ -370,7 +370,7 @@ struct Solver : SolverBase {
     int sm_count = 148;
     TmaMaps4 maps_e, maps_h;
     int setup_tma();
-    int launch_tma(int phase, int p0, int p1, bool peer_store = false);
+    int launch_tma(int phase, int p0, int p1, int peer_store = 0);   // 1: boundary plane also stored to the neighbour, 2: and announced by the kernel
     // H and E half-steps of an iteration in ONE launch (gpb_kernels_pair.cuh): items of both phases from one queue, the E items
     // of a chunk about two chunks behind its H items, so E finds its operands in L2
     bool pair_he = false;
@@ -1093,7 +1093,7 @@ int Solver<R>::setup_tma()
 
 // E or H half-step of planes [p0, p1) on the TMA-staged kernels (gpb_tma_inst.cu)
 template <typename R>
-int Solver<R>::launch_tma(int phase, int p0, int p1, bool peer_store)
+int Solver<R>::launch_tma(int phase, int p0, int p1, int peer_store)
 {
     TmaLaunch<R> a;
     PhaseParams<R> &p = a.p;
@@ -1125,14 +1125,20 @@ int Solver<R>::launch_tma(int phase, int p0, int p1, bool peer_store)
     p.progress = nullptr;
     p.peer1 = p.peer2 = nullptr;
     p.peer_plane = -1;
+    p.peer_flag = p.peer_counter = nullptr;
+    p.peer_iter = d_iter;
+    p.peer_add = 1;
+    p.peer_need = 0;
     if (peer_store && phase == 0 && right.present) {          // Hy,Hz of my last plane -> right neighbour's ghost plane x_start-1
         p.peer1 = right.F + 4 * right.narr;
         p.peer2 = right.F + 5 * right.narr;
         p.peer_plane = nplanes;
+        if (peer_store == 2) { p.peer_flag = right.flags + GPB_FLAG_H_READY; p.peer_counter = d_flags + GPB_FLAG_PUSH_COUNT; }
     } else if (peer_store && phase == 1 && left.present) {    // Ey,Ez of my first plane -> left neighbour's ghost plane x_end
         p.peer1 = left.F + 1 * left.narr + plane * (left.nplanes + 1);
         p.peer2 = left.F + 2 * left.narr + plane * (left.nplanes + 1);
         p.peer_plane = 1;
+        if (peer_store == 2) { p.peer_flag = left.flags + GPB_FLAG_E_READY; p.peer_counter = d_flags + GPB_FLAG_PUSH_COUNT + 1; }
     }
     std::string err;
     const int pv = 2 * form + order - 1;
@@ -1351,6 +1357,7 @@ int Solver<R>::launch_pair()
         p.progress = d_progress;
         p.peer1 = p.peer2 = nullptr;
         p.peer_plane = -1;
+        p.peer_flag = p.peer_counter = nullptr;
         p.pair_lag = pair_lag;
         p.prog_flags = d_progress + n_he_chunks;
         p.prog_timeout_ns = 5000000000ull;
@@ -1420,11 +1427,13 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
         k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_H_FREE, it, 0, d_flags, GPB_FLAG_H_FREE, link_timeout_ns);
         launches += 2;
     }
+    // (the kernel itself announces the plane as soon as its items are done, unless a point source changes it afterwards)
+    const bool early_h = fused && right.present && !src_on_plane(0, x_start + n - 1) && !getenv("GPB_LATE_SIGNAL");
     if (fused && right.present) {
-        if (launch_tma(0, 0, n, true)) return 1;
+        if (launch_tma(0, 0, n, early_h ? 2 : 1)) return 1;
     } else if (launch_phase(0, 0, n)) return 1;
     if (launch_sources(0, 0, n, 0, 0)) return 1;
-    if (right.present) {
+    if (right.present && !early_h) {
         if (!fused || src_on_plane(0, x_start + n - 1)) {
             k_halo_push<R><<<128, 256, 0, stream>>>(F[4] + plane * n, F[5] + plane * n, right.F + 4 * right.narr, right.F + 5 * right.narr, plane,
                                                      right.flags + GPB_FLAG_H_READY, it, 1, d_flags + GPB_FLAG_PUSH_COUNT);
@@ -1441,11 +1450,12 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
     }
     // transmission-line currents after the wait: a line on my first plane reads H of the ghost plane (sources.py:444-452)
     if (ntl && launch_sources(0, 0, 0, 0, n)) return 1;
+    const bool early_e = fused_e && left.present && !src_on_plane(1, x_start) && !getenv("GPB_LATE_SIGNAL");
     if (fused_e && left.present) {
-        if (launch_tma(1, 0, n, true)) return 1;
+        if (launch_tma(1, 0, n, early_e ? 2 : 1)) return 1;
     } else if (launch_phase(1, 0, n)) return 1;
     if (launch_sources(1, 0, n, 0, n)) return 1;
-    if (left.present) {
+    if (left.present && !early_e) {
         if (!fused_e || src_on_plane(1, x_start)) {
             k_halo_push<R><<<128, 256, 0, stream>>>(F[1] + plane, F[2] + plane, left.F + 1 * left.narr + plane * (left.nplanes + 1),
                                                      left.F + 2 * left.narr + plane * (left.nplanes + 1), plane, left.flags + GPB_FLAG_E_READY, it, 1,

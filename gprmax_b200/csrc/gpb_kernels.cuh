@@ -106,6 +106,12 @@ struct PhaseParams {
     // are stored to the neighbour's ghost plane as well; peer1 / peer2 point at that plane in the neighbour's arrays
     R *peer1, *peer2;
     int peer_plane;
+    // ... and the warp that completes the last item holding that plane publishes *peer_flag = *peer_iter + peer_add in the
+    // neighbour's memory (null: the host launches k_flag_signal after the half-step instead)
+    unsigned *peer_flag, *peer_counter;
+    unsigned peer_need;       // tiles * consumer warps
+    const int *peer_iter;
+    int peer_add;
     int monotone;
     int pair_lag;             // k_update_pair: the E items of chunk c follow the H items of chunk c + pair_lag in the queue
     unsigned *progress;       // [nchunks] finished H warps per chunk (null: kernels run one after the other)

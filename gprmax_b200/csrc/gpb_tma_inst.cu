@@ -58,6 +58,7 @@ static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
     p.pf_depth = std::min(p.pf_depth, a.pf_max);
     const size_t smem = fixed2 + p.pf_depth * pf_unit;
     const int tiles = tiles_k * tiles_j, nchunks = (p.p1 - p.p0 + p.xchunk - 1) / p.xchunk;
+    p.peer_need = (unsigned)(tiles * (TY * TZ / 4 / 32));
     // persistent: as many CTAs as fit on the GPU at once (2 per SM for fp32), pulling (tile, chunk) items from a.sched
     const int resident = a.concurrent ? a.sm_count : (sizeof(R) == 4 ? GPB_TMA_CTAS : 1) * a.sm_count;
     p.monotone = a.concurrent ? 1 : 0;
