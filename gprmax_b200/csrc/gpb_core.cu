@@ -433,6 +433,7 @@ struct Solver : SolverBase {
     bool linked = false;
     unsigned *d_flags = nullptr;   // [GPB_NFLAGS] written by the neighbours (peer stores) and by this shard's own kernels
     unsigned long long link_timeout_ns = 20000000000ull;
+    bool link_nofused = false, link_late = false;   // diagnostic switches GPB_NO_FUSED_PUSH / GPB_LATE_SIGNAL, read in link()
     bool snap_needs_right = false;
     bool snap_unlinked_ok = true;    // every snapshot cell of this slab averages planes of this slab only
     bool no_overlap_now = false;     // profile(): time the two half-step kernels one after the other   // some snapshot cell of this shard reads planes of the right neighbour
@@ -1420,7 +1421,7 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
             if (phase == 1 && h_tls[t].i == gi) return true;
         return false;
     };
-    const bool fused = use_tma && !tma_zsplit && !getenv("GPB_NO_FUSED_PUSH");
+    const bool fused = use_tma && !tma_zsplit && !link_nofused;
     const bool fused_e = fused && !(maxpoles && !tma_disp);   // (a dispersive E half-step on the register kernel has no peer stores)
     if (right.present) {
         k_flag_wait<<<1, 1, 0, stream>>>(d_flags + GPB_FLAG_E_READY, it, 0, d_flags, GPB_FLAG_E_READY, link_timeout_ns);
@@ -1428,7 +1429,7 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
         launches += 2;
     }
     // (the kernel itself announces the plane as soon as its items are done, unless a point source changes it afterwards)
-    const bool early_h = fused && right.present && !src_on_plane(0, x_start + n - 1) && !getenv("GPB_LATE_SIGNAL");
+    const bool early_h = fused && right.present && !src_on_plane(0, x_start + n - 1) && !link_late;
     if (fused && right.present) {
         if (launch_tma(0, 0, n, early_h ? 2 : 1)) return 1;
     } else if (launch_phase(0, 0, n)) return 1;
@@ -1450,7 +1451,7 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
     }
     // transmission-line currents after the wait: a line on my first plane reads H of the ghost plane (sources.py:444-452)
     if (ntl && launch_sources(0, 0, 0, 0, n)) return 1;
-    const bool early_e = fused_e && left.present && !src_on_plane(1, x_start) && !getenv("GPB_LATE_SIGNAL");
+    const bool early_e = fused_e && left.present && !src_on_plane(1, x_start) && !link_late;
     if (fused_e && left.present) {
         if (launch_tma(1, 0, n, early_e ? 2 : 1)) return 1;
     } else if (launch_phase(1, 0, n)) return 1;
@@ -1506,7 +1507,7 @@ int Solver<R>::link_info(gpb_link_t *out)
 template <typename R>
 int Solver<R>::unlink()
 {
-    if (!linked) return 0;
+    if (!linked && !left.present && !right.present && !left.ipc_F && !left.ipc_flags && !right.ipc_F && !right.ipc_flags) return 0;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     for (Peer *p : {&left, &right}) {
@@ -1527,6 +1528,8 @@ int Solver<R>::link(const gpb_link_t *l, const gpb_link_t *r)
     unlink();
     if (!l && !r) return 0;
     if (const char *e = getenv("GPB_LINK_TIMEOUT_MS")) link_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+    link_nofused = getenv("GPB_NO_FUSED_PUSH") != nullptr;
+    link_late = getenv("GPB_LATE_SIGNAL") != nullptr;
     const uint64_t me = (uint64_t)getpid();
     for (int side = 0; side < 2; ++side) {
         const gpb_link_t *q = side == 0 ? l : r;
