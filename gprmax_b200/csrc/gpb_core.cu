@@ -434,6 +434,19 @@ struct Solver : SolverBase {
     unsigned *d_flags = nullptr;   // [GPB_NFLAGS] written by the neighbours (peer stores) and by this shard's own kernels
     unsigned long long link_timeout_ns = 20000000000ull;
     bool link_nofused = false, link_late = false;   // diagnostic switches GPB_NO_FUSED_PUSH / GPB_LATE_SIGNAL, read in link()
+    bool rx_on_first_plane = false;                  // a receiver on my first plane reads the H ghost plane in the step prologue
+    bool tl_on_first_plane() const
+    {
+        for (int t = 0; t < ntl; ++t)
+            if (h_tls[t].i == x_start) return true;
+        return false;
+    }
+    bool credit_src_on_first_plane() const           // (then the E half-step does not announce early: keep the credit late as well)
+    {
+        for (size_t q = 0; q < h_src_plane.size(); ++q)
+            if (h_src_phase[q] == 1 && h_src_plane[q] == x_start) return true;
+        return false;
+    }
     bool snap_needs_right = false;
     bool snap_unlinked_ok = true;    // every snapshot cell of this slab averages planes of this slab only
     bool no_overlap_now = false;     // profile(): time the two half-step kernels one after the other   // some snapshot cell of this shard reads planes of the right neighbour
@@ -782,10 +795,12 @@ template <typename R>
 int Solver<R>::setup_points(const gpb_model_t &m)
 {
     nrx = m.nrx;
+    rx_on_first_plane = false;
     if (nrx) {
         if (upload(&d_rxc, m.rxcoords, (size_t)nrx * 3)) return 1;
         for (int r = 0; r < nrx; ++r) {
             const int *c = m.rxcoords + 3 * r;
+            if (c[0] == m.x_start) rx_on_first_plane = true;
             if (c[0] < 0 || c[0] > nx || c[1] < 0 || c[1] > ny || c[2] < 0 || c[2] > nz) return fail("receiver %d outside the grid", r);
         }
     }
@@ -1126,7 +1141,7 @@ int Solver<R>::launch_tma(int phase, int p0, int p1, int peer_store)
     p.progress = nullptr;
     p.peer1 = p.peer2 = nullptr;
     p.peer_plane = -1;
-    p.peer_flag = p.peer_counter = nullptr;
+    p.peer_flag = p.peer_counter = p.peer_flag2 = nullptr;
     p.peer_iter = d_iter;
     p.peer_add = 1;
     p.peer_need = 0;
@@ -1139,7 +1154,10 @@ int Solver<R>::launch_tma(int phase, int p0, int p1, int peer_store)
         p.peer1 = left.F + 1 * left.narr + plane * (left.nplanes + 1);
         p.peer2 = left.F + 2 * left.narr + plane * (left.nplanes + 1);
         p.peer_plane = 1;
-        if (peer_store == 2) { p.peer_flag = left.flags + GPB_FLAG_E_READY; p.peer_counter = d_flags + GPB_FLAG_PUSH_COUNT + 1; }
+        if (peer_store >= 2) { p.peer_flag = left.flags + GPB_FLAG_E_READY; p.peer_counter = d_flags + GPB_FLAG_PUSH_COUNT + 1; }
+        // the items of my first plane are also the last readers of my H ghost plane (unless the step prologue or a line reads
+        // it, see enqueue_linked_step): the left neighbour may write the next H plane into it from now on
+        if (peer_store == 3) p.peer_flag2 = left.flags + GPB_FLAG_H_FREE;
     }
     std::string err;
     const int pv = 2 * form + order - 1;
@@ -1358,7 +1376,7 @@ int Solver<R>::launch_pair()
         p.progress = d_progress;
         p.peer1 = p.peer2 = nullptr;
         p.peer_plane = -1;
-        p.peer_flag = p.peer_counter = nullptr;
+        p.peer_flag = p.peer_counter = p.peer_flag2 = nullptr;
         p.pair_lag = pair_lag;
         p.prog_flags = d_progress + n_he_chunks;
         p.prog_timeout_ns = 5000000000ull;
@@ -1395,7 +1413,14 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
     const int n = nplanes;
     const int *it = d_iter;
     if (launch_begin()) return 1;
-    if (left.present) {   // the step prologue was the last reader of my H ghost plane (receiver currents on my first plane)
+    // H_FREE credit for the left neighbour.  Readers of my H ghost plane: the E update of my first plane, and -- only if they
+    // exist -- receivers on my first plane (currents Ix, Iy, Iz in the step prologue) and transmission lines there.  Without
+    // those the E half-step kernel publishes the credit itself together with E_READY, as soon as the items of the first plane
+    // are done (loose coupling); otherwise it is published here, after the prologue of the next iteration.
+    const bool ghost_read_late = rx_on_first_plane || tl_on_first_plane();
+    const bool fused_all = use_tma && !tma_zsplit && !link_nofused && !(maxpoles && !tma_disp) && !link_late;
+    const bool credit_early = left.present && fused_all && !ghost_read_late && !credit_src_on_first_plane();
+    if (left.present && !credit_early) {
         k_flag_signal<<<1, 1, 0, stream>>>(left.flags + GPB_FLAG_H_FREE, it, 0);
         ++launches;
     }
@@ -1453,7 +1478,7 @@ int Solver<R>::enqueue_linked_step(bool with_snap)
     if (ntl && launch_sources(0, 0, 0, 0, n)) return 1;
     const bool early_e = fused_e && left.present && !src_on_plane(1, x_start) && !link_late;
     if (fused_e && left.present) {
-        if (launch_tma(1, 0, n, early_e ? 2 : 1)) return 1;
+        if (launch_tma(1, 0, n, early_e ? (credit_early ? 3 : 2) : 1)) return 1;
     } else if (launch_phase(1, 0, n)) return 1;
     if (launch_sources(1, 0, n, 0, n)) return 1;
     if (left.present && !early_e) {

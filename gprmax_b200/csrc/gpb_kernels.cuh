@@ -109,6 +109,7 @@ struct PhaseParams {
     // ... and the warp that completes the last item holding that plane publishes *peer_flag = *peer_iter + peer_add in the
     // neighbour's memory (null: the host launches k_flag_signal after the half-step instead)
     unsigned *peer_flag, *peer_counter;
+    unsigned *peer_flag2;     // second flag published with the same value (E half-step: the neighbour's H_FREE credit), or null
     unsigned peer_need;       // tiles * consumer warps
     const int *peer_iter;
     int peer_add;
