@@ -390,7 +390,6 @@ struct Solver : SolverBase {
     Cplx<R> *T[3] = {0, 0, 0};   // treal: the allocation holds R[maxpoles][narr] instead
     Cplx<R> *dcoef = 0;          // treal: R[nmat][maxpoles][3]
     bool treal = false;          // all dispersive coefficients real (Debye media): real-valued T
-    int xblock = 0;              // > 0: planes per block of the x-blocked H/E launch order (GPB_XBLOCK)
     // small grids: n iterations in ONE cooperative launch (gpb_kernels_coop.cuh)
     bool coop = false;
     int coop_grid = 0, coop_xchunk = 1, coop_gx = 0, coop_gy = 0;
@@ -1010,7 +1009,6 @@ int Solver<R>::build(const gpb_model_t &m)
     tma_disp = use_tma && maxpoles > 0 && tma_ty == 14 && tma_tz == 64 && tma_stages == 3 && tma_pw == 1 && !getenv("GPB_DISP_V4") &&
                (size_t)nmat * maxpoles * 3 * (treal ? 1 : 2) * sizeof(R) <= 24 * 1024;
     tma_tpf = getenv("GPB_TMA_TPF") ? std::max(0, atoi(getenv("GPB_TMA_TPF"))) : 2;
-    xblock = getenv("GPB_XBLOCK") ? atoi(getenv("GPB_XBLOCK")) : 0;
     // both half-steps in one launch (opt-in, GPB_PAIR=1): default tile with the producer warp, whole-domain handle (a shard's halo
     // protocol orders the half-steps itself), E half-step on the TMA kernels; models with something that acts on H between the two
     // half-steps (magnetic dipoles, transmission lines) keep the two launches (checked per step: has_hsrc).
@@ -1137,7 +1135,6 @@ int Solver<R>::launch_tma(int phase, int p0, int p1, int peer_store)
     a.sm_count = sm_count;
     a.sched = d_sched;
     a.stream = stream;
-    a.concurrent = 0;
     p.progress = nullptr;
     p.peer1 = p.peer2 = nullptr;
     p.peer_plane = -1;
@@ -1331,17 +1328,6 @@ int Solver<R>::enqueue_step(bool with_snap)
     // model_build_run.py:590-696 in order
     if (launch_begin()) return 1;
     if (with_snap && launch_snapshots()) return 1;
-    if (xblock > 0 && xblock < nplanes) {
-        // x-blocked order: the E half-step of a block of planes right after its H half-step, while the block's fields are
-        // still in L2.  Valid because E(i) needs H(i-1), H(i) (done) and the next block's H update only reads E planes the
-        // E update of this block does not write.
-        for (int a = 0; a < nplanes; a += xblock) {
-            const int b = std::min(a + xblock, nplanes);
-            if (launch_phase(0, a, b) || launch_sources(0, a, b, a, b)) return 1;
-            if (launch_phase(1, a, b) || launch_sources(1, a, b, a, b)) return 1;
-        }
-        return 0;
-    }
     if (pair_he && !has_hsrc) {
         if (launch_pair()) return 1;
         return launch_sources(1, 0, nplanes, 0, nplanes);

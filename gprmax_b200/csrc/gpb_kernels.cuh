@@ -99,9 +99,9 @@ struct PhaseParams {
     int pf_depth;             // TMA kernels: Phi prefetch distance in planes (cp.async ring per thread), 0 = direct loads
     int persist;              // TMA kernels: persistent CTAs pulling (tile, x-chunk) items from an atomic counter
     int t_depth;              // TMA kernels, dispersive E half-step: T prefetch distance in planes (cp.async ring per thread), 0 = direct loads
-    // TMA kernels, H and E half-steps of one iteration running CONCURRENTLY (Solver::overlap_he): both hand their x chunks out
-    // in increasing x; the H kernel counts finished (tile, chunk) items per chunk in progress[], the E kernel's producer loads a
-    // chunk only when the H items of that chunk and of the one before it are complete -- so E reads H (and re-reads E) out of L2
+    // k_update_pair (both half-steps of an iteration in one launch): x chunks are handed out in increasing x; finished H items are
+    // counted per chunk in progress[], the producer loads an E item only when the H items of its chunk and of the one before it
+    // are complete -- so E reads H (and re-reads E) out of L2
     // TMA kernels, linked x-slab shards: results of array plane `peer_plane` (components 1 and 2 of the phase: Ey,Ez / Hy,Hz)
     // are stored to the neighbour's ghost plane as well; peer1 / peer2 point at that plane in the neighbour's arrays
     R *peer1, *peer2;

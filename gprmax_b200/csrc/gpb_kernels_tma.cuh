@@ -16,6 +16,9 @@
 //   * a consumer warp hands a stage back (one `empty` arrival per warp) only after EVERYTHING it reads from the stage --
 //     operands, own fields, material IDs, and for slab warps the re-reads of the PML corrections -- has been read: the
 //     producer refills the stage at once, and with persistent CTAs the refill may belong to another tile.
+// The dispersive recursion of the E half-step (T read / written once by the owning thread, prefetched like Phi) and, for linked
+// x-slab shards, the halo exchange (the boundary plane is stored into the neighbour's ghost plane by the threads that update it
+// and announced by the warp that completes the last item holding it) are part of the same pass: see gpb_tma_item.inc.
 // All PML slabs are applied in the same pass: x / y slabs vectorised and warp-uniform with Phi prefetched per thread by
 // cp.async (`prefetch` in the kernel), z slabs one cell per lane with the corrections handed to the owning thread by shuffle.
 #pragma once
@@ -187,7 +190,7 @@ __device__ __forceinline__ void chunk_range(int v, int nchunks, int nsplit, int 
     const int nbig = nchunks - nsplit;
     int c, lo = 0, len = xc;
     if (monotone) {
-        c = v;   // increasing x (concurrent H / E kernels)
+        c = v;   // increasing x (k_update_pair)
     } else if (v < nbig) {
         c = chunk_of(v, nchunks);
     } else {
@@ -349,25 +352,6 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
             p_k0 = (tile % tiles_k) * TZ;
             p_j0 = (tile / tiles_k) * TY;
             chunk_range(chunk, nchunks, nsplit, p.xchunk, p.p0, p.p1, p_l0, p_l1, p.monotone);
-            if (PHASE == 1 && p.progress) {
-                // concurrent H kernel: the H fields of this chunk's planes and of the plane in front of them must be final.
-                // The finished items were published with fence + atomic by the H kernel's warps; acquire here, then order the
-                // TMA (async proxy) loads that follow behind what was acquired.
-                unsigned long long t0;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                for (int cc = chunk > 0 ? chunk - 1 : chunk; cc <= chunk; ++cc) {
-                    unsigned v;
-                    for (;;) {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.progress + cc) : "memory");
-                        if (v >= p.prog_need) break;
-                        __nanosleep(100);
-                        unsigned long long t1;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                        if (t1 - t0 > p.prog_timeout_ns) { atomicOr(p.prog_flags, 1u); break; }
-                    }
-                }
-                asm volatile("fence.proxy.async;" ::: "memory");
-            }
         }
         p_n = -1;
     };

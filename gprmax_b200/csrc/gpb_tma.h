@@ -29,7 +29,6 @@ struct TmaLaunch {
     int pf_max;               // upper bound on the Phi prefetch distance (GPB_TMA_PF)
     int disp;                 // electric half-step of a dispersive model: 1 complex T, 2 real T (0: none)
     int t_max;                // upper bound on the T prefetch distance (GPB_TMA_TPF)
-    int concurrent;           // H and E kernels of one iteration side by side: 1 CTA per SM each, monotone chunk order, no half items
     int nosplit;              // no half-size items at the end of a persistent launch (GPB_TMA_NOSPLIT)
     int sm_count;
     int *sched;               // [2] work-item scheduler state

@@ -60,12 +60,11 @@ static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
     const int tiles = tiles_k * tiles_j, nchunks = (p.p1 - p.p0 + p.xchunk - 1) / p.xchunk;
     p.peer_need = (unsigned)(tiles * (TY * TZ / 4 / 32));
     // persistent: as many CTAs as fit on the GPU at once (2 per SM for fp32), pulling (tile, chunk) items from a.sched
-    const int resident = a.concurrent ? a.sm_count : (sizeof(R) == 4 ? GPB_TMA_CTAS : 1) * a.sm_count;
-    p.monotone = a.concurrent ? 1 : 0;
-    if (a.concurrent) p.prog_need = (unsigned)(tiles * (TY * TZ / 4 / 32));
-    else p.progress = nullptr;
+    const int resident = (sizeof(R) == 4 ? GPB_TMA_CTAS : 1) * a.sm_count;
+    p.monotone = 0;
+    p.progress = nullptr;
     // persistent launches hand the last ~wave of chunks out in halves (chunk_range)
-    const int nsplit = (p.persist && p.xchunk >= 4 && !a.nosplit && !a.concurrent) ? std::min(nchunks, (resident + tiles - 1) / tiles + 1) : 0;
+    const int nsplit = (p.persist && p.xchunk >= 4 && !a.nosplit) ? std::min(nchunks, (resident + tiles - 1) / tiles + 1) : 0;
     const dim3 grid = p.persist ? dim3((unsigned)std::min(tiles * (nchunks + nsplit), resident)) : dim3((unsigned)tiles, (unsigned)nchunks);
     cudaError_t e;
     if (a.phase == 0) {
