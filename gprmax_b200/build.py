@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgprmax_b200.so')
 OBJDIR = os.path.join(os.path.dirname(HERE), 'build', 'obj')
-DEPS = ['gpb_core.cu', 'gpb_idbuild.cpp', 'gpb_tma_inst.cu', 'gpb_tma_item.inc', 'gpb_tma.h', 'gpb_kernels.cuh', 'gpb_kernels_v4.cuh', 'gpb_kernels_coop.cuh', 'gpb_kernels_tma.cuh', 'gpb_kernels_pair.cuh',
+DEPS = ['gpb_core.cu', 'gpb_idbuild.cpp', 'gpb_vtkio.cpp', 'gpb_tma_inst.cu', 'gpb_tma_item.inc', 'gpb_tma.h', 'gpb_kernels.cuh', 'gpb_kernels_v4.cuh', 'gpb_kernels_coop.cuh', 'gpb_kernels_tma.cuh', 'gpb_kernels_pair.cuh',
         os.path.join('..', '..', 'include', 'gprmax_b200.h')]
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 
@@ -38,7 +38,7 @@ def needs_build():
 
 def units():
     """(object name, source, extra defines) of every translation unit."""
-    out = [('gpb_core.o', 'gpb_core.cu', []), ('gpb_idbuild.o', 'gpb_idbuild.cpp', ['-x', 'cu'])]
+    out = [('gpb_core.o', 'gpb_core.cu', []), ('gpb_idbuild.o', 'gpb_idbuild.cpp', ['-x', 'cu']), ('gpb_vtkio.o', 'gpb_vtkio.cpp', ['-x', 'cu'])]
     for rname, rtype in (('f32', 'float'), ('f64', 'double')):
         for pv in range(4):   # 2 * formulation (HORIPML, MRIPML) + order - 1
             out.append(('gpb_tma_{}_pv{}.o'.format(rname, pv), 'gpb_tma_inst.cu', ['-DGPB_TMA_R=' + rtype, '-DGPB_TMA_PV={}'.format(pv)]))

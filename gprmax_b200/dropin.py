@@ -12,7 +12,9 @@ solver lacks the features: `#transmission_line` under `-gpu` (input_cmds_multius
 outputs (:417-418); both are CPU-only in the reference and are supported by this core.  The input commands are parsed by
 the reference's own `process_multicmds`; it merely does not see `G.gpu` while it parses.  Finally the per-edge ID build
 (`build_electric_components` / `build_magnetic_components`, model_build_run.py:216-218) runs on all host cores with an identical
-result (gprmax_b200/yee_build.py; GPRMAX_B200_REF_BUILD=1 keeps the reference's single-threaded loop).
+result (gprmax_b200/yee_build.py; GPRMAX_B200_REF_BUILD=1 keeps the reference's single-threaded loop), and the snapshot and
+geometry-view files are written by the streaming writers of gprmax_b200/vtk_writers.py (byte-identical files;
+GPRMAX_B200_REF_WRITERS=1 keeps the reference's).
 """
 import os
 import sys
@@ -79,6 +81,10 @@ def install():
         # PML face averages without the per-cell Python search through the material list (pml_build.py; identical tables)
         from .pml_build import build_pmls
         mbr.build_pmls = build_pmls
+    # snapshot and geometry-view files streamed through a bounded buffer, byte-identical (vtk_writers.py)
+    if os.environ.get('GPRMAX_B200_REF_WRITERS') != '1':
+        from . import vtk_writers
+        vtk_writers.install()
     _installed = True
     return top, mbr
 

@@ -19,7 +19,7 @@ import sys
 
 import numpy as np
 
-from . import _lib
+from . import _lib, vtk_writers
 from .exceptions import GeneralError
 from .model_io import DIRECTIONS, grid_maxpoles
 
@@ -339,10 +339,17 @@ def store_results(G, solver):
             for name in list(rx.outputs.keys()):
                 rx.outputs[name] = np.ascontiguousarray(rxs[_lib.RX_ROWS.index(name), :, n])
     for n, snap in enumerate(G.snapshots):
-        ex, ey, ez, hx, hy, hz = solver.snapshot(n)
-        # snapshots.py:128-130: Paraview ordering
-        snap.electric = np.stack((ex, ey, ez)).reshape(-1, order='F')
-        snap.magnetic = np.stack((hx, hy, hz)).reshape(-1, order='F')
+        fields = solver.snapshot(n)
+        if vtk_writers.installed():
+            # the streaming writer re-orders the six component arrays block by block while it writes the file
+            # (vtk_writers.write_vtk_imagedata): the two interleaved copies of the snapshot are never built
+            snap.fields = fields
+            snap.electric = snap.magnetic = None
+        else:
+            # snapshots.py:128-130: Paraview ordering, np.stack((ex, ey, ez)).reshape(-1, order='F') on all host cores
+            snap.fields = None
+            snap.electric = vtk_writers.paraview_vectors(*fields[:3])
+            snap.magnetic = vtk_writers.paraview_vectors(*fields[3:])
     for n, tl in enumerate(G.transmissionlines):
         tl.Vtotal, tl.Itotal = solver.tline(n)
 

@@ -247,6 +247,16 @@ int gpb_ids_scan(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigi
 int gpb_ids_apply(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
                   const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos);
 
+/* ---- host-side re-layout for the streaming VTK writers (snapshots.py:128-167, geometry_outputs.py:119-205,
+ * geometry_outputs_ext.pyx:81-110), all host cores ----
+ * ParaView order (x fastest, z slowest, components interleaved) out of z-fastest arrays:
+ *   out[((k * count[1] + j) * count[0] + i) * ncomp + c] =
+ *       src[c][(start[0] + i*step[0]) * stride[0] + (start[1] + j*step[1]) * stride[1] + (start[2] + k*step[2]) * stride[2]]
+ * for i < count[0], j < count[1], k < count[2]; strides in elements, elements of 1, 2, 4 or 8 bytes (moved as bit patterns).
+ * A caller streams a file by asking for one range of k at a time.  Return: 0 ok, 1 bad argument. */
+int gpb_vtk_transpose(const void *const *src, int ncomp, int elem_bytes, const int64_t stride[3], const int32_t start[3],
+                      const int32_t count[3], const int32_t step[3], void *out);
+
 const char *gpb_last_error(void);
 const char *gpb_version(void);
 
