@@ -457,14 +457,21 @@ struct Solver : SolverBase {
     int enqueue_linked_step(bool with_snap);
     int check_link_timeout();
     // graph
-    cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t graph = nullptr;    // one iteration
+    cudaGraphExec_t graph_k = nullptr;  // graph_iters iterations in one graph (fewer graph boundaries; small grids)
+    int graph_iters = 1;
     bool use_graph = true;
+    void drop_graphs()
+    {
+        if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
+        if (graph_k) { cudaGraphExecDestroy(graph_k); graph_k = nullptr; }
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     ~Solver()
     {
         cudaSetDevice(device);
-        if (graph) cudaGraphExecDestroy(graph);
+        drop_graphs();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamSynchronize(stream);   // cached blocks are handed to the next solver, which runs on another stream
@@ -771,7 +778,7 @@ int Solver<R>::set_points(const gpb_model_t &m)
     if (m.nx != nx || m.ny != ny || m.nz != nz || m.iterations != iterations || m.nmaterials != nmat)
         return fail("gpb_set_points: the model has another grid, iteration count or material table than the resident one");
     CK(cudaStreamSynchronize(stream));
-    if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }   // the captured launches hold the old point arrays
+    drop_graphs();   // the captured launches hold the old point arrays
     has_hsrc = has_esrc = false;
     if (setup_points(m)) return 1;
     snap_unlinked_ok = true;
@@ -920,6 +927,7 @@ int Solver<R>::build(const gpb_model_t &m)
     idbytes = nmat <= 256 ? 1 : (nmat <= 65536 ? 2 : 4);
     if (getenv("GPB_ID_BYTES")) idbytes = std::max(idbytes, atoi(getenv("GPB_ID_BYTES")) >= 4 ? 4 : (atoi(getenv("GPB_ID_BYTES")) >= 2 ? 2 : 1));
     use_graph = !getenv("GPB_NO_GRAPH");
+    if (getenv("GPB_GRAPH_ITERS")) graph_iters = std::max(1, std::min(64, atoi(getenv("GPB_GRAPH_ITERS"))));
     // all six components in one allocation: the TMA kernels address a triple (E or H) as one 4-D tensor
     if (dalloc(&F[0], (size_t)narr * 6)) return 1;
     for (int c = 1; c < 6; ++c) F[c] = F[0] + (size_t)c * narr;
@@ -1528,7 +1536,7 @@ int Solver<R>::unlink()
         if (p->ipc_flags) g_ipc.release(p->ipc_flags);
         *p = Peer();
     }
-    if (graph) { cudaGraphExecDestroy(graph); graph = nullptr; }
+    drop_graphs();
     for (int c = 0; c < 6; ++c) pp.Fr[c] = nullptr;
     linked = false;
     return 0;
@@ -1711,6 +1719,19 @@ int Solver<R>::begin_run(int n)
         if (e != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(e));
         CK(cudaGraphInstantiate(&graph, g, 0));
         cudaGraphDestroy(g);
+        if (!linked && graph_iters > 1 && n >= graph_iters) {
+            // the same step graph_iters times in one graph: the launches inside a graph follow each other more closely than
+            // two graph launches do, which is what a small grid's iteration consists of
+            g = nullptr;
+            CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            for (int q = 0; q < graph_iters && !rc; ++q) rc = enqueue_step(false);
+            e = cudaStreamEndCapture(stream, &g);
+            launches = l0;
+            if (rc) return 1;
+            if (e != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(e));
+            CK(cudaGraphInstantiate(&graph_k, g, 0));
+            cudaGraphDestroy(g);
+        }
     }
     CK(cudaEventRecord(ev0, stream));
     return 0;
@@ -1739,6 +1760,17 @@ int Solver<R>::enqueue_iterations(int n)
         return 0;
     }
     for (int s = 0; s < n; ++s) {
+        if (graph_k && s + graph_iters <= n) {
+            bool snap = false;
+            for (int q = 0; q < graph_iters; ++q) snap = snap || snapshot_due(iteration + q);
+            if (!snap) {
+                CK(cudaGraphLaunch(graph_k, stream));
+                launches += graph_launches * graph_iters;
+                iteration += graph_iters;
+                s += graph_iters - 1;
+                continue;
+            }
+        }
         if (graph && !snapshot_due(iteration)) {
             CK(cudaGraphLaunch(graph, stream));
             launches += graph_launches;

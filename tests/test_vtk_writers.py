@@ -174,3 +174,48 @@ def test_snapshot_vti_identical(tmp_path, box, block_bytes):
             out.append((f.read(), bar.n, s.vtkdatawritesize))
     assert out[0][0] == out[1][0] == out[2][0]
     assert out[0][1] == out[1][1] == out[2][1] == out[0][2]
+
+
+MODEL = '''#title: writers end to end
+#domain: 0.100 0.080 0.060
+#dx_dy_dz: 0.002 0.002 0.002
+#time_window: 30
+#material: 6 0.01 1 0 half_space
+#waveform: ricker 1 1.5e9 my_ricker
+#hertzian_dipole: z 0.050 0.044 0.030 my_ricker
+#rx: 0.060 0.044 0.030
+#box: 0 0 0 0.100 0.040 0.060 half_space
+#cylinder: 0.050 0.020 0 0.050 0.020 0.060 0.006 pec
+#geometry_view: 0 0 0 0.100 0.080 0.060 0.002 0.002 0.002 view_n n
+#geometry_view: 0.010 0.010 0.004 0.090 0.070 0.052 0.004 0.002 0.008 view_sub n
+#geometry_view: 0.010 0.010 0.004 0.090 0.070 0.052 0.002 0.002 0.002 view_f f
+#snapshot: 0 0 0 0.100 0.080 0.060 0.002 0.002 0.002 20 snap_full
+#snapshot: 0.010 0.010 0.004 0.090 0.070 0.052 0.004 0.002 0.008 25 snap_sub
+'''
+
+
+@needs_ref
+def test_command_line_writes_identical_files(tmp_path):
+    """`python -m gprmax_b200 model.in` (CPU solve: no device here) with the streaming writers installed by the drop-in against
+    the same command with GPRMAX_B200_REF_WRITERS=1: every .vti / .vtp byte-identical."""
+    import subprocess
+    outs = {}
+    for mode in ('new', 'ref'):
+        d = tmp_path / mode
+        d.mkdir()
+        (d / 'model.in').write_text(MODEL)
+        env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS='2')
+        if mode == 'ref':
+            env['GPRMAX_B200_REF_WRITERS'] = '1'
+        r = subprocess.run([sys.executable, '-m', 'gprmax_b200', str(d / 'model.in')], env=env, cwd=str(d), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        files = {}
+        for base, _, names in os.walk(str(d)):
+            for n in names:
+                if n.endswith(('.vti', '.vtp')):
+                    with open(os.path.join(base, n), 'rb') as f:
+                        files[os.path.relpath(os.path.join(base, n), str(d))] = f.read()
+        outs[mode] = files
+    assert sorted(outs['new']) == sorted(outs['ref']) and len(outs['new']) == 5, sorted(outs['new'])
+    for name in outs['ref']:
+        assert outs['new'][name] == outs['ref'][name], name
