@@ -379,7 +379,7 @@ struct Solver : SolverBase {
     int n_he_chunks = 0;
     int launch_pair();
     unsigned zslabs_e = 0, zslabs_h = 0;  // z slabs (bit per slab) handled by k_pml_slabs on the v4 path
-    uint64_t graph_launches = 0;
+    uint64_t graph_launches = 0, graph_k_launches = 0;
     size_t smem_bytes;
     // device memory
     std::vector<void *> allocs;
@@ -459,7 +459,10 @@ struct Solver : SolverBase {
     // graph
     cudaGraphExec_t graph = nullptr;    // one iteration
     cudaGraphExec_t graph_k = nullptr;  // graph_iters iterations in one graph (fewer graph boundaries; small grids)
-    int graph_iters = 1;
+    int graph_iters = 16;
+    bool fuse_begin = true;             // GPB_FUSE_BEGIN=0: the step prologue stays a launch of its own inside the multi-iteration graph
+    bool use_pdl = true;                // GPB_PDL=0: no programmatic dependent launches inside the step (gpb_kernels.cuh)
+    bool pdl_on() const { return use_pdl && !linked; }
     bool use_graph = true;
     void drop_graphs()
     {
@@ -515,10 +518,10 @@ struct Solver : SolverBase {
     template <typename IDT>
     int launch_e(int p0, int p1);
     int launch_phase(int phase, int p0, int p1);
-    int launch_sources(int phase, int p0, int p1, int t0, int t1);
+    int launch_sources(int phase, int p0, int p1, int t0, int t1, bool begin_next = false);
     int launch_begin();
     int launch_snapshots();
-    int enqueue_step(bool with_snap);
+    int enqueue_step(bool with_snap, bool with_begin = true, bool begin_next = false);
     bool snapshot_due(int it) const
     {
         for (auto &s : snaps)
@@ -927,6 +930,8 @@ int Solver<R>::build(const gpb_model_t &m)
     idbytes = nmat <= 256 ? 1 : (nmat <= 65536 ? 2 : 4);
     if (getenv("GPB_ID_BYTES")) idbytes = std::max(idbytes, atoi(getenv("GPB_ID_BYTES")) >= 4 ? 4 : (atoi(getenv("GPB_ID_BYTES")) >= 2 ? 2 : 1));
     use_graph = !getenv("GPB_NO_GRAPH");
+    use_pdl = !(getenv("GPB_PDL") && atoi(getenv("GPB_PDL")) == 0);
+    if (getenv("GPB_FUSE_BEGIN")) fuse_begin = atoi(getenv("GPB_FUSE_BEGIN")) != 0;
     if (getenv("GPB_GRAPH_ITERS")) graph_iters = std::max(1, std::min(64, atoi(getenv("GPB_GRAPH_ITERS"))));
     // all six components in one allocation: the TMA kernels address a triple (E or H) as one 4-D tensor
     if (dalloc(&F[0], (size_t)narr * 6)) return 1;
@@ -1143,6 +1148,7 @@ int Solver<R>::launch_tma(int phase, int p0, int p1, int peer_store)
     a.sm_count = sm_count;
     a.sched = d_sched;
     a.stream = stream;
+    a.pdl = pdl_on() && !peer_store ? 1 : 0;
     p.progress = nullptr;
     p.peer1 = p.peer2 = nullptr;
     p.peer_plane = -1;
@@ -1201,8 +1207,8 @@ int Solver<R>::launch_h(int p0, int p1)
     p.p0 = p0; p.p1 = p1; p.xchunk = v4_xchunk;
     if (use_v4) {
         dim3 grid((unsigned)((plane / 4 + kThreadsV4 - 1) / kThreadsV4), (unsigned)((p1 - p0 + v4_xchunk - 1) / v4_xchunk));
-        if (tabsmem) k_update_h4<R, IDT, true><<<grid, kThreadsV4, smem_bytes, stream>>>(p);
-        else k_update_h4<R, IDT, false><<<grid, kThreadsV4, 0, stream>>>(p);
+        if (tabsmem) CK(launch_pdl(pdl_on(), k_update_h4<R, IDT, true>, grid, kThreadsV4, smem_bytes, stream, p));
+        else CK(launch_pdl(pdl_on(), k_update_h4<R, IDT, false>, grid, kThreadsV4, 0, stream, p));
         CK(cudaGetLastError());
         ++launches;
         if (zslabs_h) {
@@ -1213,15 +1219,15 @@ int Solver<R>::launch_h(int p0, int p1)
                     planes = std::max(planes, p.slab[s].hi[0] - p.slab[s].lo[0]);
                 }
             dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes, (unsigned)__builtin_popcount(zslabs_h));
-            k_pml_slabs<R, IDT><<<g2, 256, 0, stream>>>(p, 0, zslabs_h, p0, p1);
+            CK(launch_pdl(pdl_on(), k_pml_slabs<R, IDT>, g2, 256, 0, stream, p, 0, zslabs_h, p0, p1));
             CK(cudaGetLastError());
             ++launches;
         }
         return 0;
     }
     dim3 grid((unsigned)((plane + kThreads - 1) / kThreads), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
-    if (tabsmem) k_update_h<R, IDT, true><<<grid, kThreads, smem_bytes, stream>>>(p);
-    else k_update_h<R, IDT, false><<<grid, kThreads, 0, stream>>>(p);
+    if (tabsmem) CK(launch_pdl(pdl_on(), k_update_h<R, IDT, true>, grid, kThreads, smem_bytes, stream, p));
+    else CK(launch_pdl(pdl_on(), k_update_h<R, IDT, false>, grid, kThreads, 0, stream, p));
     CK(cudaGetLastError());
     ++launches;
     return 0;
@@ -1236,11 +1242,11 @@ int Solver<R>::launch_e(int p0, int p1)
     if (use_v4) {
         dim3 grid((unsigned)((plane / 4 + kThreadsV4 - 1) / kThreadsV4), (unsigned)((p1 - p0 + v4_xchunk - 1) / v4_xchunk));
         if (maxpoles) {
-            if (tabsmem) k_update_e4<R, IDT, true, true><<<grid, kThreadsV4, smem_bytes, stream>>>(p);
-            else k_update_e4<R, IDT, false, true><<<grid, kThreadsV4, 0, stream>>>(p);
+            if (tabsmem) CK(launch_pdl(pdl_on(), k_update_e4<R, IDT, true, true>, grid, kThreadsV4, smem_bytes, stream, p));
+            else CK(launch_pdl(pdl_on(), k_update_e4<R, IDT, false, true>, grid, kThreadsV4, 0, stream, p));
         } else {
-            if (tabsmem) k_update_e4<R, IDT, true, false><<<grid, kThreadsV4, smem_bytes, stream>>>(p);
-            else k_update_e4<R, IDT, false, false><<<grid, kThreadsV4, 0, stream>>>(p);
+            if (tabsmem) CK(launch_pdl(pdl_on(), k_update_e4<R, IDT, true, false>, grid, kThreadsV4, smem_bytes, stream, p));
+            else CK(launch_pdl(pdl_on(), k_update_e4<R, IDT, false, false>, grid, kThreadsV4, 0, stream, p));
         }
         CK(cudaGetLastError());
         ++launches;
@@ -1252,7 +1258,7 @@ int Solver<R>::launch_e(int p0, int p1)
                     planes = std::max(planes, p.slab[s].hi[0] - p.slab[s].lo[0]);
                 }
             dim3 g2((unsigned)((cells + 255) / 256), (unsigned)planes, (unsigned)__builtin_popcount(zslabs_e));
-            k_pml_slabs<R, IDT><<<g2, 256, 0, stream>>>(p, 1, zslabs_e, p0, p1);
+            CK(launch_pdl(pdl_on(), k_pml_slabs<R, IDT>, g2, 256, 0, stream, p, 1, zslabs_e, p0, p1));
             CK(cudaGetLastError());
             ++launches;
         }
@@ -1260,11 +1266,11 @@ int Solver<R>::launch_e(int p0, int p1)
     }
     dim3 grid((unsigned)((plane + kThreads - 1) / kThreads), (unsigned)((p1 - p0 + kXChunk - 1) / kXChunk));
     if (maxpoles) {
-        if (tabsmem) k_update_e<R, IDT, true, true><<<grid, kThreads, smem_bytes, stream>>>(p);
-        else k_update_e<R, IDT, false, true><<<grid, kThreads, 0, stream>>>(p);
+        if (tabsmem) CK(launch_pdl(pdl_on(), k_update_e<R, IDT, true, true>, grid, kThreads, smem_bytes, stream, p));
+        else CK(launch_pdl(pdl_on(), k_update_e<R, IDT, false, true>, grid, kThreads, 0, stream, p));
     } else {
-        if (tabsmem) k_update_e<R, IDT, true, false><<<grid, kThreads, smem_bytes, stream>>>(p);
-        else k_update_e<R, IDT, false, false><<<grid, kThreads, 0, stream>>>(p);
+        if (tabsmem) CK(launch_pdl(pdl_on(), k_update_e<R, IDT, true, false>, grid, kThreads, smem_bytes, stream, p));
+        else CK(launch_pdl(pdl_on(), k_update_e<R, IDT, false, false>, grid, kThreads, 0, stream, p));
     }
     CK(cudaGetLastError());
     ++launches;
@@ -1287,21 +1293,29 @@ int Solver<R>::launch_phase(int phase, int p0, int p1)
 }
 
 template <typename R>
-int Solver<R>::launch_sources(int phase, int p0, int p1, int t0, int t1)
+int Solver<R>::launch_sources(int phase, int p0, int p1, int t0, int t1, bool begin_next)
 {
-    // point sources on the owned planes [p0, p1) and transmission lines on the owned planes [t0, t1) (local indices)
-    if (phase == 0 ? !has_hsrc : !has_esrc) return 0;
+    // point sources on the owned planes [p0, p1) and transmission lines on the owned planes [t0, t1) (local indices);
+    // begin_next (electric phase, inside a multi-iteration graph): the next iteration's prologue rides in the same launch
+    if (phase == 0 ? !has_hsrc : !has_esrc) return begin_next ? launch_begin() : 0;
     const int i_lo = x_start + p0, i_hi = x_start + p1, tl_lo = x_start + t0, tl_hi = x_start + t1;
     // (host copy of the source planes: no launch when nothing of this phase lies in the ranges)
     bool tl_any = false, src_any = false;
     for (int t = 0; t < ntl; ++t) tl_any = tl_any || (h_tls[t].i >= tl_lo && h_tls[t].i < tl_hi);
     for (size_t q = 0; q < h_src_plane.size(); ++q)
         src_any = src_any || (h_src_phase[q] == phase && h_src_plane[q] >= i_lo && h_src_plane[q] < i_hi);
-    if (!src_any && !tl_any) return 0;
+    if (!src_any && !tl_any) return begin_next ? launch_begin() : 0;
     const int ntl_ = tl_any ? ntl : 0;
-    if (idbytes == 1) k_sources<R, uint8_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi);
-    else if (idbytes == 2) k_sources<R, uint16_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi);
-    else k_sources<R, uint32_t><<<1, 32, 0, stream>>>(pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi);
+    if (begin_next) {
+        if (idbytes == 1) CK(launch_pdl(pdl_on(), k_sources_begin<R, uint8_t>, 1, 128, 0, stream, pp, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi, d_iter, d_iter + 1, nrx, d_rxc, d_rxs, ntl));
+        else if (idbytes == 2) CK(launch_pdl(pdl_on(), k_sources_begin<R, uint16_t>, 1, 128, 0, stream, pp, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi, d_iter, d_iter + 1, nrx, d_rxc, d_rxs, ntl));
+        else CK(launch_pdl(pdl_on(), k_sources_begin<R, uint32_t>, 1, 128, 0, stream, pp, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi, d_iter, d_iter + 1, nrx, d_rxc, d_rxs, ntl));
+        ++launches;
+        return 0;
+    }
+    if (idbytes == 1) CK(launch_pdl(pdl_on(), k_sources<R, uint8_t>, 1, 32, 0, stream, pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi));
+    else if (idbytes == 2) CK(launch_pdl(pdl_on(), k_sources<R, uint16_t>, 1, 32, 0, stream, pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi));
+    else CK(launch_pdl(pdl_on(), k_sources<R, uint32_t>, 1, 32, 0, stream, pp, phase, nsrc, d_srcs, ntl_, d_tls, i_lo, i_hi, tl_lo, tl_hi));
     CK(cudaGetLastError());
     ++launches;
     return 0;
@@ -1310,7 +1324,7 @@ int Solver<R>::launch_sources(int phase, int p0, int p1, int t0, int t1)
 template <typename R>
 int Solver<R>::launch_begin()
 {
-    k_step_begin<R><<<1, 128, 0, stream>>>(pp, d_iter, d_iter + 1, nrx, d_rxc, d_rxs, ntl, d_tls);
+    CK(launch_pdl(pdl_on(), k_step_begin<R>, 1, 128, 0, stream, pp, d_iter, d_iter + 1, nrx, d_rxc, d_rxs, ntl, d_tls));
     CK(cudaGetLastError());
     ++launches;
     return 0;
@@ -1331,19 +1345,20 @@ int Solver<R>::launch_snapshots()
 }
 
 template <typename R>
-int Solver<R>::enqueue_step(bool with_snap)
+int Solver<R>::enqueue_step(bool with_snap, bool with_begin, bool begin_next)
 {
-    // model_build_run.py:590-696 in order
-    if (launch_begin()) return 1;
+    // model_build_run.py:590-696 in order.  Inside the multi-iteration graph the prologue of every iteration but the first is
+    // part of the previous iteration's last launch (with_begin = false there, begin_next = true on all but the last)
+    if (with_begin && launch_begin()) return 1;
     if (with_snap && launch_snapshots()) return 1;
     if (pair_he && !has_hsrc) {
         if (launch_pair()) return 1;
-        return launch_sources(1, 0, nplanes, 0, nplanes);
+        return launch_sources(1, 0, nplanes, 0, nplanes, begin_next);
     }
     if (launch_phase(0, 0, nplanes)) return 1;
     if (launch_sources(0, 0, nplanes, 0, nplanes)) return 1;
     if (launch_phase(1, 0, nplanes)) return 1;
-    if (launch_sources(1, 0, nplanes, 0, nplanes)) return 1;
+    if (launch_sources(1, 0, nplanes, 0, nplanes, begin_next)) return 1;
     return 0;
 }
 
@@ -1705,31 +1720,27 @@ int Solver<R>::begin_run(int n)
 {
     CK(cudaSetDevice(device));
     if (n < 0 || iteration + n > iterations) return fail("cannot run %d iterations from %d: model has %d", n, iteration, iterations);
-    if (use_graph && !graph && n > 1 && !(coop && !ntl && !linked)) {
-        // the step is identical every iteration (the iteration index lives on the device), so it is
-        // captured once and replayed: one graph launch per time step instead of 4-6 kernel launches
-        cudaGraph_t g = nullptr;
-        const uint64_t l0 = launches;
-        CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        int rc = linked ? enqueue_linked_step(false) : enqueue_step(false);
-        cudaError_t e = cudaStreamEndCapture(stream, &g);
-        graph_launches = launches - l0;
-        launches = l0;
-        if (rc) return 1;
-        if (e != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(e));
-        CK(cudaGraphInstantiate(&graph, g, 0));
-        cudaGraphDestroy(g);
-        if (!linked && graph_iters > 1 && n >= graph_iters) {
-            // the same step graph_iters times in one graph: the launches inside a graph follow each other more closely than
-            // two graph launches do, which is what a small grid's iteration consists of
-            g = nullptr;
+    if (use_graph && n > 1 && !(coop && !ntl && !linked)) {
+        // the step is identical every iteration (the iteration index lives on the device), so it is captured once and replayed:
+        // one graph launch per time step instead of 4-6 kernel launches -- and, for unlinked solvers, a second graph that holds
+        // graph_iters steps: launches inside a graph follow each other more closely than two graph launches do (measured with
+        // 16 steps per graph: 2-D A-scan 18.4 -> 17.6, 100^3 53.3 -> 50.8, 300^3 436.5 -> 433.6 us per iteration)
+        for (int k = 0; k < 2; ++k) {
+            cudaGraphExec_t &target = k == 0 ? graph : graph_k;
+            const int steps = k == 0 ? 1 : graph_iters;
+            if (target || (k == 1 && (linked || graph_iters < 2 || n < graph_iters))) continue;
+            cudaGraph_t g = nullptr;
+            const uint64_t l0 = launches;
             CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-            for (int q = 0; q < graph_iters && !rc; ++q) rc = enqueue_step(false);
-            e = cudaStreamEndCapture(stream, &g);
+            int rc = 0;
+            for (int q = 0; q < steps && !rc; ++q)
+                rc = linked ? enqueue_linked_step(false) : (k == 0 ? enqueue_step(false) : enqueue_step(false, q == 0, fuse_begin && q + 1 < steps));
+            cudaError_t e = cudaStreamEndCapture(stream, &g);
+            (k == 0 ? graph_launches : graph_k_launches) = launches - l0;
             launches = l0;
-            if (rc) return 1;
+            if (rc) { if (g) cudaGraphDestroy(g); return 1; }
             if (e != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(e));
-            CK(cudaGraphInstantiate(&graph_k, g, 0));
+            CK(cudaGraphInstantiate(&target, g, 0));
             cudaGraphDestroy(g);
         }
     }
@@ -1765,7 +1776,7 @@ int Solver<R>::enqueue_iterations(int n)
             for (int q = 0; q < graph_iters; ++q) snap = snap || snapshot_due(iteration + q);
             if (!snap) {
                 CK(cudaGraphLaunch(graph_k, stream));
-                launches += graph_launches * graph_iters;
+                launches += graph_k_launches;
                 iteration += graph_iters;
                 s += graph_iters - 1;
                 continue;

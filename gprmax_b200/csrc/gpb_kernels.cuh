@@ -27,6 +27,33 @@
 
 namespace gpb {
 
+// Programmatic dependent launch (GPB_PDL=0 switches it off): a kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream is still draining -- every CTA of the predecessor has passed
+// pdl_launch_dependents() or exited -- and runs its prologue (shared-memory tables, barrier set-up, descriptor prefetch) there;
+// pdl_wait() returns once the predecessor has completed and its writes are visible.  EVERY kernel of the time step calls
+// pdl_wait() in every CTA before its first access to anything a predecessor writes (fields, Phi, T, iteration counter, work
+// queue) and before it exits, so that "kernel N complete" still implies "kernels < N complete".  Both instructions are no-ops
+// in a kernel that was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Launch `kern` with or without the programmatic-stream-serialization attribute (host side of the above).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 constexpr int kThreads = 256;
 constexpr int kXChunk = 16;
 constexpr int kMaxSlabs = 6;
@@ -274,6 +301,7 @@ template <typename R, typename IDT, bool TABSMEM>
 __global__ void __launch_bounds__(kThreads) k_update_h(const PhaseParams<R> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();
     const Coef4<R> *coef = p.coef;
     const R *srcm = p.src;
     if (TABSMEM) {
@@ -283,6 +311,7 @@ __global__ void __launch_bounds__(kThreads) k_update_h(const PhaseParams<R> p)
         coef = scoef;
         srcm = ssrc;
     }
+    pdl_wait();   // the coefficient tables staged above are constant during a run
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int j = (int)(idx / p.pitch);
     const int k = (int)(idx - (long long)j * p.pitch);
@@ -435,6 +464,7 @@ template <typename R, typename IDT, bool TABSMEM, bool DISP>
 __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();
     const Coef4<R> *coef = p.coef;
     const R *srce = p.src;
     if (TABSMEM) {
@@ -444,6 +474,7 @@ __global__ void __launch_bounds__(kThreads) k_update_e(const PhaseParams<R> p)
         coef = scoef;
         srce = ssrc;
     }
+    pdl_wait();   // the coefficient tables staged above are constant during a run
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int j = (int)(idx / p.pitch);
     const int k = (int)(idx - (long long)j * p.pitch);
@@ -619,8 +650,8 @@ __device__ __forceinline__ R current_at(const PointParams<R> &p, int comp, int i
 // Step prologue: receiver gather (fields_outputs.py:40-64 / :81-105), transmission-line totals
 // (:62-64) and the device iteration counter.  One block; `next` is bumped after every thread read it.
 template <typename R>
-__global__ void k_step_begin(PointParams<R> p, int *iter_cur, int *iter_next, int nrx, const int *rxc, R *rxs,
-                             int ntl, const TLDev<R> *tls)
+__device__ __forceinline__ void step_begin_body(const PointParams<R> &p, int *iter_cur, int *iter_next, int nrx, const int *rxc, R *rxs,
+                                                int ntl, const TLDev<R> *tls)
 {
     const int it = *iter_next;
     if (it < p.iterations) {
@@ -644,17 +675,26 @@ __global__ void k_step_begin(PointParams<R> p, int *iter_cur, int *iter_next, in
     }
 }
 
+template <typename R>
+__global__ void k_step_begin(PointParams<R> p, int *iter_cur, int *iter_next, int nrx, const int *rxc, R *rxs,
+                             int ntl, const TLDev<R> *tls)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    step_begin_body(p, iter_cur, iter_next, nrx, rxc, rxs, ntl, tls);
+}
+
 // Sources of one phase, applied in array order by a single thread each (order between different
 // sources only matters when two sit on the same edge; then the serial loop keeps the CPU order).
 // phase 0 (after H update + H-PML): transmission lines (current), magnetic dipoles   model_build_run.py:440-442
 // phase 1 (after E update + E-PML): voltage sources, transmission lines (voltage), Hertzian dipoles  :458-461
 template <typename R, typename IDT>
-__global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R> *srcs, int ntl, const TLDev<R> *tls, int i_lo, int i_hi, int tl_lo, int tl_hi)
+__device__ __forceinline__ void sources_body(const PointParams<R> &p, int phase, int nsrc, const SrcDev<R> *srcs, int ntl, const TLDev<R> *tls,
+                                             int i_lo, int i_hi, int tl_lo, int tl_hi)
 {
-    // [i_lo, i_hi): global planes whose point sources this launch applies (a sharded half-step applies the sources of its
-    // boundary plane before that plane is sent to the neighbour); [tl_lo, tl_hi): planes whose transmission lines it advances
-    // (a line belongs to exactly one plane, so every line is advanced by exactly one launch per phase)
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    // (one thread) [i_lo, i_hi): global planes whose point sources this launch applies (a sharded half-step applies the sources
+    // of its boundary plane before that plane is sent to the neighbour); [tl_lo, tl_hi): planes whose transmission lines it
+    // advances (a line belongs to exactly one plane, so every line is advanced by exactly one launch per phase)
     const int it = *p.iter;
     if (phase == 0) {
         for (int t = 0; t < ntl; ++t) {
@@ -713,6 +753,28 @@ __global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R>
             p.F[sc.pol][o] -= p.srcE[m] * sc.wave[it] * sc.f1 * sc.f2;
         }
     }
+}
+
+template <typename R, typename IDT>
+__global__ void k_sources(PointParams<R> p, int phase, int nsrc, const SrcDev<R> *srcs, int ntl, const TLDev<R> *tls, int i_lo, int i_hi, int tl_lo, int tl_hi)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    sources_body<R, IDT>(p, phase, nsrc, srcs, ntl, tls, i_lo, i_hi, tl_lo, tl_hi);
+}
+
+// The electric-phase sources of iteration n and the step prologue of iteration n+1 in one launch (one block): between two
+// iterations inside a multi-iteration graph nothing else happens, and a kernel boundary costs 2-3 us.
+template <typename R, typename IDT>
+__global__ void k_sources_begin(PointParams<R> p, int nsrc, const SrcDev<R> *srcs, int ntl_src, const TLDev<R> *tls, int i_lo, int i_hi, int tl_lo, int tl_hi,
+                                int *iter_cur, int *iter_next, int nrx, const int *rxc, R *rxs, int ntl)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    if (threadIdx.x == 0) sources_body<R, IDT>(p, 1, nsrc, srcs, ntl_src, tls, i_lo, i_hi, tl_lo, tl_hi);
+    __syncthreads();   // the receivers below may sample the edges the sources just wrote
+    step_begin_body(p, iter_cur, iter_next, nrx, rxc, rxs, ntl, tls);
 }
 
 // Snapshot: strided cell-centred averages (snapshots.py:87-130, snapshots_ext.pyx:56-80).

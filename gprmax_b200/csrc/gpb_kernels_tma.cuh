@@ -304,6 +304,7 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
     const int tid = threadIdx.x, lane = tid & 31;
     const int W = tiles * (nchunks + nsplit);
 
+    pdl_launch_dependents();
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full + s, 1);
@@ -334,6 +335,9 @@ k_update_tma(const PhaseParams<R> p, const __grid_constant__ TmaMaps4 maps, int 
         }
     }
     __syncthreads();
+    // everything above reads tables that are constant during a run; from here on the kernel touches what its predecessor in the
+    // stream wrote (the work queue it re-armed, fields, Phi, T)
+    pdl_wait();
 
     // ---------------- producer: one slot of the CTA's slot sequence per call (3 TMA instructions per plane)
     int p_item = -1, p_n = -1, p_q = 0, p_g = 0;   // item being loaded, its next plane (-1 = x-neighbour slot), item ordinal, slot

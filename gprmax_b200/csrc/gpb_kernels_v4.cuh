@@ -269,6 +269,7 @@ template <typename R, typename IDT, bool TABSMEM>
 __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(const PhaseParams<R> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();
     const Coef4<R> *coef = p.coef;
     const R *srcm = p.src;
     if (TABSMEM) {
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_h4(cons
         coef = scoef;
         srcm = ssrc;
     }
+    pdl_wait();   // the coefficient tables staged above are constant during a run
     h4_body<R, IDT, true>(p, coef, srcm, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
 }
 
@@ -466,6 +468,7 @@ template <typename R, typename IDT, bool TABSMEM, bool DISP>
 __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(const PhaseParams<R> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_launch_dependents();
     const Coef4<R> *coef = p.coef;
     const R *srce = p.src;
     if (TABSMEM) {
@@ -475,6 +478,7 @@ __global__ void __launch_bounds__(kThreadsV4, GPB_V4_MINBLOCKS) k_update_e4(cons
         coef = scoef;
         srce = ssrc;
     }
+    pdl_wait();   // the coefficient tables staged above are constant during a run
     e4_body<R, IDT, DISP, true>(p, coef, srce, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
 }
 
@@ -527,6 +531,8 @@ __device__ __forceinline__ void pml_slab_cell(const PhaseParams<R> &p, int phase
 template <typename R, typename IDT>
 __global__ void __launch_bounds__(256) k_pml_slabs(const PhaseParams<R> p, int phase, unsigned slabsel, int p0, int p1)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     // blockIdx.z selects the n-th slab of `slabsel`: the slabs run side by side instead of back to back
     int s = -1;
     for (int q = 0, n = 0; q < p.nslabs; ++q)

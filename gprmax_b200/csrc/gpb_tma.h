@@ -33,6 +33,7 @@ struct TmaLaunch {
     int sm_count;
     int *sched;               // [2] work-item scheduler state
     cudaStream_t stream;
+    int pdl;                  // launch with the programmatic-stream-serialization attribute (gpb_kernels.cuh: launch_pdl)
 };
 
 // PV = 2 * formulation + order - 1.  Returns 0, or 1 with *err filled.

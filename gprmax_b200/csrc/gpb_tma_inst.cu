@@ -70,11 +70,13 @@ static int tma_launch_cfg(const TmaLaunch<R> &a, std::string *err)
     if (a.phase == 0) {
         auto kern = k_update_tma<R, IDT, TY, TZ, S, 0, PW, PV>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return tma_fail(err, "cudaFuncSetAttribute", e);
-        kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, nsplit, a.sched);
+        if ((e = launch_pdl(a.pdl != 0, kern, grid, dim3(TY * TZ / 4 + 32 * PW), smem, a.stream, p, *a.maps, tiles_k, tiles, nchunks, nsplit, a.sched)) != cudaSuccess)
+            return tma_fail(err, "k_update_tma launch", e);
     } else {
         auto kern = k_update_tma<R, IDT, TY, TZ, S, 1, PW, PV, DISP>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return tma_fail(err, "cudaFuncSetAttribute", e);
-        kern<<<grid, TY * TZ / 4 + 32 * PW, smem, a.stream>>>(p, *a.maps, tiles_k, tiles, nchunks, nsplit, a.sched);
+        if ((e = launch_pdl(a.pdl != 0, kern, grid, dim3(TY * TZ / 4 + 32 * PW), smem, a.stream, p, *a.maps, tiles_k, tiles, nchunks, nsplit, a.sched)) != cudaSuccess)
+            return tma_fail(err, "k_update_tma launch", e);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return tma_fail(err, "k_update_tma launch", e);
     return 0;

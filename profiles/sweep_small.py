@@ -10,7 +10,7 @@ import numpy as np
 from gprmax_b200 import Solver, load_model
 from benchkit.synthetic import bench_model
 
-SWITCHES = ('GPB_GRAPH_ITERS', 'GPB_V4_XCHUNK', 'GPB_NO_TMA', 'GPB_FORCE_TMA', 'GPB_TMA_XCHUNK', 'GPB_TMA_TZ', 'GPB_TMA_TY', 'GPB_NO_GRAPH')
+SWITCHES = ('GPB_PDL', 'GPB_FUSE_BEGIN', 'GPB_GRAPH_ITERS', 'GPB_V4_XCHUNK', 'GPB_NO_TMA', 'GPB_FORCE_TMA', 'GPB_TMA_XCHUNK', 'GPB_TMA_TZ', 'GPB_TMA_TY', 'GPB_NO_GRAPH')
 
 
 def run(G, env, reference=None):
@@ -37,23 +37,25 @@ def run(G, env, reference=None):
 def main():
     t00 = time.time()
     budget = float(os.environ.get('SWEEP_SECONDS', '100'))
-    graph = [{'GPB_GRAPH_ITERS': '4'}, {'GPB_GRAPH_ITERS': '16'}, {'GPB_NO_GRAPH': '1'}]
-    v4 = [{'GPB_V4_XCHUNK': '2'}, {'GPB_V4_XCHUNK': '4'}, {'GPB_V4_XCHUNK': '8'}, {'GPB_V4_XCHUNK': '4', 'GPB_GRAPH_ITERS': '16'}]
-    plan = [
-        ('cylinder_Ascan_2D_f32', graph + v4),
-        ('bench:100', graph + v4 + [{'GPB_FORCE_TMA': '1'}, {'GPB_FORCE_TMA': '1', 'GPB_GRAPH_ITERS': '16'}]),
-        ('bench:150', graph + [{'GPB_NO_TMA': '1'}, {'GPB_NO_TMA': '1', 'GPB_V4_XCHUNK': '8'}, {'GPB_TMA_XCHUNK': '2'}, {'GPB_TMA_XCHUNK': '8'}, {'GPB_TMA_TZ': '64', 'GPB_TMA_TY': '16'}]),
-        ('bench:200', graph[:2] + [{'GPB_NO_TMA': '1'}, {'GPB_TMA_XCHUNK': '4'}, {'GPB_TMA_XCHUNK': '16'}]),
-        ('heterogeneous_soil_full_f32', graph[:2] + [{'GPB_TMA_XCHUNK': '4'}]),
-        ('bench:300', graph[:2]),
-    ]
+    plan_name = os.environ.get('SWEEP_PLAN', 'pdl')
+    graph = [{'GPB_GRAPH_ITERS': '1'}, {'GPB_GRAPH_ITERS': '4'}, {'GPB_NO_GRAPH': '1'}]
+    v4 = [{'GPB_V4_XCHUNK': '2'}, {'GPB_V4_XCHUNK': '4'}, {'GPB_V4_XCHUNK': '8'}]
+    pdl = [{'GPB_FUSE_BEGIN': '0'}, {'GPB_PDL': '0'}, {'GPB_PDL': '0', 'GPB_GRAPH_ITERS': '1'}]
+    if plan_name == 'pdl':
+        plan = [(m, pdl) for m in ('cylinder_Ascan_2D_f32', 'bench:100', 'bench:150', 'bench:200', 'bench:300', 'heterogeneous_soil_full_f32', 'transmission_line_f32')]
+    else:
+        plan = [
+            ('cylinder_Ascan_2D_f32', graph + v4),
+            ('bench:100', graph + v4 + [{'GPB_FORCE_TMA': '1'}]),
+            ('bench:150', graph + [{'GPB_NO_TMA': '1'}, {'GPB_NO_TMA': '1', 'GPB_V4_XCHUNK': '8'}, {'GPB_TMA_XCHUNK': '2'}, {'GPB_TMA_XCHUNK': '8'}, {'GPB_TMA_TZ': '64', 'GPB_TMA_TY': '16'}]),
+            ('bench:200', graph[:2] + [{'GPB_NO_TMA': '1'}, {'GPB_TMA_XCHUNK': '4'}, {'GPB_TMA_XCHUNK': '16'}]),
+            ('bench:300', graph[:2]),
+        ]
     for spec, envs in plan:
         if spec.startswith('bench:'):
             G = bench_model(int(spec[6:]), iterations=300)
         else:
             G, _ = load_model('tests/golden/' + spec + '.npz')
-            if G.iterations > 700:
-                G.iterations = 700
         base, ref = run(G, {})
         base['model'] = spec
         print(json.dumps(base), flush=True)

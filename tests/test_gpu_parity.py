@@ -98,6 +98,48 @@ def test_restart_and_chunked_run_bit_identical():
     assert np.array_equal(a, b)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['sources_mixed', 'transmission_line', 'snapshots', 'pml_MRIPML_2', 'hertzian_dipole_dispersive'])
+def test_launch_side_switches_bit_identical(name, monkeypatch):
+    """How the step is launched does not change a bit of the result: programmatic dependent launches on / off (GPB_PDL),
+    16 / 5 / 1 iterations per CUDA graph (GPB_GRAPH_ITERS; with more than one the electric-phase sources and the next
+    iteration's prologue share a launch unless GPB_FUSE_BEGIN=0), plain launches (GPB_NO_GRAPH), each on the register-vectorised
+    and on the TMA kernels, run in one piece and in ragged chunks (snapshot iterations leave the graph)."""
+    from gprmax_b200 import Solver
+    from gprmax_b200.model_io import load_model
+    G, _ = load_model(golden_path(name, 'f32'))
+
+    def run(env, chunks=None):
+        for k in ('GPB_PDL', 'GPB_GRAPH_ITERS', 'GPB_FUSE_BEGIN', 'GPB_NO_GRAPH', 'GPB_FORCE_TMA'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Solver(G, device_id=0) as sv:
+            if chunks:
+                done = 0
+                for n in chunks:
+                    n = min(n, G.iterations - done)
+                    sv.run(n)
+                    done += n
+                sv.run(G.iterations - done)
+            else:
+                sv.run()
+            out = [sv.receivers()] + [np.stack(sv.snapshot(q)) for q in range(len(G.snapshots))]
+            out += [np.stack(sv.tline(q)) for q in range(len(G.transmissionlines))]
+        return out
+
+    ref = run({'GPB_PDL': '0', 'GPB_NO_GRAPH': '1'})
+    for tma in ({}, {'GPB_FORCE_TMA': '1'}):
+        base = run(dict(tma, GPB_PDL='0', GPB_NO_GRAPH='1'))
+        for env, chunks in (({}, None), ({}, (1, 17, 3, 40, 16, 33)), ({'GPB_PDL': '0'}, None), ({'GPB_GRAPH_ITERS': '1'}, None),
+                            ({'GPB_GRAPH_ITERS': '5'}, (7, 23)), ({'GPB_FUSE_BEGIN': '0'}, None), ({'GPB_NO_GRAPH': '1'}, None)):
+            got = run(dict(tma, **env), chunks)
+            assert len(got) == len(base)
+            for a, b in zip(got, base):
+                assert np.array_equal(a, b), (name, tma, env, chunks)
+    assert len(ref) == len(base)
+
+
 def test_config2_bench_300_full_trace():
     """BASELINE.json configs[1], the headline benchmark at its own size: tests/benchmarking/bench_300x300x300.in, all 1559
     iterations, against the trace of the unmodified reference CPU solver (tests/golden/make_golden.py `bench_300_trace`, float32
