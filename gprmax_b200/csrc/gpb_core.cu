@@ -1734,7 +1734,7 @@ int Solver<R>::begin_run(int n)
             CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
             int rc = 0;
             for (int q = 0; q < steps && !rc; ++q)
-                rc = linked ? enqueue_linked_step(false) : (k == 0 ? enqueue_step(false) : enqueue_step(false, q == 0, fuse_begin && q + 1 < steps));
+                rc = linked ? enqueue_linked_step(false) : (k == 0 ? enqueue_step(false) : enqueue_step(false, q == 0 || !fuse_begin, fuse_begin && q + 1 < steps));
             cudaError_t e = cudaStreamEndCapture(stream, &g);
             (k == 0 ? graph_launches : graph_k_launches) = launches - l0;
             launches = l0;
