@@ -19,7 +19,7 @@ RX_ROWS = ['Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz', 'Ix', 'Iy', 'Iz']
 SYMBOLS = ['gpb_device_count', 'gpb_device_info', 'gpb_create', 'gpb_destroy', 'gpb_run', 'gpb_iteration',
            'gpb_elapsed_seconds', 'gpb_mem_used', 'gpb_kernel_launches', 'gpb_reset', 'gpb_set_points', 'gpb_profile', 'gpb_kernel_path', 'gpb_half_step', 'gpb_halo',
            'gpb_stream', 'gpb_synchronize', 'gpb_create_sharded', 'gpb_link_info', 'gpb_link', 'gpb_get_receivers', 'gpb_get_snapshot', 'gpb_get_tline',
-           'gpb_get_field', 'gpb_set_field', 'gpb_release_cached', 'gpb_ids_scan', 'gpb_ids_apply', 'gpb_vtk_transpose', 'gpb_last_error', 'gpb_version']
+           'gpb_get_field', 'gpb_set_field', 'gpb_release_cached', 'gpb_ids_scan', 'gpb_ids_apply', 'gpb_ids_scan_slab', 'gpb_ids_apply_slab', 'gpb_vtk_transpose', 'gpb_last_error', 'gpb_version']
 
 
 class DeviceInfo(C.Structure):
@@ -107,6 +107,8 @@ def lib():
     P = C.c_void_p
     L.gpb_ids_scan.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(IdCombo), C.c_int, C.POINTER(C.c_int)]
     L.gpb_ids_apply.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(IdCombo), P, C.c_int]
+    L.gpb_ids_scan_slab.argtypes = [P, P, P, P] + [C.c_int] * 9 + [C.POINTER(IdCombo), C.c_int, C.POINTER(C.c_int)]
+    L.gpb_ids_apply_slab.argtypes = [P, P, P, P] + [C.c_int] * 9 + [C.POINTER(IdCombo), P, C.c_int]
     L.gpb_vtk_transpose.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), P]
     L.gpb_destroy.argtypes = [H]
     L.gpb_run.argtypes = [H, C.c_int]

@@ -32,11 +32,20 @@ struct Grid {
     const int8_t *rigidE;    // [12][nx][ny][nz]
     const int8_t *rigidH;    // [6][nx][ny][nz]
     uint32_t *ID;            // [6][nx+1][ny+1][nz+1]
-    int nx, ny, nz;
-    size_t cell(int i, int j, int k) const { return ((size_t)i * ny + j) * nz + k; }
-    size_t node(int c, int i, int j, int k) const { return (((size_t)c * (nx + 1) + i) * (ny + 1) + j) * (nz + 1) + k; }
-    bool rE(int q, int i, int j, int k) const { return rigidE[(size_t)q * nx * ny * nz + cell(i, j, k)] != 0; }
-    bool rH(int q, int i, int j, int k) const { return rigidH[(size_t)q * nx * ny * nz + cell(i, j, k)] != 0; }
+    int nx, ny, nz;          // the whole domain
+    // a slab-local build holds only a range of x planes of every array: cell planes [sx0, sx0 + snx) of solid / rigidE / rigidH,
+    // node planes [ix0, ix0 + inx) of ID (whole arrays: 0, nx and 0, nx + 1); i, j, k below are always global indices
+    int sx0, snx, ix0, inx;
+    size_t cell(int i, int j, int k) const { return ((size_t)(i - sx0) * ny + j) * nz + k; }
+    size_t node(int c, int i, int j, int k) const { return (((size_t)c * inx + (i - ix0)) * (ny + 1) + j) * (nz + 1) + k; }
+    bool rE(int q, int i, int j, int k) const { return rigidE[(size_t)q * snx * ny * nz + cell(i, j, k)] != 0; }
+    bool rH(int q, int i, int j, int k) const { return rigidH[(size_t)q * snx * ny * nz + cell(i, j, k)] != 0; }
+    // planes [x0, x1) can be built from these arrays: the edges of node plane i look at the cell planes i - 1 and i
+    bool covers(int x0, int x1) const
+    {
+        if (x1 <= x0) return true;
+        return x0 >= ix0 && x1 <= ix0 + inx && sx0 <= std::max(x0 - 1, 0) && sx0 + snx >= std::min(x1, nx);
+    }
     // yee_cell_setget_rigid_ext.pyx:24-66, 108-138 (loop ranges keep every index inside the arrays)
     bool rigid(int comp, int i, int j, int k) const
     {
@@ -115,11 +124,9 @@ void parallel_planes(int x0, int x1, F f)
 
 extern "C" {
 
-int gpb_ids_scan(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
-                 gpb_idcombo_t *combos, int max_combos, int *ncombos)
+static int ids_scan(const Grid &g, int x0, int x1, gpb_idcombo_t *combos, int max_combos, int *ncombos)
 {
-    if (!solid || !rigidE || !rigidH || !ID || !combos || !ncombos || nx < 1 || ny < 1 || nz < 1 || x0 < 0 || x1 > nx + 1 || x1 < x0) return 1;
-    const Grid g{solid, rigidE, rigidH, ID, nx, ny, nz};
+    uint32_t *ID = g.ID;
     const int nt = std::max(1, std::min(host_threads(), std::max(1, x1 - x0)));
     std::vector<std::map<Key, Pos>> found(nt);
     parallel_planes(x0, x1, [&](int t, int a, int b) {
@@ -168,11 +175,9 @@ int gpb_ids_scan(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigi
     return 0;
 }
 
-int gpb_ids_apply(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
-                  const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos)
+static int ids_apply(const Grid &g, int x0, int x1, const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos)
 {
-    if (!solid || !rigidE || !rigidH || !ID || (ncombos && (!combos || !numid)) || x0 < 0 || x1 > nx + 1 || x1 < x0) return 1;
-    const Grid g{solid, rigidE, rigidH, ID, nx, ny, nz};
+    uint32_t *ID = g.ID;
     std::map<Key, uint32_t> table;
     for (int q = 0; q < ncombos; ++q) {
         Key k{combos[q].comp, {combos[q].id[0], combos[q].id[1], combos[q].id[2], combos[q].id[3]}};
@@ -207,6 +212,38 @@ int gpb_ids_apply(const uint32_t *solid, const int8_t *rigidE, const int8_t *rig
         }
     });
     return missing ? 3 : 0;
+}
+
+int gpb_ids_scan(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
+                 gpb_idcombo_t *combos, int max_combos, int *ncombos)
+{
+    if (!solid || !rigidE || !rigidH || !ID || !combos || !ncombos || nx < 1 || ny < 1 || nz < 1 || x0 < 0 || x1 > nx + 1 || x1 < x0) return 1;
+    return ids_scan(Grid{solid, rigidE, rigidH, ID, nx, ny, nz, 0, nx, 0, nx + 1}, x0, x1, combos, max_combos, ncombos);
+}
+
+int gpb_ids_apply(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
+                  const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos)
+{
+    if (!solid || !rigidE || !rigidH || !ID || (ncombos && (!combos || !numid)) || nx < 1 || ny < 1 || nz < 1 || x0 < 0 || x1 > nx + 1 || x1 < x0) return 1;
+    return ids_apply(Grid{solid, rigidE, rigidH, ID, nx, ny, nz, 0, nx, 0, nx + 1}, x0, x1, combos, numid, ncombos);
+}
+
+int gpb_ids_scan_slab(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz,
+                      int solid_x0, int solid_nx, int id_x0, int id_nx, int x0, int x1, gpb_idcombo_t *combos, int max_combos, int *ncombos)
+{
+    if (!solid || !rigidE || !rigidH || !ID || !combos || !ncombos || nx < 1 || ny < 1 || nz < 1 || x0 < 0 || x1 > nx + 1 || x1 < x0) return 1;
+    const Grid g{solid, rigidE, rigidH, ID, nx, ny, nz, solid_x0, solid_nx, id_x0, id_nx};
+    if (solid_x0 < 0 || solid_nx < 1 || solid_x0 + solid_nx > nx || id_x0 < 0 || id_nx < 1 || id_x0 + id_nx > nx + 1 || !g.covers(x0, x1)) return 1;
+    return ids_scan(g, x0, x1, combos, max_combos, ncombos);
+}
+
+int gpb_ids_apply_slab(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz,
+                       int solid_x0, int solid_nx, int id_x0, int id_nx, int x0, int x1, const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos)
+{
+    if (!solid || !rigidE || !rigidH || !ID || (ncombos && (!combos || !numid)) || nx < 1 || ny < 1 || nz < 1 || x0 < 0 || x1 > nx + 1 || x1 < x0) return 1;
+    const Grid g{solid, rigidE, rigidH, ID, nx, ny, nz, solid_x0, solid_nx, id_x0, id_nx};
+    if (solid_x0 < 0 || solid_nx < 1 || solid_x0 + solid_nx > nx || id_x0 < 0 || id_nx < 1 || id_x0 + id_nx > nx + 1 || !g.covers(x0, x1)) return 1;
+    return ids_apply(g, x0, x1, combos, numid, ncombos);
 }
 
 }  // extern "C"

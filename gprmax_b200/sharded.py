@@ -188,6 +188,28 @@ def link_neighbours(solver, rank, world, group=None):
     solver.link(left=infos[rank - 1] if rank > 0 else None, right=infos[rank + 1] if rank < world - 1 else None)
 
 
+def build_id_slab(G, solid, rigidE, rigidH, ID_local, group=None, create_electric_average=None, create_magnetic_average=None):
+    """Sharded host build of the per-edge material IDs (yee_cell_build_ext.pyx:110-257): this rank fills
+    `ID_local` = uint32[6][its node planes][ny+1][nz+1] (as the geometry commands left it: rigid edges set) from ITS slab of the
+    geometry only -- `solid` uint32 / `rigidE` int8[12] / `rigidH` int8[6] holding the cell planes [max(x0 - 1, 0), min(x1, nx))
+    for its node planes [x0, x1) = partition_planes(G.nx, world)[rank].  The distinct material combinations of all ranks are
+    exchanged with all_gather_object and resolved in the reference's order on every rank, so `G.materials` ends identical on
+    all ranks and equal to the single-process build (yee_build.build_slab).  The result goes to `solve_gpu_sharded(G,
+    ID_local=ID_local)` after the material coefficients have been computed from `G.materials`."""
+    import types
+    import torch.distributed as dist
+    from . import yee_build
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    x0, n = partition_planes(G.nx, world)[rank]
+
+    def gather(mine):
+        out = [None] * world
+        dist.all_gather_object(out, mine, group=group)
+        return out
+    slab = types.SimpleNamespace(nx=G.nx, ny=G.ny, nz=G.nz, solid=solid, rigidE=rigidE, rigidH=rigidH, ID=ID_local, materials=G.materials)
+    return yee_build.build_slab(slab, (x0, x0 + n), max(x0 - 1, 0), x0, gather if world > 1 else None, create_electric_average, create_magnetic_average)
+
+
 def solve_gpu_sharded(G, iterations=None, overlap=True, ID_local=None, timing=None, transport=None, results=None):
     """Run `G` sharded over all ranks of the default process group (call under torchrun).
     Returns (rxs, seconds): the R[9][iterations][nrx] receiver array (identical on every rank) and

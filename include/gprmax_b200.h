@@ -246,6 +246,14 @@ int gpb_ids_scan(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigi
                  gpb_idcombo_t *combos, int max_combos, int *ncombos);
 int gpb_ids_apply(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz, int x0, int x1,
                   const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos);
+/* The same two passes for a caller that holds only a slab of the arrays (one rank of a sharded build): solid / rigidE /
+ * rigidH carry the cell planes [solid_x0, solid_x0 + solid_nx) and ID the node planes [id_x0, id_x0 + id_nx) of the nx x ny x nz
+ * domain; x0, x1 and the edges returned in `combos` are global plane indices.  The arrays must cover the node planes [x0, x1)
+ * and the cell planes [x0 - 1, x1) (an edge looks at the cells on both sides of its plane), else 1 is returned. */
+int gpb_ids_scan_slab(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz,
+                      int solid_x0, int solid_nx, int id_x0, int id_nx, int x0, int x1, gpb_idcombo_t *combos, int max_combos, int *ncombos);
+int gpb_ids_apply_slab(const uint32_t *solid, const int8_t *rigidE, const int8_t *rigidH, uint32_t *ID, int nx, int ny, int nz,
+                       int solid_x0, int solid_nx, int id_x0, int id_nx, int x0, int x1, const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos);
 
 /* ---- host-side re-layout for the streaming VTK writers (snapshots.py:128-167, geometry_outputs.py:119-205,
  * geometry_outputs_ext.pyx:81-110), all host cores ----

@@ -169,3 +169,82 @@ def test_halo_protocol_bit_exact_over_gloo(world, oracle_built):
             r = ref['rx{}_{}'.format(n, k)]
             assert not np.isnan(v).any(), (n, k)
             assert np.array_equal(v[:nit], r[:nit]), (n, k)
+
+
+# ---------------------------------------------------------------------------------------- sharded host build of the ID array
+
+class _Mat(object):
+    def __init__(self, numID, ID):
+        self.numID, self.ID = numID, ID
+
+
+def _avg(i, j, k, *args):
+    """Stand-in for the reference's create_electric_average / create_magnetic_average (yee_cell_build_ext.pyx:31-107) with the
+    property this test is about: the number a combination gets depends on the ORDER in which the combinations are resolved."""
+    G, comp, ids = args[-1], args[-2], args[:-2]
+    name = '+'.join(sorted(G.materials[n].ID for n in ids))
+    for m in G.materials:
+        if m.ID == name:
+            G.ID[comp, i, j, k] = m.numID
+            return
+    G.materials.append(_Mat(len(G.materials), name))
+    G.ID[comp, i, j, k] = len(G.materials) - 1
+
+
+def _geometry(nx=37, ny=18, nz=22, seed=4):
+    import types
+    rng = np.random.default_rng(seed)
+    G = types.SimpleNamespace(nx=nx, ny=ny, nz=nz)
+    blocks = rng.integers(0, 5, size=(nx // 3 + 1, ny // 4 + 1, nz // 5 + 1)).astype(np.uint32)     # blocky geometry: runs of equal cells and interfaces
+    G.solid = np.ascontiguousarray(np.repeat(np.repeat(np.repeat(blocks, 3, 0), 4, 1), 5, 2)[:nx, :ny, :nz])
+    G.rigidE = (rng.random((12, nx, ny, nz)) < 0.02).astype(np.int8)
+    G.rigidH = (rng.random((6, nx, ny, nz)) < 0.02).astype(np.int8)
+    G.ID = rng.integers(0, 5, size=(6, nx + 1, ny + 1, nz + 1)).astype(np.uint32)     # what the geometry commands left on rigid edges
+    G.materials = [_Mat(n, 'm{}'.format(n)) for n in range(5)]
+    return G
+
+
+def _build_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    G = _geometry()
+    x0, n = partition_planes(G.nx, world)[rank]
+    x1 = x0 + n
+    s0, s1 = max(x0 - 1, 0), min(x1, G.nx)
+    # this rank holds ONLY its slab (+ the cell plane to the left of its first node plane)
+    from gprmax_b200.sharded import build_id_slab
+    ID_local = np.ascontiguousarray(G.ID[:, x0:x1])
+    ncombos = build_id_slab(G, np.ascontiguousarray(G.solid[s0:s1]), np.ascontiguousarray(G.rigidE[:, s0:s1]), np.ascontiguousarray(G.rigidH[:, s0:s1]),
+                            ID_local, create_electric_average=_avg, create_magnetic_average=_avg)
+    q.put((rank, x0, x1, ID_local, [(m.numID, m.ID) for m in G.materials], ncombos))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_id_build_over_gloo(world):
+    """Every rank builds the ID planes of its slab from its slab of solid / rigid only; the distinct material combinations are
+    exchanged (all_gather_object) and resolved in the global scan order on every rank: the slabs put together equal the
+    single-process build and every rank ends with the same material list."""
+    import torch.multiprocessing as mp
+    from gprmax_b200 import yee_build
+    G = _geometry()
+    yee_build.build_components(G, _avg, _avg)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_build_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    mats = [(m.numID, m.ID) for m in G.materials]
+    assert len(mats) > 5                                        # the geometry does produce averaged materials
+    for rank, x0, x1, ID, mats_r, ncombos in results:
+        assert np.array_equal(ID, G.ID[:, x0:x1]), rank
+        assert mats_r == mats, rank
+        assert ncombos > 0

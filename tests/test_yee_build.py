@@ -62,6 +62,43 @@ def electric(solid, rigidE, ID, G):
     yee_build.apply(G, merged, numid, (0, cut))
     yee_build.apply(G, merged, numid, (cut, G.nx + 1))
     res['same_id_slabs'] = bool(np.array_equal(G.ID, ID_ref))
+    # slab-LOCAL: three "ranks" (threads) that each hold only their x range of solid / rigid / ID (plus the one cell plane to the
+    # left that the edges of their first node plane look at), exchange their distinct combinations and resolve them on their own
+    # copy of the material list (yee_build.build_slab)
+    import copy, threading, types
+    del G.materials[nmat0:]
+    nranks = 1 if G.nx < 3 else 3
+    cuts = [0] + [(G.nx + 1) * r // nranks for r in range(1, nranks)] + [G.nx + 1]
+    slots, barrier = [None] * nranks, threading.Barrier(nranks)
+    slabs = []
+    for r in range(nranks):
+        x0, x1 = cuts[r], cuts[r + 1]
+        s0, s1 = max(x0 - 1, 0), min(x1, G.nx)
+        slabs.append(types.SimpleNamespace(nx=G.nx, ny=G.ny, nz=G.nz, x0=x0, x1=x1, s0=s0,
+                                           solid=np.ascontiguousarray(G.solid[s0:s1]), rigidE=np.ascontiguousarray(G.rigidE[:, s0:s1]),
+                                           rigidH=np.ascontiguousarray(G.rigidH[:, s0:s1]), ID=np.ascontiguousarray(ID0[:, x0:x1]),
+                                           materials=copy.deepcopy(G.materials)))
+    errors = []
+    def rank(r):
+        def gather(mine):
+            slots[r] = mine
+            barrier.wait()
+            return list(slots)
+        try:
+            sl = slabs[r]
+            yee_build.build_slab(sl, (sl.x0, sl.x1), sl.s0, sl.x0, gather if nranks > 1 else None, ref.create_electric_average, ref.create_magnetic_average)
+        except Exception as e:
+            errors.append(repr(e))
+            barrier.abort()
+    threads = [threading.Thread(target=rank, args=(r,)) for r in range(nranks)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    same = not errors
+    for sl in slabs:
+        same = same and bool(np.array_equal(sl.ID, ID_ref[:, sl.x0:sl.x1]))
+        same = same and [(m.numID, m.ID, m.type, float(m.er), float(m.se), float(m.mr), float(m.sm)) for m in sl.materials] == mats_ref
+    res['same_id_slab_local'] = same
+    res['slab_errors'] = errors
     raise Done()
 
 from gprmax_b200 import pml_build
@@ -101,7 +138,7 @@ try:
 except Done:
     pass
 print('RESULT', res)
-assert res['same_id'] and res['same_mats'] and res['same_id_slabs'] and res['same_pml'], res
+assert res['same_id'] and res['same_mats'] and res['same_id_slabs'] and res['same_id_slab_local'] and res['same_pml'], res
 print('YEE_OK')
 '''
 
