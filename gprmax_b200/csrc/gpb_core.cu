@@ -462,7 +462,8 @@ struct Solver : SolverBase {
     int graph_iters = 16;
     bool fuse_begin = true;             // GPB_FUSE_BEGIN=0: the step prologue stays a launch of its own inside the multi-iteration graph
     bool use_pdl = true;                // GPB_PDL=0: no programmatic dependent launches inside the step (gpb_kernels.cuh)
-    bool pdl_on() const { return use_pdl && !linked; }
+    bool host_driven = false;           // advanced through gpb_half_step
+    bool pdl_on() const { return use_pdl && !linked && !host_driven; }
     bool use_graph = true;
     void drop_graphs()
     {
@@ -1885,6 +1886,7 @@ int Solver<R>::half_step(int phase, int part)
     // plane reads H of the ghost plane (sources.py:444-452).
     CK(cudaSetDevice(device));
     if (linked) return fail("this shard is linked to its neighbours: advance it with gpb_run");
+    host_driven = true;   // the caller orders these launches against its own transfers with events: plain launches from now on
     if (!snaps.empty() && !snap_unlinked_ok)
         return fail("a snapshot spans the cut plane at x = %d: link the shards (gpb_link / gpb_create_sharded), host-driven half-steps cannot reach the neighbour's planes",
                     x_start + nplanes);
