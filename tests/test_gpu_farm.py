@@ -110,3 +110,47 @@ def test_dropin_command_line_with_the_reference_front_end(tmp_path):
         got, ref = out['data']['/rxs/rx1/' + c], golden['rx0_' + c]
         scale = np.abs(ref).max()
         assert scale > 0 and np.abs(got - ref).max() <= 1e-4 * scale, c
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'gprMax')), reason='baseline/_ref not installed')
+def test_command_line_snapshots_and_geometry_views_on_the_gpu(tmp_path):
+    """`python -m gprmax_b200 model.in -gpu` with `#snapshot` and `#geometry_view` commands: the device snapshots reach the
+    streaming writer as component arrays (solver.store_results -> vtk_writers.write_vtk_imagedata).  Against the same command
+    on the reference's CPU solver with the reference's own writers: geometry files byte-identical, snapshot files identical in
+    layout and within float32 tolerance in the field values."""
+    from test_vtk_writers import MODEL
+    files = {}
+    for mode in ('gpu', 'cpu'):
+        d = tmp_path / mode
+        d.mkdir()
+        (d / 'model.in').write_text(MODEL)
+        env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS='4')
+        if mode == 'cpu':
+            env['GPRMAX_B200_REF_WRITERS'] = '1'
+        r = subprocess.run([sys.executable, '-m', 'gprmax_b200', str(d / 'model.in')] + (['-gpu'] if mode == 'gpu' else []), stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, universal_newlines=True, timeout=600, cwd=str(d), env=env)
+        assert r.returncode == 0, r.stdout[-3000:]
+        assert ('GPU solving using' in r.stdout) == (mode == 'gpu')
+        found = {}
+        for base, _, names in os.walk(str(d)):
+            for n in names:
+                if n.endswith(('.vti', '.vtp')):
+                    with open(os.path.join(base, n), 'rb') as f:
+                        found[os.path.relpath(os.path.join(base, n), str(d))] = f.read()
+        files[mode] = found
+    assert sorted(files['gpu']) == sorted(files['cpu']) and len(files['gpu']) == 5
+    for name, ref in files['cpu'].items():
+        got = files['gpu'][name]
+        if 'snap' not in name:
+            assert got == ref, name
+            continue
+        assert len(got) == len(ref), name
+        start = ref.index(b'<AppendedData encoding="raw">\n_') + len(b'<AppendedData encoding="raw">\n_')
+        assert got[:start] == ref[:start], name
+        n = int(np.frombuffer(ref[start:start + 4], dtype=np.uint32)[0])
+        for off in (start, start + 4 + n):
+            assert got[off:off + 4] == ref[off:off + 4]
+            a = np.frombuffer(got[off + 4:off + 4 + n], dtype=np.float32)
+            b = np.frombuffer(ref[off + 4:off + 4 + n], dtype=np.float32)
+            assert np.abs(b).max() > 0
+            assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max(), (name, off)
