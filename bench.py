@@ -32,6 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+PUBLISHED_300_F32 = 5777.0  # Mcells/s the reference publishes for bench_300x300x300.in (Tesla V100, PyCUDA solver)
 B_ALG_FP32 = 96.0  # algorithmic bytes per cell per time step, non-dispersive fp32 with uint32 IDs
 
 
@@ -369,10 +370,13 @@ def run_single_gpu(args):
 
     line = {
         'metric': 'FDTD throughput', 'value': value, 'unit': 'Mcells/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+        'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        # the reference's published figure for this metric on this model (300^3, float32) -- other hardware
+        'vs_baseline': (value / PUBLISHED_300_F32) if (N == 300 and not f64) else None, 'dtype': args.dtype, 'data': 'synthetic',
         'config': {'workload': 'tests/benchmarking/bench_{0}x{0}x{0}.in: {0}^3 free space, Hertzian dipole, 1 rx, 10-cell HORIPML x6, {1}'.format(N, 'float64' if f64 else 'float32'),
                    'cells': cells, 'iterations_per_step': its, 'l2': 'working set {:.0f} MB >> 126 MB L2 (no flush needed)'.format(mem / 1e6),
-                   'gpu': G.gpu.name, 'alg_bytes_per_cell_step': b_alg, 'model_built_by': model_source, 'kernels': kpath},
+                   'gpu': G.gpu.name, 'alg_bytes_per_cell_step': b_alg, 'model_built_by': model_source, 'kernels': kpath,
+                   'vs_baseline_is': '{} Mcells/s, 300^3 float32 on an NVIDIA Tesla V100 with the reference PyCUDA solver (BASELINE.md; tests/benchmarking/results/gpu/NVIDIA.png)'.format(PUBLISHED_300_F32)},
         'roofline': roof, 'cpu_baseline': cpu, 'parity': parity, 'weak_scaling_baseline': wsb,
         'e2e': {'value': e2e_value, 'unit': 'Mcells/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'call': 'gprmax_b200.solve_gpu(1, 1, G) from host arrays', 'seconds_per_call': [round(t, 4) for t in e2e_t], 'statistic': 'median'},
