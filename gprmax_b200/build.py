@@ -2,7 +2,8 @@
 
     python -m gprmax_b200.build [--force] [--verbose]
 
-Translation units: gpb_core.cu (C ABI, host logic, register-vectorised and scalar kernels) and gpb_tma_inst.cu once per
+Translation units: gpb_core.cu (C ABI, host logic, register-vectorised and scalar kernels), the host-only gpb_idbuild.cpp and
+gpb_vtkio.cpp (ID build, VTK re-ordering) and gpb_tma_inst.cu once per
 (float type, PML variant) -- the TMA-staged kernels are specialised on the PML formulation and order, and the eight
 variants compile in parallel.  Objects go to build/obj; the .so is git-ignored but travels to the GPU box with the
 source snapshot.
