@@ -86,3 +86,20 @@ def test_committed_extraction_matches_the_reference_files():
     for k, v in fresh.items():
         assert np.array_equal(np.asarray(v), shipped[k]), k
     assert sorted({k.split('/')[0] for k in fresh}) == sorted(MODELS)
+
+
+def test_analytic_hertzian_dipole_known_answer():
+    """The reference's analytical KAT (tests/analytical_solutions.py:26-158, model hertzian_dipole_fs_analytical = the
+    hertzian_dipole_fs fixture): a second-order FDTD grid at 20 cells from the source reproduces the analytic dipole fields to
+    0.5 % (Ex, Ey), 1.1 % (Ez) and 2.2 % (Hx, Hy: the analytic H is evaluated at the E time points, half a step off) of peak;
+    Hz is zero.  Fixture written by tests/golden/make_analytic.py with the reference's own function."""
+    from gprmax_b200.model_io import load_model
+    z = np.load(os.path.join(GOLDEN, 'hertzian_dipole_fs_analytic.npz'))
+    G, golden = load_model(golden_path('hertzian_dipole_fs', 'f32'))
+    assert int(z['iterations']) == G.iterations and float(z['dt']) == G.dt
+    fields = z['fields']
+    for n, (comp, tol) in enumerate((('Ex', 1e-2), ('Ey', 1e-2), ('Ez', 2e-2), ('Hx', 4e-2), ('Hy', 4e-2))):
+        a, b = fields[:, n], np.asarray(golden['rx0_' + comp], dtype=np.float64)
+        assert np.abs(a - b).max() <= tol * np.abs(a).max(), comp
+    assert np.abs(fields[:, 5]).max() == 0
+    assert np.abs(golden['rx0_Hz']).max() <= 2e-3 * np.abs(golden['rx0_Hx']).max()
