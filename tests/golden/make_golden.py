@@ -77,6 +77,13 @@ for form in ('HORIPML', 'MRIPML'):
 #rx: 0.003 0.004 0.003
 """.format(form=form, cfs=cfs))
 
+# --- the reference's own PML test models (tests/models_pmls/pml_3D_pec_plate: the elongated thin PEC plate of the PML
+#     literature, 51 x 126 x 26 cells, receiver 3 cells from the PML): CFS with alpha and kappa > 1, 'reverse' scaling profiles,
+#     two CFS per PML, a reduced time step (#time_step_stability_factor), #python blocks.  Shortened from 2100 to 700 iterations
+#     (the wave runs along the 100-cell plate and back in ~350).
+for _v, _f in (('CFS', 'CFS-PML'), ('HORIPML_2', 'HORIPML-2'), ('MRIPML_2', 'MRIPML-2')):
+    ref_file('pec_plate_' + _v, 'tests/models_pmls/pml_3D_pec_plate/pml_3D_pec_plate_{}.in'.format(_f), replace={'#time_window: 2100': '#time_window: 700'})
+
 # --- sources: resistive + hard voltage source, magnetic dipole, start/stop gating, Ix/Iy/Iz outputs
 inline('sources_mixed', _BOX.format(title='mixed sources') + """#material: 3 0.005 1.5 0.1 stuff
 #box: 0.010 0.008 0.006 0.030 0.026 0.020 stuff
