@@ -17,6 +17,9 @@ what changes is how they are produced:
   offsets are one `arange` instead of a Python loop with one `struct.pack` and one progress-bar update per line
   (geometry_outputs.py:266-268).
 
+* an appended array of 4 GiB or more (a `.vti` view of more than 1.07 G cells, a snapshot of more than 358 M cells) gets 64-bit
+  block headers (`header_type="UInt64"`); the reference's `pack('I', ...)` fails there.
+
 `install()` patches the two methods on the reference's classes (done by `gprmax_b200.dropin.install()`).
 """
 import ctypes as C
@@ -28,6 +31,17 @@ from . import _lib
 from .exceptions import GeneralError
 
 BLOCK_BYTES = 64 << 20   # size of the streaming buffer
+WIDE_HEADER_FROM = 1 << 32   # an appended array of this many bytes or more needs 64-bit block headers (see _block_header)
+
+
+def _block_header(sizes):
+    """Every appended array is preceded by its byte count.  The reference writes it as UInt32 (`pack('I', ...)`: an array of 4 GiB
+    or more -- a `.vti` view of more than 1.07 G cells, a snapshot of more than 358 M cells -- ends in a struct.error).  Below that
+    limit the files are the reference's byte for byte; above it the count is written as UInt64 and the file says so
+    (`header_type="UInt64"`, VTK XML format 1.0).  Returns (struct format, header bytes, attribute text for <VTKFile>)."""
+    if max(sizes) >= WIDE_HEADER_FROM:
+        return 'Q', 8, ' header_type="UInt64"'
+    return 'I', 4, ''
 
 
 def transpose(arrays, start, count, step):
@@ -85,11 +99,12 @@ def write_vtk_imagedata(self, pbar, G):
     from gprMax.snapshots import Snapshot
     from gprMax.utilities import round_value
     itemsize = np.dtype(_floattype()).itemsize
-    hfield_offset = 3 * itemsize * self.ncells + np.dtype(np.uint32).itemsize
+    hfmt, hbytes, hattr = _block_header([self.datasizefield])
+    hfield_offset = 3 * itemsize * self.ncells + hbytes
     ext = (self.xs, round_value(self.xf / self.dx), self.ys, round_value(self.yf / self.dy), self.zs, round_value(self.zf / self.dz))
     with open(self.filename, 'wb') as f:
         f.write('<?xml version="1.0"?>\n'.encode('utf-8'))
-        f.write('<VTKFile type="ImageData" version="1.0" byte_order="{}">\n'.format(Snapshot.byteorder).encode('utf-8'))
+        f.write('<VTKFile type="ImageData" version="1.0" byte_order="{}"{}>\n'.format(Snapshot.byteorder, hattr).encode('utf-8'))
         f.write('<ImageData WholeExtent="{} {} {} {} {} {}" Origin="0 0 0" Spacing="{:.3} {:.3} {:.3}">\n'.format(*ext, self.dx * G.dx, self.dy * G.dy, self.dz * G.dz).encode('utf-8'))
         f.write('<Piece Extent="{} {} {} {} {} {}">\n'.format(*ext).encode('utf-8'))
         f.write('<CellData Vectors="E-field H-field">\n'.encode('utf-8'))
@@ -98,7 +113,7 @@ def write_vtk_imagedata(self, pbar, G):
         f.write('</CellData>\n</Piece>\n</ImageData>\n<AppendedData encoding="raw">\n_'.encode('utf-8'))
         fields = getattr(self, 'fields', None)
         for n, name in enumerate(('electric', 'magnetic')):
-            f.write(pack('I', self.datasizefield))
+            f.write(pack(hfmt, self.datasizefield))
             pbar.update(n=4)
             if fields is not None:
                 comps = fields[3 * n:3 * n + 3]
@@ -162,13 +177,14 @@ def _write_vti(self, G, pbar):
     rx_points = [(r.xcoord, r.ycoord, r.zcoord, index + 1) for index, r in enumerate(G.rxs)]
     pml_boxes = [(p.xs, p.xf, p.ys, p.yf, p.zs, p.zf) for p in G.pmls]
     u32 = np.dtype(np.uint32).itemsize
-    vtk_srcs_pml_offset = u32 * ncells + u32
-    vtk_rxs_offset = u32 * ncells + u32 + ncells + u32
+    hfmt, hbytes, hattr = _block_header([u32 * ncells])
+    vtk_srcs_pml_offset = u32 * ncells + hbytes
+    vtk_rxs_offset = u32 * ncells + hbytes + ncells + hbytes
     spacing = (self.dx * G.dx, self.dy * G.dy, self.dz * G.dz)
     ext = (self.vtk_xscells, self.vtk_xfcells, self.vtk_yscells, self.vtk_yfcells, self.vtk_zscells, self.vtk_zfcells)
     with open(self.filename, 'wb') as f:
         f.write('<?xml version="1.0"?>\n'.encode('utf-8'))
-        f.write('<VTKFile type="ImageData" version="1.0" byte_order="{}">\n'.format(GeometryView.byteorder).encode('utf-8'))
+        f.write('<VTKFile type="ImageData" version="1.0" byte_order="{}"{}>\n'.format(GeometryView.byteorder, hattr).encode('utf-8'))
         f.write('<ImageData WholeExtent="{} {} {} {} {} {}" Origin="0 0 0" Spacing="{:.3} {:.3} {:.3}">\n'.format(*ext, *spacing).encode('utf-8'))
         f.write('<Piece Extent="{} {} {} {} {} {}">\n'.format(*ext).encode('utf-8'))
         f.write('<CellData Scalars="Material">\n'.encode('utf-8'))
@@ -179,7 +195,7 @@ def _write_vti(self, G, pbar):
         f.write('</Piece>\n</ImageData>\n<AppendedData encoding="raw">\n_'.encode('utf-8'))
 
         # Material: G.solid sampled and re-ordered, a few z planes at a time
-        f.write(pack('I', u32 * ncells))
+        f.write(pack(hfmt, u32 * ncells))
         pbar.update(n=4)
         for k0, kn in _kblocks(nzs, u32 * nxs * nys):
             block = transpose([G.solid], (self.xs, self.ys, self.zs + k0 * self.dz), (nxs, nys, kn), (self.dx, self.dy, self.dz))
@@ -187,7 +203,7 @@ def _write_vti(self, G, pbar):
             pbar.update(n=block.nbytes)
         # Sources_PML (0 not set, 1 PML, sources from 2) and Receivers (from 1)
         for boxes, points in ((pml_boxes, src_points), ([], rx_points)):
-            f.write(pack('I', ncells))
+            f.write(pack(hfmt, ncells))
             pbar.update(n=4)
             for k0, kn in _kblocks(nzs, nxs * nys):
                 block = np.zeros((kn, nys, nxs), dtype=np.int8)

@@ -219,3 +219,45 @@ def test_command_line_writes_identical_files(tmp_path):
     assert sorted(outs['new']) == sorted(outs['ref']) and len(outs['new']) == 5, sorted(outs['new'])
     for name in outs['ref']:
         assert outs['new'][name] == outs['ref'][name], name
+
+
+@needs_ref
+def test_wide_block_headers_beyond_4_gib(tmp_path, monkeypatch):
+    """An appended array of 4 GiB or more cannot be described by the reference's UInt32 byte count (its writer ends in a
+    struct.error); the streaming writers switch to `header_type="UInt64"` there.  Forced on a small view: same payload, 8-byte
+    counts, offsets that account for them."""
+    import baseline
+    baseline.use_reference()
+    from gprMax.geometry_outputs import GeometryView
+    from gprMax.snapshots import Snapshot
+    from gprMax.constants import floattype
+    G = _grid(24, 20, 28)
+    narrow, wide = {}, {}
+    for store, limit in ((narrow, 1 << 32), (wide, 0)):
+        monkeypatch.setattr(vtk_writers, 'WIDE_HEADER_FROM', limit)
+        v = GeometryView(0, 0, 0, 24, 20, 28, 2, 2, 2, 'view', '.vti')
+        v.filename = str(tmp_path / 'v.vti')
+        vtk_writers.write_vtk(v, G, Bar())
+        store['view'] = open(v.filename, 'rb').read()
+        s = Snapshot(0, 0, 0, 24, 20, 28, 1, 1, 1, 5, 'snap')
+        s.filename = str(tmp_path / 's.vti')
+        rng = np.random.default_rng(8)
+        s.fields = [rng.standard_normal((s.nx, s.ny, s.nz)).astype(floattype) for _ in range(6)]
+        s.electric = s.magnetic = None
+        vtk_writers.write_vtk_imagedata(s, Bar(), G)
+        store['snap'] = open(s.filename, 'rb').read()
+    mark = b'<AppendedData encoding="raw">\n_'
+    for kind, nblocks in (('view', 3), ('snap', 2)):
+        a, b = narrow[kind], wide[kind]
+        assert b'header_type' not in a and b'header_type="UInt64"' in b
+        pa, pb = a.index(mark) + len(mark), b.index(mark) + len(mark)
+        import re
+        offs_a = [int(x) for x in re.findall(rb'offset="(\d+)"', a[:pa])]
+        offs_b = [int(x) for x in re.findall(rb'offset="(\d+)"', b[:pb])]
+        assert len(offs_a) == len(offs_b) == nblocks
+        for n in range(nblocks):
+            size_a = int(np.frombuffer(a[pa + offs_a[n]:pa + offs_a[n] + 4], dtype='<u4')[0])
+            size_b = int(np.frombuffer(b[pb + offs_b[n]:pb + offs_b[n] + 8], dtype='<u8')[0])
+            assert size_a == size_b
+            assert a[pa + offs_a[n] + 4:pa + offs_a[n] + 4 + size_a] == b[pb + offs_b[n] + 8:pb + offs_b[n] + 8 + size_b]
+            assert offs_b[n] == offs_a[n] + 4 * n
