@@ -99,3 +99,15 @@ def test_h5py_standin_round_trip(tmp_path):
     out = standins.read_out(str(tmp_path / 'a.out'))
     assert int(out['attrs']['/']['Iterations']) == 7 and out['attrs']['/rxs/rx1']['Position'].tolist() == [0.1, 0.2, 0.3]
     assert np.array_equal(out['data']['/rxs/rx1/Ez'], np.arange(7, dtype=np.float32)) and '/rxs/rx1/Hx' in out['data']
+
+
+def test_committed_ncu_capture_belongs_to_these_kernel_sources():
+    """bench.py quotes `roofline.traffic` from profiles/traffic.json only while the capture's hash over the device-code files equals
+    the sources being built; a kernel edit without a new `ncu --set full` capture (profiles/ncu_r2.sh) turns the figure into null."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic, source = bench.committed_traffic(300)
+    assert traffic is not None, source
+    assert 1.0e9 < traffic < 1.4e9          # 300^3 half-step: 1.18 GB moved, 1.38 GB algorithmic
