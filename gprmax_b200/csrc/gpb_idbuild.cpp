@@ -14,7 +14,8 @@
 //   host   (Python, gprmax_b200/yee_build.py): for the distinct combinations in that order call the reference's OWN
 //           create_*_average on the recorded edge (a few hundred calls), which yields exactly the material numbering of the
 //           reference;
-//   pass 2 (here, all host cores): write the resolved material on every disagreeing edge.
+//   pass 2 (here, all host cores): write the resolved material on every disagreeing edge (pass 1 marks them in ID, so pass 2
+//           only streams through ID and looks at the cells of the marked edges again).
 // The resulting ID array is bit-identical with the reference's (tests/test_yee_build.py).
 #include "../../include/gprmax_b200.h"
 
@@ -124,9 +125,58 @@ void parallel_planes(int x0, int x1, F f)
 
 extern "C" {
 
+// Row-wise form of Grid::rigid / Grid::around: for one (component, i, j) the taps are pointers to the k rows of the rigid and
+// solid arrays plus a k offset (0 or -1), so the inner loop over k is a handful of byte / word loads per edge.
+struct Row {
+    const int8_t *r[4];      // rigid taps (magnetic components have two: they are listed twice)
+    const uint32_t *s[4];    // solid taps (likewise)
+    int rk[4], sk[4];        // k offsets of the taps
+    uint32_t *id;
+    int nid;
+    bool rigid(int k) const { return (r[0][k + rk[0]] | r[1][k + rk[1]] | r[2][k + rk[2]] | r[3][k + rk[3]]) != 0; }
+    uint32_t cell(int t, int k) const { return s[t][k + sk[t]]; }
+};
+
+// (array 0 = rigidE, 1 = rigidH; q; di, dj, dk) and (di, dj, dk): the same taps as Grid::rigid and Grid::around
+const int kRigidTap[6][4][4] = {
+    {{0, 0, 0, 0}, {1, 0, -1, 0}, {3, 0, 0, -1}, {2, 0, -1, -1}},
+    {{4, 0, 0, 0}, {7, -1, 0, 0}, {5, 0, 0, -1}, {6, -1, 0, -1}},
+    {{8, 0, 0, 0}, {9, -1, 0, 0}, {11, 0, -1, 0}, {10, -1, -1, 0}},
+    {{0, 0, 0, 0}, {1, -1, 0, 0}, {0, 0, 0, 0}, {1, -1, 0, 0}},
+    {{2, 0, 0, 0}, {3, 0, -1, 0}, {2, 0, 0, 0}, {3, 0, -1, 0}},
+    {{4, 0, 0, 0}, {5, 0, 0, -1}, {4, 0, 0, 0}, {5, 0, 0, -1}}};
+const int kSolidTap[6][4][3] = {
+    {{0, 0, 0}, {0, -1, 0}, {0, -1, -1}, {0, 0, -1}},
+    {{0, 0, 0}, {-1, 0, 0}, {-1, 0, -1}, {0, 0, -1}},
+    {{0, 0, 0}, {-1, 0, 0}, {-1, -1, 0}, {0, -1, 0}},
+    {{0, 0, 0}, {-1, 0, 0}, {0, 0, 0}, {-1, 0, 0}},
+    {{0, 0, 0}, {0, -1, 0}, {0, 0, 0}, {0, -1, 0}},
+    {{0, 0, 0}, {0, 0, -1}, {0, 0, 0}, {0, 0, -1}}};
+
+inline Row row_of(const Grid &g, int comp, int i, int j)
+{
+    Row w;
+    const size_t cells = (size_t)g.snx * g.ny * g.nz;
+    for (int t = 0; t < 4; ++t) {
+        const int *rt = kRigidTap[comp][t];
+        const int8_t *base = comp < 3 ? g.rigidE : g.rigidH;
+        // (a k offset of -1 belongs to components whose loops start at k = 1)
+        w.r[t] = base + (size_t)rt[0] * cells + ((size_t)(i + rt[1] - g.sx0) * g.ny + (j + rt[2])) * g.nz;
+        w.rk[t] = rt[3];
+        const int *st = kSolidTap[comp][t];
+        w.s[t] = g.solid + ((size_t)(i + st[0] - g.sx0) * g.ny + (j + st[1])) * g.nz;
+        w.sk[t] = st[2];
+    }
+    w.id = g.ID + (((size_t)comp * g.inx + (i - g.ix0)) * (g.ny + 1) + j) * (g.nz + 1);
+    w.nid = comp < 3 ? 4 : 2;
+    return w;
+}
+
+// An edge whose surrounding cells disagree is marked in ID between the two passes (material numbers stay far below this)
+constexpr uint32_t kPending = 0xffffffffu;
+
 static int ids_scan(const Grid &g, int x0, int x1, gpb_idcombo_t *combos, int max_combos, int *ncombos)
 {
-    uint32_t *ID = g.ID;
     const int nt = std::max(1, std::min(host_threads(), std::max(1, x1 - x0)));
     std::vector<std::map<Key, Pos>> found(nt);
     parallel_planes(x0, x1, [&](int t, int a, int b) {
@@ -135,24 +185,31 @@ static int ids_scan(const Grid &g, int x0, int x1, gpb_idcombo_t *combos, int ma
         for (int comp = 0; comp < 6; ++comp) {
             int lo[3], hi[3];
             ranges(g, comp, lo, hi);
-            const int nid = comp < 3 ? 4 : 2;
             for (int i = std::max(a, lo[0]); i < std::min(b, hi[0]); ++i)
-                for (int j = lo[1]; j < hi[1]; ++j)
+                for (int j = lo[1]; j < hi[1]; ++j) {
+                    const Row w = row_of(g, comp, i, j);
+                    // branch-free sweep of the row: agreeing edges get their material, disagreeing ones the mark, rigid ones keep
+                    // what they have; almost every row ends here
+                    unsigned any_pending = 0;
                     for (int k = lo[2]; k < hi[2]; ++k) {
-                        if (g.rigid(comp, i, j, k)) continue;
-                        uint32_t id[4];
-                        g.around(comp, i, j, k, id);
-                        bool same = id[0] == id[1];
-                        if (nid == 4) same = same && id[0] == id[2] && id[0] == id[3];
-                        if (same) {
-                            ID[g.node(comp, i, j, k)] = id[0];
-                            continue;
-                        }
+                        const uint32_t c0 = w.cell(0, k), c1 = w.cell(1, k), c2 = w.cell(2, k), c3 = w.cell(3, k);
+                        const unsigned same = (unsigned)(c0 == c1) & (unsigned)(c0 == c2) & (unsigned)(c0 == c3);
+                        const unsigned rig = w.rigid(k) ? 1u : 0u;
+                        const uint32_t v = same ? c0 : kPending;
+                        w.id[k] = rig ? w.id[k] : v;
+                        any_pending |= (rig ^ 1u) & (same ^ 1u);
+                    }
+                    if (!any_pending) continue;
+                    for (int k = lo[2]; k < hi[2]; ++k) {
+                        if (w.id[k] != kPending || w.rigid(k)) continue;
+                        const uint32_t c0 = w.cell(0, k), c1 = w.cell(1, k), c2 = w.cell(2, k), c3 = w.cell(3, k);
+                        const uint32_t id[4] = {c0, c1, w.nid == 4 ? c2 : 0u, w.nid == 4 ? c3 : 0u};
                         if (last.comp == comp && !memcmp(last.id, id, sizeof id)) continue;
                         last.comp = comp;
                         memcpy(last.id, id, sizeof id);
                         mine.insert({last, Pos{i, j, k}});   // keeps the first (scan order inside this thread's planes)
                     }
+                }
         }
     });
     // threads own increasing plane ranges, so the first thread that met a combination met it first in scan order
@@ -177,7 +234,6 @@ static int ids_scan(const Grid &g, int x0, int x1, gpb_idcombo_t *combos, int ma
 
 static int ids_apply(const Grid &g, int x0, int x1, const gpb_idcombo_t *combos, const uint32_t *numid, int ncombos)
 {
-    uint32_t *ID = g.ID;
     std::map<Key, uint32_t> table;
     for (int q = 0; q < ncombos; ++q) {
         Key k{combos[q].comp, {combos[q].id[0], combos[q].id[1], combos[q].id[2], combos[q].id[3]}};
@@ -190,16 +246,16 @@ static int ids_apply(const Grid &g, int x0, int x1, const gpb_idcombo_t *combos,
         for (int comp = 0; comp < 6; ++comp) {
             int lo[3], hi[3];
             ranges(g, comp, lo, hi);
-            const int nid = comp < 3 ? 4 : 2;
             for (int i = std::max(a, lo[0]); i < std::min(b, hi[0]); ++i)
-                for (int j = lo[1]; j < hi[1]; ++j)
+                for (int j = lo[1]; j < hi[1]; ++j) {
+                    const Row w = row_of(g, comp, i, j);
+                    unsigned any_pending = 0;
+                    for (int k = lo[2]; k < hi[2]; ++k) any_pending |= (unsigned)(w.id[k] == kPending);
+                    if (!any_pending) continue;
                     for (int k = lo[2]; k < hi[2]; ++k) {
-                        if (g.rigid(comp, i, j, k)) continue;
-                        uint32_t id[4];
-                        g.around(comp, i, j, k, id);
-                        bool same = id[0] == id[1];
-                        if (nid == 4) same = same && id[0] == id[2] && id[0] == id[3];
-                        if (same) continue;
+                        if (w.id[k] != kPending) continue;   // only the edges pass 1 marked look at their cells again
+                        if (w.rigid(k)) continue;
+                        const uint32_t id[4] = {w.cell(0, k), w.cell(1, k), w.nid == 4 ? w.cell(2, k) : 0u, w.nid == 4 ? w.cell(3, k) : 0u};
                         if (!(last.comp == comp && !memcmp(last.id, id, sizeof id))) {
                             last.comp = comp;
                             memcpy(last.id, id, sizeof id);
@@ -207,8 +263,9 @@ static int ids_apply(const Grid &g, int x0, int x1, const gpb_idcombo_t *combos,
                             if (it == table.end()) { __atomic_store_n(&missing, 1, __ATOMIC_RELAXED); last.comp = -1; continue; }
                             last_num = it->second;
                         }
-                        ID[g.node(comp, i, j, k)] = last_num;
+                        w.id[k] = last_num;
                     }
+                }
         }
     });
     return missing ? 3 : 0;

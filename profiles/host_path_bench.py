@@ -29,7 +29,7 @@ def main():
             if mode == 'reference_rows':
                 env.update(GPRMAX_B200_REF_BUILD='1', GPRMAX_B200_REF_WRITERS='1')
             best = None
-            for rep in range(2):
+            for rep in range(3):
                 t0 = time.perf_counter()
                 r = subprocess.run([sys.executable, '-m', 'gprmax_b200', 'model.in', '--geometry-only'], cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
                 t = time.perf_counter() - t0
